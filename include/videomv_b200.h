@@ -1,0 +1,153 @@
+/*
+ * videomv_b200 -- C ABI of the B200-native (sm_100a) kernels behind the VideoMV video-UNet forward.
+ *
+ * The reference (alibaba/VideoMV) is 100% Python: its "FFI" for this path is the set of torch library
+ * calls made from tools/modules/unet/{unet_t2v.py,unet_i2vgen.py,util.py}.  Each entry point below
+ * names the reference call sites it replaces.  Signatures are plain C: raw device pointers, sizes,
+ * strides (in ELEMENTS unless stated), and a CUDA stream handle passed as void*.  No torch types.
+ *
+ * Conventions
+ *   - activations are channels-last fp16:  x[(b*F + f), h, w, c]  ==  row-major [M = B*F*H*W, C]
+ *   - accumulation, normalisation statistics and softmax are fp32 (stats are reduced in fp64)
+ *   - every function returns 0 on success; otherwise vmv_last_error() describes the failure.
+ *     Nothing falls back to a CPU path.
+ *   - all launches go to `stream` and are CUDA-graph capturable.
+ */
+#ifndef VIDEOMV_B200_H_
+#define VIDEOMV_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* vmv_last_error(void);
+/* ABI version of this header; bump on any struct change. */
+int vmv_abi_version(void);
+/* Number of kernels launched through this library since process start (bench.py `gpu_launches`). */
+long long vmv_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Tensor-core contraction:  D[M,N] = epilogue( A (*) W^T )      (tcgen05.mma, TMA-staged, TMEM acc)
+ *
+ * mode VMV_GEMM_LINEAR   A = [A1 | A2]  ([M,K1] and [M,K2] fp16, K-concatenated, K2 may be 0)
+ *      replaces nn.Linear (util.py:223-227,337,351,546,573,667; unet_t2v.py:141-151), nn.Conv1d k=1
+ *      (util.py:1016,1032), nn.Conv2d 1x1 skip (util.py:688) incl. the torch.cat of unet_t2v.py:361.
+ * mode VMV_GEMM_CONV3X3  A = implicit im2col of x[BF,H,W,Cin], 3x3, stride 1, zero pad 1
+ *      (9 shifted 4-D TMA box loads per K block; halo by TMA out-of-bounds zero fill)
+ *      replaces nn.Conv2d 3x3 (util.py:651,677,595; unet_t2v.py:264).
+ * mode VMV_GEMM_TCONV3   A = implicit 3-tap unfold along frames of x[B,F,HW,Cin], zero pad 1 on F
+ *      replaces nn.Conv3d (3,1,1) (util.py:1360-1375) without the NCHW<->NCFHW rearranges.
+ *
+ * W is fp16 [N, Ktot] row-major (K contiguous): Ktot = K1+K2 (linear), 9*Cin ordered (ky,kx,c),
+ * or 3*Cin ordered (kt,c).  See videomv_b200/packing.py for the repack from reference layouts.
+ *
+ * epilogue, in fp32, in this order:  + bias[n]  + rowbias[row / rows_per_group, n]
+ *                                    act (none | SiLU | GEGLU)  + residual[row, n]   -> fp16
+ * GEGLU (util.py:543-550): W rows are packed per N tile as [BN/2 value rows | BN/2 gate rows];
+ * output has N/2 columns: value * gelu_erf(gate).
+ * ---------------------------------------------------------------------------------------------- */
+enum { VMV_GEMM_LINEAR = 0, VMV_GEMM_CONV3X3 = 1, VMV_GEMM_TCONV3 = 2 };
+enum { VMV_ACT_NONE = 0, VMV_ACT_SILU = 1, VMV_ACT_GEGLU = 2 };
+
+typedef struct vmv_gemm_params {
+    int32_t mode;
+    int32_t M, N;               /* output rows / GEMM columns (GEGLU writes N/2 columns) */
+    int32_t K1, K2;             /* linear: K of A1, A2.  conv modes: K1 = Cin, K2 = 0 */
+    const void* A1; int64_t lda1;   /* fp16; lda = row (pixel) stride in elements */
+    const void* A2; int64_t lda2;
+    const void* W;  int64_t ldw;    /* fp16 [N, Ktot] */
+    void* D;        int64_t ldd;    /* fp16 [M, N or N/2] */
+    /* geometry for the conv modes */
+    int32_t B, F, H, Wd;        /* CONV3X3: images = B*F of H x Wd.  TCONV3: B samples, F frames, H*Wd pixels */
+    /* epilogue */
+    const float* bias;          /* fp32 [N] or NULL */
+    const void* rowbias; int64_t ld_rowbias; int32_t rows_per_group;  /* fp16 [M/rows_per_group, N] or NULL */
+    const void* residual; int64_t ldr;                                /* fp16 [M, N_out] or NULL */
+    int32_t act;
+    /* tuning (0 = auto) */
+    int32_t block_n;            /* 64, 128, 160 or 256 */
+    int32_t stages;             /* smem pipeline depth */
+    int32_t split_k;            /* >1: K split across CTAs, fp32 partials in workspace, reduced by a 2nd kernel */
+    void* workspace; int64_t workspace_bytes;
+} vmv_gemm_params;
+
+int vmv_gemm(const vmv_gemm_params* p, void* stream);
+/* bytes of workspace vmv_gemm needs for p (0 when split_k <= 1) */
+int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p);
+
+/* ------------------------------------------------------------------------------------------------
+ * GroupNorm(32 groups) over channels-last rows; replaces nn.GroupNorm at util.py:329,649,673,1014,
+ * 1358-1372 and unet_t2v.py:262, plus the following nn.SiLU, plus the torch.cat feeding it.
+ *
+ * The logical input is [x1 | x2] along channels (C2 may be 0).  Rows are split into `nbatch`
+ * consecutive chunks of `rows_per_batch` rows; statistics are per (chunk, group): a chunk is one frame
+ * (4-D GroupNorm) or one whole sample (5-D GroupNorm: statistics span frames, util.py:1358,1014).
+ *   vmv_groupnorm_stats: stats[nbatch*32*2] (fp64 sum, sum of squares); zeroed by the call.
+ *   vmv_groupnorm_apply: out[rows, C1+C2] fp16 = (x-mean)*rstd*gamma+beta, optional SiLU.
+ * ---------------------------------------------------------------------------------------------- */
+int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                        int64_t rows_per_batch, int32_t nbatch, double* stats, void* stream);
+int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                        int64_t rows_per_batch, int32_t nbatch, const double* stats,
+                        const float* gamma, const float* beta, float eps, int32_t silu,
+                        void* out, int64_t ldo, void* stream);
+
+/* LayerNorm over the last dim (eps 1e-5): nn.LayerNorm util.py:528-530.  x,out fp16 [M,C]. */
+int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
+                  float eps, void* out, int64_t ldo, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Fused softmax(q k^T * scale) v, head_dim 64, fp16 in/out, fp32 softmax (online, flash style).
+ * Replaces xformers.ops.memory_efficient_attention + the head split/merge reshapes of util.py:237-268.
+ * Batch index = bo*inner + bi (bo < outer, bi < inner); element offset of token n, head h:
+ *     base + bo*bs_outer + bi*bs_inner + n*row_stride + h*64
+ * K/V batch = (q batch) / kv_group  (kv_group = frames for text cross-attention, else 1).
+ *   spatial self  (util.py:536 attn1 in SpatialTransformer): outer=B*F frames, inner=1, n over H*W
+ *   text cross    (attn2, context [B,77|145,1024] projected once per sample)
+ *   temporal self (attn1+attn2 in TemporalTransformer): outer=B, inner=H*W pixels, n over F frames
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct vmv_attn_params {
+    const void* q; const void* k; const void* v; void* o;     /* fp16 */
+    int32_t outer, inner, heads, nq, nk;
+    int64_t q_bs_outer, q_bs_inner, q_rs;
+    int64_t k_bs_outer, k_bs_inner, k_rs;
+    int64_t v_bs_outer, v_bs_inner, v_rs;
+    int64_t o_bs_outer, o_bs_inner, o_rs;
+    int32_t kv_group;          /* kv outer index = bo / kv_group */
+    float scale;               /* head_dim^-0.5 */
+} vmv_attn_params;
+int vmv_attention(const vmv_attn_params* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Small data-movement / CUDA-core kernels on the path
+ * ---------------------------------------------------------------------------------------------- */
+/* F.interpolate(scale 2, nearest) util.py:604: x[n,H,W,C] -> out[n,2H,2W,C] fp16 */
+int vmv_upsample_nearest2x(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream);
+/* patch gather for the stride-2 3x3 Downsample conv (util.py:749): out[n*(H/2)*(W/2), 9*C] ordered (ky,kx,c) */
+int vmv_im2col_3x3_s2(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream);
+/* input conv (unet_t2v.py:169): x fp32 NCFHW [B,C1,F,H,W] (+ optional second tensor [B,C2,F,H,W], I2V concat
+ * unet_i2vgen.py:384), w fp32 [Cout, C1+C2, 3, 3], bias fp32 -> out fp16 [B*F,H,W,Cout] */
+int vmv_conv3x3_in(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t F, int32_t H,
+                   int32_t W, const float* w, const float* bias, int32_t Cout, void* out, void* stream);
+/* head conv (unet_t2v.py:264-265,368): x fp16 [B*F,H,W,C] (already GN+SiLU), w fp32 [Cout,C,3,3]
+ * -> out fp32 NCFHW [B,Cout,F,H,W] */
+int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, int32_t W, int32_t C, const float* w,
+                    const float* bias, int32_t Cout, float* out, void* stream);
+/* sinusoidal_embedding util.py:177-189: t int64 [B] -> out fp16 [B, dim] = [cos | sin] */
+int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out, void* stream);
+/* e[b*F+f, :] = silu( t_emb[b,:] (+ t_emb2[b,:]) (+ cam_emb[b*F+f,:]) )   (unet_t2v.py:326-335 + the nn.SiLU
+ * that opens every ResBlock.emb_layers, util.py:665).  fp16 in/out. */
+int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, const void* cam_emb, int32_t B, int32_t F,
+                           int32_t E, void* out, void* stream);
+/* classifier-free guidance + DDIM update (diffusion_ddim.py:157-160,193-195,233-243), eta = 0:
+ *   eps = u + s*(y-u);  x0 = c_recip*xt - c_recipm1*eps (clamped if clamp>0);  x_prev = sqrt(a_prev)*x0 + sqrt(1-a_prev)*eps'
+ * all tensors fp32, n elements. coef = {sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac_prev, sqrt_1m_ac_prev, guide_scale} */
+int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef5, int64_t n,
+                      float* x_prev, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDEOMV_B200_H_ */

@@ -1,0 +1,147 @@
+"""Build + load the C-ABI shared library (include/videomv_b200.h) with ctypes.
+
+The library is built IN-TREE (videomv_b200/lib/libvideomv_b200.so) by plain nvcc for sm_100a only.
+There is no fallback: if the library is missing or fails to load, every op raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIBDIR = os.path.join(_HERE, "lib")
+LIBPATH = os.path.join(LIBDIR, "libvideomv_b200.so")
+SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "misc.cu"]
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC"]
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isfile(cand) or cand == "nvcc"):
+            return cand
+    return "nvcc"
+
+
+def _stale() -> bool:
+    if not os.path.isfile(LIBPATH):
+        return True
+    t = os.path.getmtime(LIBPATH)
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(_HERE, "..", "include", "videomv_b200.h")]
+    return any(os.path.getmtime(d) > t for d in deps if os.path.isfile(d))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile every CUDA source for sm_100a and link the shared library. Returns its path."""
+    if not force and not _stale():
+        return LIBPATH
+    os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(objdir, src.replace(".cu", ".o"))
+        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            print(" ".join(cmd))
+        return obj
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        objs = list(ex.map(compile_one, SOURCES))
+    cmd = [nvcc, "-shared", "-o", LIBPATH, *objs, "-lcudart"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    return LIBPATH
+
+
+c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
+
+
+class GemmParams(ctypes.Structure):
+    """Mirror of `vmv_gemm_params` (include/videomv_b200.h)."""
+    _fields_ = [
+        ("mode", c_i32), ("M", c_i32), ("N", c_i32), ("K1", c_i32), ("K2", c_i32),
+        ("A1", c_vp), ("lda1", c_i64), ("A2", c_vp), ("lda2", c_i64),
+        ("W", c_vp), ("ldw", c_i64), ("D", c_vp), ("ldd", c_i64),
+        ("B", c_i32), ("F", c_i32), ("H", c_i32), ("Wd", c_i32),
+        ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
+        ("residual", c_vp), ("ldr", c_i64), ("act", c_i32),
+        ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32),
+        ("workspace", c_vp), ("workspace_bytes", c_i64),
+    ]
+
+
+class AttnParams(ctypes.Structure):
+    """Mirror of `vmv_attn_params`."""
+    _fields_ = [
+        ("q", c_vp), ("k", c_vp), ("v", c_vp), ("o", c_vp),
+        ("outer", c_i32), ("inner", c_i32), ("heads", c_i32), ("nq", c_i32), ("nk", c_i32),
+        ("q_bs_outer", c_i64), ("q_bs_inner", c_i64), ("q_rs", c_i64),
+        ("k_bs_outer", c_i64), ("k_bs_inner", c_i64), ("k_rs", c_i64),
+        ("v_bs_outer", c_i64), ("v_bs_inner", c_i64), ("v_rs", c_i64),
+        ("o_bs_outer", c_i64), ("o_bs_inner", c_i64), ("o_rs", c_i64),
+        ("kv_group", c_i32), ("scale", c_f32),
+    ]
+
+
+# every symbol include/videomv_b200.h declares: (restype, argtypes)
+SYMBOLS = {
+    "vmv_last_error": (ctypes.c_char_p, []),
+    "vmv_abi_version": (ctypes.c_int, []),
+    "vmv_launch_count": (ctypes.c_longlong, []),
+    "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
+    "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
+    "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
+    "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+                                           c_f32, c_i32, c_vp, c_i64, c_vp]),
+    "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
+    "vmv_attention": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),
+    "vmv_upsample_nearest2x": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "vmv_im2col_3x3_s2": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "vmv_conv3x3_in": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "vmv_conv3x3_out": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "vmv_sinusoidal_embedding": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp]),
+    "vmv_embed_combine_silu": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
+    "vmv_cfg_ddim_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+}
+
+_LIB = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (never build implicitly on a GPU box without nvcc) the shared library; raise loudly if absent."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    if not os.path.isfile(LIBPATH):
+        raise RuntimeError(
+            f"videomv_b200: native library {LIBPATH} is missing. Run `python -c 'import __graft_entry__ as g; g.build()'`"
+            " (nvcc, sm_100a). There is no CPU or PyTorch fallback for the UNet hot path.")
+    L = ctypes.CDLL(LIBPATH)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(L, name)           # AttributeError if the .so does not export a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    if L.vmv_abi_version() != 1:
+        raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
+    _LIB = L
+    return L
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = lib().vmv_last_error().decode(errors="replace")
+        raise RuntimeError(f"videomv_b200 {what} failed (code {rc}): {msg}")
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True))

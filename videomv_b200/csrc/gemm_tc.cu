@@ -1,0 +1,629 @@
+// Tensor-core contraction kernel for the VideoMV UNet: Linear / 1x1 / 3x3 conv / (3,1,1) temporal conv.
+//
+//   D[M,N] = epilogue( A (*) W^T ),   A fp16 (K-major), W fp16 [N,Ktot] (K-major), fp32 accumulate in TMEM.
+//
+// One CTA = one 128 x BN output tile (or one K split of it).  Warp roles (192 threads):
+//   warp 0      TMA producer: per K block (64 halfs = one 128B swizzle atom) one A box + one W box
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer (4 x K=16 MMAs per K block)
+//   warps 2..5  epilogue: tcgen05.ld (32 lanes x 16 cols) -> fp32 epilogue -> fp16 16B global stores
+// smem ring of STAGES {A 128x64, W BNx64} tiles, full/empty mbarriers; tcgen05.commit frees a stage.
+//
+// The A operand is never materialised as im2col: for the 3x3 conv each K block is one 4-D TMA box
+// (64 ch, bw, bh, bf) of the channels-last activation shifted by the tap offset, with the halo supplied
+// by TMA out-of-bounds zero fill; the temporal conv shifts the box along the frame axis of a
+// (C, HW, F, B) view.  Box rows land in smem in exactly the (f,h,w) row order of the output tile, so the
+// 128B-swizzled tile is a legal K-major UMMA operand as is.
+#include "common.cuh"
+#include "../../include/videomv_b200.h"
+
+#include <mutex>
+#include <string.h>
+
+namespace vmv {
+
+void count_launch(int n = 1);
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
+
+struct GemmArgs {
+    int mode, M, N, n_out;
+    int nkb;          // total K blocks
+    int nkb1;         // linear: K blocks in source 1
+    int cblocks;      // conv: K blocks per tap (= Cin/64)
+    int kb_per_split; // K blocks per split (== nkb when no split)
+    // conv geometry (tile decode)
+    int F, H, W, HW;
+    int bw, bh, bf, bp;
+    int tiles_w, tiles_h;          // CONV3X3
+    int tiles_per_sample, tiles_p; // TCONV3
+    // epilogue
+    __half* D;
+    long long ldd;
+    const float* bias;
+    const __half* rowbias;
+    long long ld_rowbias;
+    int rows_per_group;
+    const __half* residual;
+    long long ldr;
+    int act;
+    float* partial;   // split-K: fp32 [splits, M, N]
+};
+
+// Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
+__device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int mt, int r) {
+    if (a.mode == VMV_GEMM_LINEAR) {
+        long long g = (long long)mt * BM + r;
+        return g < a.M ? g : -1;
+    } else if (a.mode == VMV_GEMM_CONV3X3) {
+        int tw = mt % a.tiles_w;
+        int th = (mt / a.tiles_w) % a.tiles_h;
+        int tf = mt / (a.tiles_w * a.tiles_h);
+        int rw = r % a.bw;
+        int rh = (r / a.bw) % a.bh;
+        int rf = r / (a.bw * a.bh);
+        long long f = (long long)tf * a.bf + rf;
+        long long g = (f * a.H + (th * a.bh + rh)) * a.W + (tw * a.bw + rw);
+        return g < a.M ? g : -1;
+    } else {
+        int b = mt / a.tiles_per_sample;
+        int ts = mt % a.tiles_per_sample;
+        int tp = ts % a.tiles_p;
+        int tf = ts / a.tiles_p;
+        int rp = r % a.bp;
+        int rf = r / a.bp;
+        int f = tf * a.bf + rf;
+        if (f >= a.F) return -1;
+        return ((long long)b * a.F + f) * a.HW + (tp * a.bp + rp);
+    }
+}
+
+template <int BN, int STAGES>
+struct SmemLayout {
+    static constexpr int B_STAGE_BYTES = BN * BK * 2;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + (2 * STAGES + 1) * 8 + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;   // slack for manual 1024B alignment
+};
+
+template <int BN>
+struct TmemCols {
+    static constexpr int value = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : BN <= 256 ? 256 : 512;
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+               const __grid_constant__ CUtensorMap tmW, const GemmArgs a) {
+    using L = SmemLayout<BN, STAGES>;
+    constexpr int TCOLS = TmemCols<BN>::value;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const int nt = blockIdx.x;      // N tile
+    const int mt = blockIdx.y;      // M tile
+    const int split = blockIdx.z;
+    const int kb_begin = split * a.kb_per_split;
+    const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
+    const int n0 = nt * BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmW);
+        if (a.nkb1 < a.nkb && a.mode == VMV_GEMM_LINEAR) tma_prefetch_desc(&tmA2);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        mbar_init(tmem_full_bar, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<TCOLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------ TMA producer ------------------------------
+            // tile origin in the coordinates of the A tensor map
+            int c1 = 0, c2 = 0, c3 = 0;
+            if (a.mode == VMV_GEMM_LINEAR) {
+                c1 = mt * BM;
+            } else if (a.mode == VMV_GEMM_CONV3X3) {
+                c1 = (mt % a.tiles_w) * a.bw;
+                c2 = ((mt / a.tiles_w) % a.tiles_h) * a.bh;
+                c3 = (mt / (a.tiles_w * a.tiles_h)) * a.bf;
+            } else {
+                int ts = mt % a.tiles_per_sample;
+                c1 = (ts % a.tiles_p) * a.bp;
+                c2 = (ts / a.tiles_p) * a.bf;
+                c3 = mt / a.tiles_per_sample;
+            }
+            constexpr uint32_t tx_bytes = A_STAGE_BYTES + L::B_STAGE_BYTES;
+            int it = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&empty_bar[s], ph ^ 1);
+                mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                void* sa = smem + L::A_OFF + s * A_STAGE_BYTES;
+                void* sb = smem + L::B_OFF + s * L::B_STAGE_BYTES;
+                if (a.mode == VMV_GEMM_LINEAR) {
+                    if (kb < a.nkb1) tma_load_2d(sa, &tmA1, &full_bar[s], kb * BK, c1);
+                    else tma_load_2d(sa, &tmA2, &full_bar[s], (kb - a.nkb1) * BK, c1);
+                } else if (a.mode == VMV_GEMM_CONV3X3) {
+                    const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+                    const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                    tma_load_4d(sa, &tmA1, &full_bar[s], cb * BK, c1 + dx, c2 + dy, c3);
+                } else {
+                    const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+                    tma_load_4d(sa, &tmA1, &full_bar[s], cb * BK, c1, c2 + tap - 1, c3);
+                }
+                tma_load_2d(sb, &tmW, &full_bar[s], kb * BK, n0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            // ------------------------------ MMA issuer --------------------------------
+            constexpr uint32_t idesc = umma_idesc_f16_f32(BM, BN);
+            int it = 0;
+            for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                const int s = it % STAGES;
+                const uint32_t ph = (it / STAGES) & 1;
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
+                const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + L::B_OFF + s * L::B_STAGE_BYTES));
+#pragma unroll
+                for (int k = 0; k < BK / 16; ++k) {
+                    // advance 16 halfs = 32 bytes inside the 128B swizzle atom: +2 in the (addr>>4) field
+                    umma_f16_ss(tmem_base, adesc + 2 * k, bdesc + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+                }
+                umma_commit(&empty_bar[s]);     // frees the smem stage when these MMAs retire
+            }
+            umma_commit(tmem_full_bar);         // accumulator complete
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------- epilogue ----------------------------------
+        const int q = warp & 3;                 // TMEM lane quarter this warp may access
+        const int r = q * 32 + lane;
+        const long long grow = tile_row_to_global(a, mt, r);
+        const bool valid = grow >= 0;
+        mbar_wait(tmem_full_bar, 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+
+        if (a.partial != nullptr) {
+            // split-K: raw fp32 partial sums, reduced by splitk_finish_kernel
+            float* prow = a.partial + ((long long)split * a.M + (valid ? grow : 0)) * a.N;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                if (n0 + c >= a.N) break;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(trow + c, v);
+                tmem_ld_wait();
+                if (valid) {
+                    float4* dst = reinterpret_cast<float4*>(prow + n0 + c);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+                }
+            }
+        } else if (a.act == VMV_ACT_GEGLU) {
+            constexpr int HB = BN / 2;
+            const int o0 = nt * HB;
+#pragma unroll 1
+            for (int c = 0; c < HB; c += 16) {
+                if (n0 + c >= a.N) break;
+                uint32_t v[16], g[16];
+                tmem_ld_32x32b_x16(trow + c, v);
+                tmem_ld_32x32b_x16(trow + HB + c, g);
+                tmem_ld_wait();
+                if (valid) {
+                    float x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
+                        if (a.bias) {
+                            val += __ldg(a.bias + n0 + c + j);
+                            gate += __ldg(a.bias + n0 + HB + c + j);
+                        }
+                        x[j] = val * gelu_erf_f(gate);
+                    }
+                    if (a.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + o0 + c);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 u = __ldg(rp + h);
+                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = unpack_half2(w[j]);
+                                x[8 * h + 2 * j] += f.x;
+                                x[8 * h + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + o0 + c);
+                    dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                                       pack_half2(x[6], x[7]));
+                    dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
+                                       pack_half2(x[14], x[15]));
+                }
+            }
+        } else {
+            const __half* rb = nullptr;
+            if (a.rowbias && valid) rb = a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 16) {
+                if (n0 + c >= a.N) break;
+                uint32_t v[16];
+                tmem_ld_32x32b_x16(trow + c, v);
+                tmem_ld_wait();
+                if (valid) {
+                    const int n = n0 + c;
+                    float x[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+                    if (a.bias) {
+                        const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float4 b4 = __ldg(bp + j);
+                            x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                        }
+                    }
+                    if (rb) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 u = __ldg(rp + h);
+                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = unpack_half2(w[j]);
+                                x[8 * h + 2 * j] += f.x;
+                                x[8 * h + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    if (a.act == VMV_ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) x[j] = silu_f(x[j]);
+                    }
+                    if (a.residual) {
+                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + n);
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint4 u = __ldg(rp + h);
+                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = unpack_half2(w[j]);
+                                x[8 * h + 2 * j] += f.x;
+                                x[8 * h + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + n);
+                    dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                                       pack_half2(x[6], x[7]));
+                    dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
+                                       pack_half2(x[14], x[15]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// Reduce split-K partials and apply the (non-GEGLU) epilogue.  One thread per 8 output columns.
+__global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int M, int N, GemmArgs a) {
+    const int nvec = N / 8;
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)M * nvec) return;
+    const long long row = idx / nvec;
+    const int n = (int)(idx % nvec) * 8;
+    float x[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) x[j] = 0.f;
+    for (int s = 0; s < splits; ++s) {
+        const float4* p = reinterpret_cast<const float4*>(partial + ((long long)s * M + row) * N + n);
+        float4 u = p[0], w = p[1];
+        x[0] += u.x; x[1] += u.y; x[2] += u.z; x[3] += u.w;
+        x[4] += w.x; x[5] += w.y; x[6] += w.z; x[7] += w.w;
+    }
+    if (a.bias) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += a.bias[n + j];
+    }
+    if (a.rowbias) {
+        const __half* rb = a.rowbias + (row / a.rows_per_group) * a.ld_rowbias + n;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += __half2float(rb[j]);
+    }
+    if (a.act == VMV_ACT_SILU) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+    }
+    if (a.residual) {
+        const __half* rp = a.residual + row * a.ldr + n;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] += __half2float(rp[j]);
+    }
+    uint4 o = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                         pack_half2(x[6], x[7]));
+    *reinterpret_cast<uint4*>(a.D + row * a.ldd + n) = o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+// fp16 tensor map, 128B swizzle, inner box = 64 elements.  dims/strides innermost first; strides in bytes
+// for dims 1..rank-1.
+static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+                    const cuuint32_t* box) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled not available from the driver");
+        return VMV_ERR_CUDA;
+    }
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
+                  "stride0 %llu base %p",
+                  (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0),
+                  (unsigned long long)(rank > 2 ? dims[2] : 0), (unsigned long long)(rank > 3 ? dims[3] : 0), box[0],
+                  rank > 1 ? box[1] : 0, rank > 2 ? box[2] : 0, rank > 3 ? box[3] : 0,
+                  (unsigned long long)(rank > 1 ? strides[0] : 0), base);
+        return VMV_ERR_CUDA;
+    }
+    return VMV_OK;
+}
+
+template <int BN, int STAGES>
+static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
+                           dim3 grid, cudaStream_t st) {
+    using L = SmemLayout<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::DYN_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(e));
+            return VMV_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    gemm_tc_kernel<BN, STAGES><<<grid, 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, a);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_gemm");
+    return VMV_OK;
+}
+
+static int pick_block_n(const vmv_gemm_params* p) {
+    if (p->block_n) return p->block_n;
+    const int N = p->N;
+    if (p->act == VMV_ACT_GEGLU) return (N % 160 == 0) ? 160 : 128;
+    if (N % 160 == 0) return 160;
+    if (N % 128 == 0) return 128;
+    if (N <= 64) return 64;
+    return 128;
+}
+
+struct Plan {
+    GemmArgs a;
+    int bn, stages, splits, m_tiles, n_tiles;
+};
+
+static int make_plan(const vmv_gemm_params* p, Plan* pl) {
+    GemmArgs& a = pl->a;
+    memset(&a, 0, sizeof(a));
+    VMV_CHECK_ARG(p->M > 0 && p->N > 0, "vmv_gemm: M, N must be positive (M=%d N=%d)", p->M, p->N);
+    VMV_CHECK_ARG(p->N % 16 == 0, "vmv_gemm: N=%d must be a multiple of 16", p->N);
+    VMV_CHECK_ARG(p->A1 && p->W && p->D, "vmv_gemm: null A1/W/D");
+    VMV_CHECK_ARG(p->K1 > 0 && p->K1 % BK == 0 && p->K2 % BK == 0,
+                  "vmv_gemm: K1=%d, K2=%d must be multiples of %d", p->K1, p->K2, BK);
+    VMV_CHECK_ARG(p->lda1 % 8 == 0 && p->ldw % 8 == 0 && p->ldd % 8 == 0, "vmv_gemm: leading dims must be multiples of 8");
+    a.mode = p->mode;
+    a.M = p->M;
+    a.N = p->N;
+    a.act = p->act;
+    a.n_out = p->act == VMV_ACT_GEGLU ? p->N / 2 : p->N;
+    a.D = static_cast<__half*>(p->D);
+    a.ldd = p->ldd;
+    a.bias = p->bias;
+    a.rowbias = static_cast<const __half*>(p->rowbias);
+    a.ld_rowbias = p->ld_rowbias;
+    a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1;
+    a.residual = static_cast<const __half*>(p->residual);
+    a.ldr = p->ldr;
+    if (p->rowbias) VMV_CHECK_ARG(p->ld_rowbias % 8 == 0, "vmv_gemm: ld_rowbias must be a multiple of 8");
+    if (p->residual) VMV_CHECK_ARG(p->ldr % 8 == 0, "vmv_gemm: ldr must be a multiple of 8");
+
+    if (p->mode == VMV_GEMM_LINEAR) {
+        if (p->K2 > 0) VMV_CHECK_ARG(p->A2 && p->lda2 % 8 == 0, "vmv_gemm: K2>0 needs A2 with lda2 %% 8 == 0");
+        a.nkb1 = p->K1 / BK;
+        a.nkb = (p->K1 + p->K2) / BK;
+        a.cblocks = a.nkb;
+        pl->m_tiles = (p->M + BM - 1) / BM;
+    } else if (p->mode == VMV_GEMM_CONV3X3) {
+        VMV_CHECK_ARG(p->K2 == 0, "vmv_gemm: conv modes take a single source");
+        const int H = p->H, W = p->Wd, NF = p->B * p->F;
+        VMV_CHECK_ARG(H > 0 && W > 0 && NF > 0 && (long long)NF * H * W == p->M, "vmv_gemm conv3x3: M != B*F*H*W");
+        VMV_CHECK_ARG(W >= 128 ? (W % 128 == 0) : (128 % W == 0), "vmv_gemm conv3x3: W=%d must divide or be a multiple of 128", W);
+        a.bw = W >= 128 ? 128 : W;
+        const int rem = 128 / a.bw;
+        VMV_CHECK_ARG(H >= rem ? (H % rem == 0) : (rem % H == 0), "vmv_gemm conv3x3: H=%d incompatible with 128-row tiles", H);
+        a.bh = H >= rem ? rem : H;
+        a.bf = 128 / (a.bw * a.bh);
+        a.tiles_w = W / a.bw;
+        a.tiles_h = H / a.bh;
+        a.F = NF; a.H = H; a.W = W; a.HW = H * W;
+        a.cblocks = p->K1 / BK;
+        a.nkb = 9 * a.cblocks;
+        a.nkb1 = a.nkb;
+        pl->m_tiles = a.tiles_w * a.tiles_h * ((NF + a.bf - 1) / a.bf);
+    } else if (p->mode == VMV_GEMM_TCONV3) {
+        VMV_CHECK_ARG(p->K2 == 0, "vmv_gemm: conv modes take a single source");
+        const int HW = p->H * p->Wd;
+        VMV_CHECK_ARG(HW > 0 && p->B > 0 && p->F > 0 && (long long)p->B * p->F * HW == p->M, "vmv_gemm tconv3: M != B*F*H*W");
+        VMV_CHECK_ARG(HW >= 128 ? (HW % 128 == 0) : (128 % HW == 0), "vmv_gemm tconv3: H*W=%d must divide or be a multiple of 128", HW);
+        a.bp = HW >= 128 ? 128 : HW;
+        a.bf = 128 / a.bp;
+        a.tiles_p = HW / a.bp;
+        a.tiles_per_sample = a.tiles_p * ((p->F + a.bf - 1) / a.bf);
+        a.F = p->F; a.HW = HW; a.H = p->H; a.W = p->Wd;
+        a.cblocks = p->K1 / BK;
+        a.nkb = 3 * a.cblocks;
+        a.nkb1 = a.nkb;
+        pl->m_tiles = p->B * a.tiles_per_sample;
+    } else {
+        set_error("vmv_gemm: unknown mode %d", p->mode);
+        return VMV_ERR_INVALID;
+    }
+    pl->bn = pick_block_n(p);
+    VMV_CHECK_ARG(pl->bn == 64 || pl->bn == 128 || pl->bn == 160 || pl->bn == 256, "vmv_gemm: block_n=%d unsupported", pl->bn);
+    if (p->act == VMV_ACT_GEGLU)
+        VMV_CHECK_ARG(p->N % pl->bn == 0 && (pl->bn / 2) % 16 == 0, "vmv_gemm: GEGLU needs N %% block_n == 0");
+    pl->n_tiles = (p->N + pl->bn - 1) / pl->bn;
+    pl->splits = p->split_k > 1 ? p->split_k : 1;
+    if (pl->splits > a.nkb) pl->splits = a.nkb;
+    if (p->act == VMV_ACT_GEGLU) pl->splits = 1;
+    a.kb_per_split = (a.nkb + pl->splits - 1) / pl->splits;
+    pl->splits = (a.nkb + a.kb_per_split - 1) / a.kb_per_split;
+    pl->stages = p->stages;
+    return VMV_OK;
+}
+
+}  // namespace vmv
+
+using namespace vmv;
+
+extern "C" int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p) {
+    Plan pl;
+    if (make_plan(p, &pl) != VMV_OK) return -1;
+    if (pl.splits <= 1) return 0;
+    return (int64_t)pl.splits * p->M * p->N * (int64_t)sizeof(float);
+}
+
+extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    Plan pl;
+    int rc = make_plan(p, &pl);
+    if (rc != VMV_OK) return rc;
+    GemmArgs& a = pl.a;
+    const int BN = pl.bn;
+
+    CUtensorMap tA1, tA2, tW;
+    const long long Ktot = p->mode == VMV_GEMM_LINEAR ? (long long)p->K1 + p->K2
+                           : p->mode == VMV_GEMM_CONV3X3 ? 9LL * p->K1 : 3LL * p->K1;
+    VMV_CHECK_ARG(p->ldw >= Ktot, "vmv_gemm: ldw=%lld < Ktot=%lld", (long long)p->ldw, Ktot);
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->N};
+        cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
+        cuuint32_t box[2] = {BK, (cuuint32_t)BN};
+        if ((rc = make_map(&tW, p->W, 2, dims, strides, box)) != VMV_OK) return rc;
+    }
+    if (p->mode == VMV_GEMM_LINEAR) {
+        cuuint64_t dims[2] = {(cuuint64_t)p->K1, (cuuint64_t)p->M};
+        cuuint64_t strides[1] = {(cuuint64_t)p->lda1 * 2};
+        cuuint32_t box[2] = {BK, BM};
+        if ((rc = make_map(&tA1, p->A1, 2, dims, strides, box)) != VMV_OK) return rc;
+        if (p->K2 > 0) {
+            cuuint64_t dims2[2] = {(cuuint64_t)p->K2, (cuuint64_t)p->M};
+            cuuint64_t strides2[1] = {(cuuint64_t)p->lda2 * 2};
+            if ((rc = make_map(&tA2, p->A2, 2, dims2, strides2, box)) != VMV_OK) return rc;
+        } else {
+            tA2 = tA1;
+        }
+    } else if (p->mode == VMV_GEMM_CONV3X3) {
+        const cuuint64_t ld = (cuuint64_t)p->lda1 * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)p->K1, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.F};
+        cuuint64_t strides[3] = {ld, ld * a.W, ld * a.W * a.H};
+        cuuint32_t box[4] = {BK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bf};
+        if ((rc = make_map(&tA1, p->A1, 4, dims, strides, box)) != VMV_OK) return rc;
+        tA2 = tA1;
+    } else {
+        const cuuint64_t ld = (cuuint64_t)p->lda1 * 2;
+        cuuint64_t dims[4] = {(cuuint64_t)p->K1, (cuuint64_t)a.HW, (cuuint64_t)a.F, (cuuint64_t)p->B};
+        cuuint64_t strides[3] = {ld, ld * a.HW, ld * a.HW * a.F};
+        cuuint32_t box[4] = {BK, (cuuint32_t)a.bp, (cuuint32_t)a.bf, 1};
+        if ((rc = make_map(&tA1, p->A1, 4, dims, strides, box)) != VMV_OK) return rc;
+        tA2 = tA1;
+    }
+
+    if (pl.splits > 1) {
+        const int64_t need = (int64_t)pl.splits * p->M * p->N * (int64_t)sizeof(float);
+        VMV_CHECK_ARG(p->workspace && p->workspace_bytes >= need,
+                      "vmv_gemm: split_k=%d needs %lld workspace bytes (have %lld)", pl.splits, (long long)need,
+                      (long long)p->workspace_bytes);
+        a.partial = static_cast<float*>(p->workspace);
+    }
+
+    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+    // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one
+    // CTA's epilogue overlaps the other's main loop.
+    int stages = pl.stages;
+    const int nkb_cta = a.kb_per_split;
+    if (stages == 0) stages = (nkb_cta <= 3) ? 3 : (BN == 256 ? 4 : (BN == 160 ? 3 : 3));
+
+#define VMV_LAUNCH(BN_, ST_) rc = launch_instance<BN_, ST_>(tA1, tA2, tW, a, grid, st)
+    if (BN == 64) {
+        if (stages <= 4) VMV_LAUNCH(64, 4); else VMV_LAUNCH(64, 8);
+    } else if (BN == 128) {
+        if (stages <= 3) VMV_LAUNCH(128, 3); else VMV_LAUNCH(128, 6);
+    } else if (BN == 160) {
+        if (stages <= 3) VMV_LAUNCH(160, 3); else VMV_LAUNCH(160, 6);
+    } else {
+        VMV_LAUNCH(256, 4);
+    }
+#undef VMV_LAUNCH
+    if (rc != VMV_OK) return rc;
+
+    if (pl.splits > 1) {
+        const long long nthreads = (long long)p->M * (p->N / 8);
+        const int tb = 256;
+        splitk_finish_kernel<<<(unsigned)((nthreads + tb - 1) / tb), tb, 0, st>>>(a.partial, pl.splits, p->M, p->N, a);
+        count_launch();
+        VMV_CUDA_LAUNCH_CHECK("vmv_gemm split-K finish");
+    }
+    return VMV_OK;
+}

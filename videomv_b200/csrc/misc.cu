@@ -1,0 +1,260 @@
+// Small CUDA-core kernels around the tensor-core path: data movement (nearest upsample, stride-2 patch gather),
+// the 4-channel input / output convolutions, embeddings, and the CFG + DDIM update.
+#include "common.cuh"
+#include "../../include/videomv_b200.h"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <atomic>
+
+namespace vmv {
+
+// ------------------------------------------------------------------------------------------------
+// error / accounting plumbing shared by all translation units
+// ------------------------------------------------------------------------------------------------
+void count_launch(int n = 1);
+static thread_local char g_err[1024] = "";
+static std::atomic<long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------------
+__global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int cv, uint4* __restrict__ out,
+                                  long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int ow = (int)(r % (2 * W)); r /= (2 * W);
+    const int oh = (int)(r % (2 * H));
+    const long long n = r / (2 * H);
+    out[i] = __ldg(x + ((n * H + (oh >> 1)) * W + (ow >> 1)) * cv + c);
+}
+
+// out[(n,oh,ow), (ky,kx,c)] = x[n, 2*oh+ky-1, 2*ow+kx-1, c]  (zero outside)
+__global__ void im2col_s2_kernel(const uint4* __restrict__ x, int H, int W, int cv, uint4* __restrict__ out,
+                                 long long total) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int c = (int)(i % cv);
+    long long r = i / cv;
+    const int tap = (int)(r % 9); r /= 9;
+    const int OW = W / 2, OH = H / 2;
+    const int ow = (int)(r % OW); r /= OW;
+    const int oh = (int)(r % OH);
+    const long long n = r / OH;
+    const int ih = 2 * oh + tap / 3 - 1, iw = 2 * ow + tap % 3 - 1;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (ih >= 0 && ih < H && iw >= 0 && iw < W) v = __ldg(x + ((n * H + ih) * W + iw) * cv + c);
+    out[i] = v;
+}
+
+// Input conv: tiny Cin (4 or 8).  One thread per (pixel, 8 output channels); weights via the read-only cache.
+__global__ void conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int B,
+                                  int F, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
+                                  int Cout, __half* __restrict__ out) {
+    const int cov = Cout / 8;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)B * F * H * W * cov;
+    if (i >= total) return;
+    const int co0 = (int)(i % cov) * 8;
+    long long pix = i / cov;
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const int f = (int)((pix / ((long long)W * H)) % F);
+    const int b = (int)(pix / ((long long)W * H * F));
+    const int Cin = C1 + C2;
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = bias[co0 + j];
+    for (int ci = 0; ci < Cin; ++ci) {
+        const float* src = ci < C1 ? x1 + (((long long)b * C1 + ci) * F + f) * H * W
+                                   : x2 + (((long long)b * C2 + (ci - C1)) * F + f) * H * W;
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+            const int ih = yh + ky - 1;
+            if (ih < 0 || ih >= H) continue;
+#pragma unroll
+            for (int kx = 0; kx < 3; ++kx) {
+                const int iw = xw + kx - 1;
+                if (iw < 0 || iw >= W) continue;
+                const float v = __ldg(src + ih * W + iw);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += v * __ldg(w + (((long long)(co0 + j) * Cin + ci) * 3 + ky) * 3 + kx);
+            }
+        }
+    }
+    uint4 o = make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]), pack_half2(acc[4], acc[5]),
+                         pack_half2(acc[6], acc[7]));
+    *reinterpret_cast<uint4*>(out + pix * Cout + co0) = o;
+}
+
+// Head conv: tiny Cout (4).  One warp per output pixel: lanes stride the (tap, channel-vector) reduction.
+template <int COUT>
+__global__ void conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int C,
+                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const long long npix = (long long)B * F * H * W;
+    if (pix >= npix) return;
+    const int xw = (int)(pix % W);
+    const int yh = (int)((pix / W) % H);
+    const long long n = pix / ((long long)W * H);     // b*F + f
+    const int cv = C / 8;
+    float acc[COUT];
+#pragma unroll
+    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+    for (int i = lane; i < 9 * cv; i += 32) {
+        const int tap = i / cv, c0 = (i % cv) * 8;
+        const int ih = yh + tap / 3 - 1, iw = xw + tap % 3 - 1;
+        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+        uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * C + c0));
+        uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { float2 f2 = unpack_half2(ww[j]); v[2 * j] = f2.x; v[2 * j + 1] = f2.y; }
+#pragma unroll
+        for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[co] += v[j] * __ldg(w + ((long long)co * C + c0 + j) * 9 + tap);
+        }
+    }
+#pragma unroll
+    for (int co = 0; co < COUT; ++co) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
+    }
+    if (lane == 0) {
+        const int f = (int)(n % F);
+        const long long b = n / F;
+#pragma unroll
+        for (int co = 0; co < COUT; ++co)
+            out[(((b * COUT + co) * F + f) * H + yh) * W + xw] = acc[co] + bias[co];
+    }
+}
+
+__global__ void sinusoidal_kernel(const long long* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+    const int half_dim = dim / 2;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * half_dim) return;
+    const int b = i / half_dim, k = i % half_dim;
+    const float tv = (float)t[b];
+    // torch.pow(10000, -arange(half)/half) evaluated in fp32 (util.py:184-186)
+    const float freq = powf(10000.0f, -(float)k / (float)half_dim);
+    const float ang = tv * freq;
+    out[(long long)b * dim + k] = __float2half_rn(cosf(ang));
+    out[(long long)b * dim + half_dim + k] = __float2half_rn(sinf(ang));
+}
+
+__global__ void embed_combine_silu_kernel(const __half* __restrict__ te, const __half* __restrict__ te2,
+                                          const __half* __restrict__ cam, int B, int F, int E, __half* __restrict__ out) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * F * E) return;
+    const int e = (int)(i % E);
+    const long long bf = i / E;
+    const long long b = bf / F;
+    float v = __half2float(te[b * E + e]);
+    if (te2) v += __half2float(te2[b * E + e]);
+    if (cam) v += __half2float(cam[bf * E + e]);
+    out[i] = __float2half_rn(silu_f(v));
+}
+
+__global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __restrict__ y, const float* __restrict__ u,
+                                const float* __restrict__ coef, long long n, float* __restrict__ xprev) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float c_recip = coef[0], c_recipm1 = coef[1], sa_prev = coef[2], s1a_prev = coef[3], gs = coef[4];
+    const float uu = u[i];
+    const float eps_hat = uu + gs * (y[i] - uu);                   // diffusion_ddim.py:157-160
+    const float x0 = c_recip * xt[i] - c_recipm1 * eps_hat;        // :193-195
+    const float eps = (c_recip * xt[i] - x0) / c_recipm1;          // :233-234
+    xprev[i] = sa_prev * x0 + s1a_prev * eps;                      // :240-243 (eta = 0)
+}
+
+}  // namespace vmv
+
+using namespace vmv;
+
+extern "C" const char* vmv_last_error(void) { return g_err; }
+extern "C" int vmv_abi_version(void) { return 1; }
+extern "C" long long vmv_launch_count(void) { return g_launches.load(); }
+
+extern "C" int vmv_upsample_nearest2x(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
+    VMV_CHECK_ARG(x && out && n > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vmv_upsample_nearest2x: bad args");
+    const long long total = (long long)n * 4 * H * W * (C / 8);
+    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), H, W, C / 8, static_cast<uint4*>(out), total);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_upsample_nearest2x");
+    return VMV_OK;
+}
+
+extern "C" int vmv_im2col_3x3_s2(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
+    VMV_CHECK_ARG(x && out && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vmv_im2col_3x3_s2: bad args");
+    const long long total = (long long)n * (H / 2) * (W / 2) * 9 * (C / 8);
+    im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const uint4*>(x), H, W, C / 8, static_cast<uint4*>(out), total);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_im2col_3x3_s2");
+    return VMV_OK;
+}
+
+extern "C" int vmv_conv3x3_in(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t F, int32_t H,
+                              int32_t W, const float* w, const float* bias, int32_t Cout, void* out, void* stream) {
+    VMV_CHECK_ARG(x1 && w && bias && out && C1 > 0 && (C2 == 0 || x2) && Cout % 8 == 0, "vmv_conv3x3_in: bad args");
+    const long long total = (long long)B * F * H * W * (Cout / 8);
+    conv3x3_in_kernel<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        x1, C1, x2, C2, B, F, H, W, w, bias, Cout, static_cast<__half*>(out));
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_in");
+    return VMV_OK;
+}
+
+extern "C" int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, int32_t W, int32_t C, const float* w,
+                               const float* bias, int32_t Cout, float* out, void* stream) {
+    VMV_CHECK_ARG(x && w && bias && out && C % 8 == 0, "vmv_conv3x3_out: bad args");
+    VMV_CHECK_ARG(Cout == 4, "vmv_conv3x3_out: only out_dim=4 is instantiated (got %d)", Cout);
+    const long long npix = (long long)B * F * H * W;
+    conv3x3_out_kernel<4><<<(unsigned)((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), B, F, H, W, C, w, bias, out);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_out");
+    return VMV_OK;
+}
+
+extern "C" int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out, void* stream) {
+    VMV_CHECK_ARG(t && out && B > 0 && dim > 0 && dim % 2 == 0, "vmv_sinusoidal_embedding: bad args");
+    const int total = B * (dim / 2);
+    sinusoidal_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const long long*>(t), B, dim, static_cast<__half*>(out));
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_sinusoidal_embedding");
+    return VMV_OK;
+}
+
+extern "C" int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, const void* cam_emb, int32_t B, int32_t F,
+                                      int32_t E, void* out, void* stream) {
+    VMV_CHECK_ARG(t_emb && out && B > 0 && F > 0 && E > 0, "vmv_embed_combine_silu: bad args");
+    const long long total = (long long)B * F * E;
+    embed_combine_silu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(t_emb), static_cast<const __half*>(t_emb2), static_cast<const __half*>(cam_emb), B,
+        F, E, static_cast<__half*>(out));
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_embed_combine_silu");
+    return VMV_OK;
+}
+
+extern "C" int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef5, int64_t n,
+                                 float* x_prev, void* stream) {
+    VMV_CHECK_ARG(xt && y_out && u_out && coef5 && x_prev && n > 0, "vmv_cfg_ddim_step: bad args");
+    cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, y_out, u_out, coef5, n, x_prev);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_cfg_ddim_step");
+    return VMV_OK;
+}

@@ -1,0 +1,269 @@
+// GroupNorm(32) statistics / apply(+SiLU) and LayerNorm on channels-last fp16 rows.  HBM-bound kernels:
+// 16-byte vector loads/stores along C, one fixed channel vector per thread so the per-channel scale/shift
+// live in registers, fp32 partials per CTA, fp64 atomics across CTAs.
+#include "common.cuh"
+#include "../../include/videomv_b200.h"
+
+namespace vmv {
+
+void count_launch(int n = 1);
+
+constexpr int GN_THREADS = 256;
+constexpr int GN_GROUPS = 32;
+
+struct GnGeom {
+    int C, C1, nvec, slabs, vw, lanes;   // vw = channel vectors per CTA slab, lanes = row lanes per CTA
+    int rows_per_cta;
+};
+
+static GnGeom gn_geom(int C1, int C2, long long rows_per_batch, int nbatch) {
+    GnGeom g;
+    g.C = C1 + C2;
+    g.C1 = C1;
+    g.nvec = g.C / 8;
+    g.slabs = (g.nvec + GN_THREADS - 1) / GN_THREADS;
+    g.vw = (g.nvec + g.slabs - 1) / g.slabs;
+    g.lanes = GN_THREADS / g.vw;
+    // aim for >= ~4 CTAs per SM overall while keeping >= 8 rows per row lane
+    long long target_ctas = 148LL * 4;
+    long long per_batch = (target_ctas + nbatch - 1) / nbatch;
+    long long rpc = (rows_per_batch + per_batch - 1) / per_batch;
+    long long min_rpc = (long long)g.lanes * 8;
+    if (rpc < min_rpc) rpc = min_rpc;
+    if (rpc > rows_per_batch) rpc = rows_per_batch;
+    g.rows_per_cta = (int)rpc;
+    return g;
+}
+
+__device__ __forceinline__ const uint4* gn_src(const __half* x1, long long ld1, int C1, const __half* x2,
+                                               long long ld2, long long row, int c) {
+    return (c < C1) ? reinterpret_cast<const uint4*>(x1 + row * ld1 + c)
+                    : reinterpret_cast<const uint4*>(x2 + row * ld2 + (c - C1));
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
+                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats) {
+    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+    const int t = threadIdx.x;
+    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
+    __syncthreads();
+    const int batch = blockIdx.y;
+    const int tx = t % vw, ty = t / vw;
+    const int vec = blockIdx.z * vw + tx;
+    const int c0 = vec * 8;
+    const int cpg = C / GN_GROUPS;
+    if (ty < lanes && c0 < C) {
+        const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+        long long r_end = r_begin + rows_per_cta;
+        if (r_end > rows_per_batch) r_end = rows_per_batch;
+        const long long base = (long long)batch * rows_per_batch;
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+        for (long long r = r_begin + ty; r < r_end; r += lanes) {
+            uint4 u = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(w[j]);
+                s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+                s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+            }
+        }
+        // fold the 8 channels into their groups (a vector may straddle two groups)
+        int g_prev = c0 / cpg;
+        float as = 0.f, aq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int g = (c0 + j) / cpg;
+            if (g != g_prev) {
+                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+                as = 0.f; aq = 0.f; g_prev = g;
+            }
+            as += s[j]; aq += q[j];
+        }
+        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+    }
+    __syncthreads();
+    if (t < GN_GROUPS) {
+        // only groups touched by this slab are non-zero; skip exact zeros to save atomics
+        float a = s_sum[t], b = s_sq[t];
+        if (a != 0.f || b != 0.f) {
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)a);
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
+                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes,
+                const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu, __half* __restrict__ out, long long ldo) {
+    const int t = threadIdx.x;
+    const int batch = blockIdx.y;
+    const int tx = t % vw, ty = t / vw;
+    const int vec = blockIdx.z * vw + tx;
+    const int c0 = vec * 8;
+    if (ty >= lanes || c0 >= C) return;
+    const int cpg = C / GN_GROUPS;
+    const double cnt = (double)rows_per_batch * cpg;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const int g = c / cpg;
+        const double sum = stats[((long long)batch * GN_GROUPS + g) * 2];
+        const double sq = stats[((long long)batch * GN_GROUPS + g) * 2 + 1];
+        const double mean = sum / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
+        const float ga = gamma[c] * rstd;
+        sc[j] = ga;
+        sh[j] = beta[c] - (float)mean * ga;
+    }
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    long long r_end = r_begin + rows_per_cta;
+    if (r_end > rows_per_batch) r_end = rows_per_batch;
+    const long long base = (long long)batch * rows_per_batch;
+    for (long long r = r_begin + ty; r < r_end; r += lanes) {
+        uint4 u = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_half2(w[j]);
+            float a = f.x * sc[2 * j] + sh[2 * j];
+            float b = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+            if (silu) { a = silu_f(a); b = silu_f(b); }
+            o[j] = pack_half2(a, b);
+        }
+        *reinterpret_cast<uint4*>(out + (base + r) * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// One warp per row; the row lives in registers (<= 8 vectors of 8 halfs per lane => C <= 2048).
+constexpr int LN_MAX_VEC = 8;
+__global__ void __launch_bounds__(256)
+layernorm_kernel(const __half* __restrict__ x, long long ldx, long long M, int C, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, float eps, __half* __restrict__ out, long long ldo) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nvec = C / 8;
+    float v[LN_MAX_VEC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < nvec) {
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vec * 8));
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(w[j]);
+                v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float d = v[i][j] - mean; sq += d * d; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq / (float)C + eps);
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < nvec) {
+            const int c = vec * 8;
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + c));
+            const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + c + 4));
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + c));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + c + 4));
+            const float g[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+            const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                o[j] = pack_half2((v[i][2 * j] - mean) * rstd * g[2 * j] + b[2 * j],
+                                  (v[i][2 * j + 1] - mean) * rstd * g[2 * j + 1] + b[2 * j + 1]);
+            *reinterpret_cast<uint4*>(out + row * ldo + c) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+}  // namespace vmv
+
+using namespace vmv;
+
+static int gn_check(const char* who, const void* x1, int64_t ldx1, int C1, const void* x2, int64_t ldx2, int C2,
+                    int64_t rows_per_batch, int nbatch) {
+    VMV_CHECK_ARG(x1 && C1 > 0 && C1 % 8 == 0 && ldx1 % 8 == 0, "%s: bad x1/C1/ldx1", who);
+    VMV_CHECK_ARG(C2 == 0 || (x2 && C2 % 8 == 0 && ldx2 % 8 == 0), "%s: bad x2/C2/ldx2", who);
+    VMV_CHECK_ARG((C1 + C2) % GN_GROUPS == 0, "%s: C=%d not divisible by 32 groups", who, C1 + C2);
+    VMV_CHECK_ARG(rows_per_batch > 0 && nbatch > 0 && nbatch <= 65535, "%s: bad rows_per_batch/nbatch", who);
+    return VMV_OK;
+}
+
+extern "C" int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                                   int64_t rows_per_batch, int32_t nbatch, double* stats, void* stream) {
+    int rc = gn_check("vmv_groupnorm_stats", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
+    if (rc) return rc;
+    VMV_CHECK_ARG(stats != nullptr, "vmv_groupnorm_stats: null stats");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * GN_GROUPS * nbatch, st);
+    if (e != cudaSuccess) { set_error("vmv_groupnorm_stats: memset failed: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+    GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch);
+    dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
+    gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+                                                 static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
+                                                 g.rows_per_cta, g.vw, g.lanes, stats);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_stats");
+    return VMV_OK;
+}
+
+extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                                   int64_t rows_per_batch, int32_t nbatch, const double* stats, const float* gamma,
+                                   const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
+    int rc = gn_check("vmv_groupnorm_apply", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
+    if (rc) return rc;
+    VMV_CHECK_ARG(stats && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_apply: bad stats/gamma/beta/out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch);
+    dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
+    gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+                                                 static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
+                                                 g.rows_per_cta, g.vw, g.lanes, stats, gamma, beta, eps, silu,
+                                                 static_cast<__half*>(out), ldo);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_apply");
+    return VMV_OK;
+}
+
+extern "C" int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
+                             float eps, void* out, int64_t ldo, void* stream) {
+    VMV_CHECK_ARG(x && out && gamma && beta, "vmv_layernorm: null pointer");
+    VMV_CHECK_ARG(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 32 * 8, "vmv_layernorm: C=%d must be a multiple of 8 and <= %d", C, LN_MAX_VEC * 256);
+    VMV_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && M > 0, "vmv_layernorm: bad ld/M");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int wpb = 8;
+    layernorm_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+        static_cast<const __half*>(x), ldx, M, C, gamma, beta, eps, static_cast<__half*>(out), ldo);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_layernorm");
+    return VMV_OK;
+}

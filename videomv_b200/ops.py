@@ -1,0 +1,215 @@
+"""Thin torch-tensor front end over the C ABI (include/videomv_b200.h).
+
+PyTorch is used for device memory and streams only; every op below launches the library's own sm_100a kernels on
+the current CUDA stream (so they are captured by torch.cuda.graph).  Activations are channels-last fp16 `[rows, C]`.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import AttnParams, GemmParams, check
+
+LINEAR, CONV3X3, TCONV3 = 0, 1, 2
+ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _rows(t: torch.Tensor, what: str, dtype=torch.float16) -> None:
+    if not (t.is_cuda and t.dtype == dtype and t.dim() == 2 and t.stride(1) == 1):
+        raise ValueError(f"{what}: expected a CUDA {dtype} [rows, C] tensor with unit inner stride, got "
+                         f"{tuple(t.shape)} {t.dtype} strides {t.stride()} on {t.device}")
+
+
+def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+         bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_group: int = 0,
+         residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
+         geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
+         workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
+
+    a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
+    w [N,Ktot] fp16 packed by videomv_b200.packing.
+    """
+    _rows(a1, "gemm a1")
+    _rows(w, "gemm w")
+    M, K1 = a1.shape
+    N = w.shape[0]
+    n_out = N // 2 if act == ACT_GEGLU else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=torch.float16, device=a1.device)
+    _rows(out, "gemm out")
+    p = GemmParams()
+    p.mode, p.M, p.N, p.K1 = mode, M, N, K1
+    p.A1, p.lda1 = a1.data_ptr(), a1.stride(0)
+    if a2 is not None:
+        _rows(a2, "gemm a2")
+        p.A2, p.lda2, p.K2 = a2.data_ptr(), a2.stride(0), a2.shape[1]
+    p.W, p.ldw = w.data_ptr(), w.stride(0)
+    p.D, p.ldd = out.data_ptr(), out.stride(0)
+    if geom is not None:
+        p.B, p.F, p.H, p.Wd = geom
+    if bias is not None:
+        if bias.dtype != torch.float32 or bias.numel() != N:
+            raise ValueError("gemm bias must be fp32 [N]")
+        p.bias = bias.data_ptr()
+    if rowbias is not None:
+        _rows(rowbias, "gemm rowbias")
+        p.rowbias, p.ld_rowbias, p.rows_per_group = rowbias.data_ptr(), rowbias.stride(0), rows_per_group
+    if residual is not None:
+        _rows(residual, "gemm residual")
+        p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
+    p.act, p.block_n, p.stages, p.split_k = act, block_n, stages, split_k
+    if split_k > 1:
+        need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
+        if need < 0:
+            check(1, "gemm (workspace query)")
+        if workspace is None or workspace.numel() * workspace.element_size() < need:
+            workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=a1.device)
+        p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
+    return out
+
+
+def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
+              silu: bool, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+              stats: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """GroupNorm(32) over [x1 | x2] rows, statistics per chunk of `rows_per_batch` rows, optional SiLU."""
+    _rows(x1, "groupnorm x1")
+    rows, C1 = x1.shape
+    C2 = 0
+    if x2 is not None:
+        _rows(x2, "groupnorm x2")
+        C2 = x2.shape[1]
+    nbatch = rows // rows_per_batch
+    if nbatch * rows_per_batch != rows:
+        raise ValueError("groupnorm: rows not divisible by rows_per_batch")
+    if stats is None:
+        stats = torch.empty(nbatch * 64, dtype=torch.float64, device=x1.device)
+    if out is None:
+        out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
+    L = _lib.lib()
+    st = _stream()
+    check(L.vmv_groupnorm_stats(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
+                                rows_per_batch, nbatch, stats.data_ptr(), st), "vmv_groupnorm_stats")
+    check(L.vmv_groupnorm_apply(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
+                                rows_per_batch, nbatch, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
+    return out
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+              out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _rows(x, "layernorm x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().vmv_layernorm(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], gamma.data_ptr(),
+                                   beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), _stream()),
+          "vmv_layernorm")
+    return out
+
+
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, outer: int, inner: int,
+              heads: int, nq: int, nk: int, q_strides, k_strides, v_strides, o_strides, kv_group: int = 1,
+              scale: float = 0.125) -> torch.Tensor:
+    """softmax(q k^T scale) v with explicit (outer, inner, row) element strides; q/k/v/out are any fp16 CUDA
+    tensors whose data_ptr is the first element of head 0."""
+    p = AttnParams()
+    p.q, p.k, p.v, p.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    p.outer, p.inner, p.heads, p.nq, p.nk = outer, inner, heads, nq, nk
+    p.q_bs_outer, p.q_bs_inner, p.q_rs = q_strides
+    p.k_bs_outer, p.k_bs_inner, p.k_rs = k_strides
+    p.v_bs_outer, p.v_bs_inner, p.v_rs = v_strides
+    p.o_bs_outer, p.o_bs_inner, p.o_rs = o_strides
+    p.kv_group, p.scale = kv_group, scale
+    check(_lib.lib().vmv_attention(ctypes.byref(p), _stream()), "vmv_attention")
+    return out
+
+
+def upsample_nearest2x(x: torch.Tensor, n: int, H: int, W: int) -> torch.Tensor:
+    _rows(x, "upsample x")
+    C = x.shape[1]
+    assert x.is_contiguous()
+    out = torch.empty((n * 4 * H * W, C), dtype=torch.float16, device=x.device)
+    check(_lib.lib().vmv_upsample_nearest2x(x.data_ptr(), n, H, W, C, out.data_ptr(), _stream()), "vmv_upsample_nearest2x")
+    return out
+
+
+def im2col_3x3_s2(x: torch.Tensor, n: int, H: int, W: int) -> torch.Tensor:
+    _rows(x, "im2col x")
+    C = x.shape[1]
+    assert x.is_contiguous()
+    out = torch.empty((n * (H // 2) * (W // 2), 9 * C), dtype=torch.float16, device=x.device)
+    check(_lib.lib().vmv_im2col_3x3_s2(x.data_ptr(), n, H, W, C, out.data_ptr(), _stream()), "vmv_im2col_3x3_s2")
+    return out
+
+
+def conv3x3_in(x1: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, x2: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x1 fp32 [B,C1,F,H,W] (+x2 [B,C2,F,H,W]) -> fp16 [B*F*H*W, Cout]."""
+    assert x1.dtype == torch.float32 and x1.is_contiguous() and x1.is_cuda
+    B, C1, F, H, W = x1.shape
+    C2 = 0
+    if x2 is not None:
+        assert x2.dtype == torch.float32 and x2.is_contiguous() and x2.shape[0] == B and x2.shape[2:] == x1.shape[2:]
+        C2 = x2.shape[1]
+    Cout = w.shape[0]
+    assert w.dtype == torch.float32 and w.is_contiguous() and w.shape[1] == C1 + C2
+    out = torch.empty((B * F * H * W, Cout), dtype=torch.float16, device=x1.device)
+    check(_lib.lib().vmv_conv3x3_in(x1.data_ptr(), C1, _p(x2), C2, B, F, H, W, w.data_ptr(), bias.data_ptr(), Cout,
+                                    out.data_ptr(), _stream()), "vmv_conv3x3_in")
+    return out
+
+
+def conv3x3_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, B: int, F: int, H: int, W: int) -> torch.Tensor:
+    """x fp16 [B*F*H*W, C] -> fp32 [B,Cout,F,H,W]."""
+    _rows(x, "conv3x3_out x")
+    assert x.is_contiguous() and w.dtype == torch.float32 and w.is_contiguous()
+    Cout = w.shape[0]
+    out = torch.empty((B, Cout, F, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.lib().vmv_conv3x3_out(x.data_ptr(), B, F, H, W, x.shape[1], w.data_ptr(), bias.data_ptr(), Cout,
+                                     out.data_ptr(), _stream()), "vmv_conv3x3_out")
+    return out
+
+
+def sinusoidal_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
+    assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
+    out = torch.empty((t.shape[0], dim), dtype=torch.float16, device=t.device)
+    check(_lib.lib().vmv_sinusoidal_embedding(t.data_ptr(), t.shape[0], dim, out.data_ptr(), _stream()),
+          "vmv_sinusoidal_embedding")
+    return out
+
+
+def embed_combine_silu(t_emb: torch.Tensor, t_emb2: Optional[torch.Tensor], cam_emb: Optional[torch.Tensor], B: int,
+                       F: int) -> torch.Tensor:
+    _rows(t_emb, "embed t_emb")
+    E = t_emb.shape[1]
+    assert t_emb.is_contiguous() and (cam_emb is None or cam_emb.is_contiguous())
+    out = torch.empty((B * F, E), dtype=torch.float16, device=t_emb.device)
+    check(_lib.lib().vmv_embed_combine_silu(t_emb.data_ptr(), _p(t_emb2), _p(cam_emb), B, F, E, out.data_ptr(),
+                                            _stream()), "vmv_embed_combine_silu")
+    return out
+
+
+def cfg_ddim_step(xt: torch.Tensor, y_out: torch.Tensor, u_out: torch.Tensor, coef5: torch.Tensor,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    for t in (xt, y_out, u_out):
+        assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
+    if out is None:
+        out = torch.empty_like(xt)
+    check(_lib.lib().vmv_cfg_ddim_step(xt.data_ptr(), y_out.data_ptr(), u_out.data_ptr(), coef5.data_ptr(),
+                                       xt.numel(), out.data_ptr(), _stream()), "vmv_cfg_ddim_step")
+    return out
+
+
+def launch_count() -> int:
+    return int(_lib.lib().vmv_launch_count())

@@ -1,0 +1,55 @@
+"""Weight repacking: reference `state_dict` layouts -> the K-major fp16 operands `vmv_gemm` consumes.
+
+All functions are pure tensor reshapes (exact apart from the fp32->fp16 cast), done once after
+`load_state_dict`; the fp32 reference-named parameters stay the module's source of truth.
+"""
+from __future__ import annotations
+
+import torch
+
+
+def pack_linear(w: torch.Tensor) -> torch.Tensor:
+    """nn.Linear [N,K], nn.Conv1d k=1 [N,K,1], nn.Conv2d 1x1 [N,K,1,1] -> fp16 [N,K]."""
+    return w.reshape(w.shape[0], w.shape[1]).to(torch.float16).contiguous()
+
+
+def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d [Cout,Cin,3,3] -> fp16 [Cout, 9*Cin] with K ordered (ky, kx, c)."""
+    co, ci = w.shape[:2]
+    return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.float16).contiguous()
+
+
+def pack_tconv3(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv3d [Cout,Cin,3,1,1] -> fp16 [Cout, 3*Cin] with K ordered (kt, c)."""
+    co, ci = w.shape[:2]
+    return w[:, :, :, 0, 0].permute(0, 2, 1).reshape(co, 3 * ci).to(torch.float16).contiguous()
+
+
+def geglu_block_n(n: int) -> int:
+    """N tile used for a GEGLU GEMM with N = 8C columns (must divide N; mirrors pick_block_n in gemm_tc.cu)."""
+    return 160 if n % 160 == 0 else 128
+
+
+def pack_geglu(w: torch.Tensor, b: torch.Tensor):
+    """GEGLU.proj (util.py:546): W [8C,C] = [value rows | gate rows], bias [8C].
+
+    Re-order rows so every BN-row tile holds BN/2 value rows followed by the BN/2 matching gate rows; the GEMM
+    epilogue then computes value*gelu(gate) inside one tile.  Returns (fp16 W, fp32 bias, block_n).
+    """
+    n = w.shape[0]
+    half = n // 2
+    bn = geglu_block_n(n)
+    hb = bn // 2
+    assert n % bn == 0 and half % hb == 0
+    idx = []
+    for t in range(n // bn):
+        idx.extend(range(t * hb, (t + 1) * hb))
+        idx.extend(range(half + t * hb, half + (t + 1) * hb))
+    idx = torch.tensor(idx, dtype=torch.long, device=w.device)
+    return (w.index_select(0, idx).to(torch.float16).contiguous(),
+            b.index_select(0, idx).to(torch.float32).contiguous(), bn)
+
+
+def pack_cat(*ws: torch.Tensor) -> torch.Tensor:
+    """Row-concatenate several [Ni,K] projections (fused QKV / KV)."""
+    return torch.cat([pack_linear(w) for w in ws], dim=0).contiguous()
