@@ -147,6 +147,10 @@ int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, const void* ca
 int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef5, int64_t n,
                       float* x_prev, void* stream);
 
+/* sizeof() of the two parameter structs as compiled, so a foreign-language binding can verify its mirror. */
+int vmv_sizeof_gemm_params(void);
+int vmv_sizeof_attn_params(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -98,6 +98,8 @@ SYMBOLS = {
     "vmv_last_error": (ctypes.c_char_p, []),
     "vmv_abi_version": (ctypes.c_int, []),
     "vmv_launch_count": (ctypes.c_longlong, []),
+    "vmv_sizeof_gemm_params": (ctypes.c_int, []),
+    "vmv_sizeof_attn_params": (ctypes.c_int, []),
     "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
     "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
@@ -133,6 +135,9 @@ def lib() -> ctypes.CDLL:
         fn.argtypes = args
     if L.vmv_abi_version() != 1:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
+    if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
+            L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams)):
+        raise RuntimeError("videomv_b200: ctypes struct mirrors do not match the compiled vmv_*_params layouts")
     _LIB = L
     return L
 

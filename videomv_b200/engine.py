@@ -1,0 +1,390 @@
+"""UNetEngine: executes the VideoMV video-UNet forward with the library's sm_100a kernels.
+
+Data layout in HBM: every activation is channels-last fp16 `x[(b*F + f)*H*W + h*W + w, c]`, i.e. ONE row-major
+[M, C] matrix that is simultaneously
+  * the NHWC image batch the 3x3 convs tile with 4-D TMA boxes,
+  * the (frame, token, channel) sequence batch of the spatial transformers,
+  * the (pixel, frame, channel) sequence batch of the temporal transformers / temporal convs (strided views),
+so the reference's rearrange(...).contiguous() transposes (util.py:363,370,1054-1083,726-729) and torch.cat skip
+concats (unet_t2v.py:361) never materialise.  Weights are repacked once to K-major fp16 (packing.py).
+
+Reference call graph being replaced: unet_t2v.py:283-403 / unet_i2vgen.py:287-439 and every block in util.py they
+dispatch to.  Per-op reference citations live in include/videomv_b200.h.
+"""
+from __future__ import annotations
+
+from typing import Dict, List, Optional, Tuple
+
+import torch
+import torch.nn.functional as F
+
+from . import ops, packing
+
+SM_COUNT = 148
+
+
+class _W:
+    """Packed fp16 weight [N,K] + fp32 bias."""
+    __slots__ = ("w", "b", "bn")
+
+    def __init__(self, w, b=None, bn=0):
+        self.w, self.b, self.bn = w, b, bn
+
+
+def _f32(p):
+    return None if p is None else p.detach().to(torch.float32).contiguous()
+
+
+class UNetEngine:
+    def __init__(self, module):
+        self.m = module
+        self.device = next(module.parameters()).device
+        if self.device.type != "cuda":
+            raise RuntimeError("videomv_b200: move the UNet to a CUDA device before calling it (no CPU fallback)")
+        self.head_dim = module.head_dim
+        self.variant = module.variant
+        self._ws: Optional[torch.Tensor] = None        # split-K workspace
+        self._ctx_cache: Dict[Tuple, torch.Tensor] = {}
+        self._i2v_cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
+        self._graphs: Dict[Tuple, "_Graph"] = {}
+        self.use_graphs = False
+        self._pack()
+
+    # ------------------------------------------------------------------------------------------------------------
+    # weight packing (once per load)
+    # ------------------------------------------------------------------------------------------------------------
+    def _lin(self, layer, bias=True) -> _W:
+        return _W(packing.pack_linear(layer.weight.detach()), _f32(layer.bias) if bias and layer.bias is not None else None)
+
+    def _pack_tblock(self, tb, cross: bool):
+        d = {}
+        a1, a2 = tb.attn1, tb.attn2
+        d["qkv1"] = _W(packing.pack_cat(a1.to_q.weight.detach(), a1.to_k.weight.detach(), a1.to_v.weight.detach()))
+        d["o1"] = self._lin(a1.to_out[0])
+        if cross:
+            d["q2"] = _W(packing.pack_linear(a2.to_q.weight.detach()))
+            d["kv2_w"] = packing.pack_cat(a2.to_k.weight.detach(), a2.to_v.weight.detach())   # gathered into kv_all
+        else:
+            d["qkv2"] = _W(packing.pack_cat(a2.to_q.weight.detach(), a2.to_k.weight.detach(), a2.to_v.weight.detach()))
+        d["o2"] = self._lin(a2.to_out[0])
+        w, b, bn = packing.pack_geglu(tb.ff.net[0].proj.weight.detach(), tb.ff.net[0].proj.bias.detach())
+        d["ff1"] = _W(w, b, bn)
+        d["ff2"] = self._lin(tb.ff.net[2])
+        for i in (1, 2, 3):
+            n = getattr(tb, f"norm{i}")
+            d[f"ln{i}"] = (_f32(n.weight), _f32(n.bias))
+        return d
+
+    def _pack_block(self, mod):
+        kind = getattr(mod, "kind", None)
+        if kind == "res":
+            d = {"kind": "res", "cin": mod.channels, "cout": mod.out_channels}
+            d["gn1"] = (_f32(mod.in_layers[0].weight), _f32(mod.in_layers[0].bias))
+            d["c1"] = _W(packing.pack_conv3x3(mod.in_layers[2].weight.detach()), _f32(mod.in_layers[2].bias))
+            d["emb_off"] = self._emb_total
+            self._emb_w.append(packing.pack_linear(mod.emb_layers[1].weight.detach()))
+            self._emb_b.append(_f32(mod.emb_layers[1].bias))
+            self._emb_total += mod.out_channels
+            d["gn2"] = (_f32(mod.out_layers[0].weight), _f32(mod.out_layers[0].bias))
+            d["c2"] = _W(packing.pack_conv3x3(mod.out_layers[3].weight.detach()), _f32(mod.out_layers[3].bias))
+            d["skip"] = None
+            if not isinstance(mod.skip_connection, torch.nn.Identity):
+                d["skip"] = self._lin(mod.skip_connection)
+            tc = mod.temopral_conv
+            d["t"] = []
+            for st in (tc.conv1, tc.conv2, tc.conv3, tc.conv4):
+                d["t"].append(((_f32(st[0].weight), _f32(st[0].bias)),
+                               _W(packing.pack_tconv3(st[-1].weight.detach()), _f32(st[-1].bias))))
+            return d
+        if kind == "spatial":
+            d = {"kind": "spatial", "c": mod.in_channels, "heads": mod.heads}
+            d["gn"] = (_f32(mod.norm.weight), _f32(mod.norm.bias))
+            d["pin"], d["pout"] = self._lin(mod.proj_in), self._lin(mod.proj_out)
+            d["tb"] = self._pack_tblock(mod.transformer_blocks[0], cross=True)
+            d["kv_off"] = self._kv_total
+            self._kv_w.append(d["tb"].pop("kv2_w"))
+            self._kv_total += 2 * mod.heads * self.head_dim
+            return d
+        if kind == "temporal":
+            d = {"kind": "temporal", "c": mod.in_channels, "heads": mod.heads}
+            d["gn"] = (_f32(mod.norm.weight), _f32(mod.norm.bias))
+            d["pin"], d["pout"] = self._lin(mod.proj_in), self._lin(mod.proj_out)
+            d["tb"] = self._pack_tblock(mod.transformer_blocks[0], cross=False)
+            return d
+        if kind == "down":
+            return {"kind": "down", "c": mod.op.in_channels,
+                    "w": _W(packing.pack_conv3x3(mod.op.weight.detach()), _f32(mod.op.bias))}
+        if kind == "up":
+            return {"kind": "up", "c": mod.conv.in_channels,
+                    "w": _W(packing.pack_conv3x3(mod.conv.weight.detach()), _f32(mod.conv.bias))}
+        if isinstance(mod, torch.nn.Conv2d):
+            return {"kind": "stem", "w": _f32(mod.weight), "b": _f32(mod.bias)}
+        if isinstance(mod, torch.nn.ModuleList):
+            return {"kind": "list", "items": [self._pack_block(s) for s in mod]}
+        raise RuntimeError(f"videomv_b200: unknown block {type(mod)}")
+
+    def _pack_mlp(self, seq, pad_k: int = 0):
+        w0 = seq[0].weight.detach()
+        if pad_k and w0.shape[1] < pad_k:
+            w0 = F.pad(w0, (0, pad_k - w0.shape[1]))
+        return (_W(packing.pack_linear(w0), _f32(seq[0].bias)), self._lin(seq[2]))
+
+    @torch.no_grad()
+    def _pack(self):
+        m = self.m
+        self._emb_w: List[torch.Tensor] = []
+        self._emb_b: List[torch.Tensor] = []
+        self._emb_total = 0
+        self._kv_w: List[torch.Tensor] = []
+        self._kv_total = 0
+        self.time_mlp = self._pack_mlp(m.time_embed)
+        self.cam_mlp = self._pack_mlp(m.camera_embedding, pad_k=64) if hasattr(m, "camera_embedding") else None
+        self.fps_mlp = self._pack_mlp(m.fps_embedding) if hasattr(m, "fps_embedding") else None
+        self.enc = [self._pack_block(b) for b in m.input_blocks]
+        self.mid = [self._pack_block(b) for b in m.middle_block]
+        self.dec = [self._pack_block(b) for b in m.output_blocks]
+        self.head_gn = (_f32(m.out[0].weight), _f32(m.out[0].bias))
+        self.head_w, self.head_b = _f32(m.out[2].weight), _f32(m.out[2].bias)
+        # one GEMM produces every ResBlock's emb projection / every cross-attention's K,V
+        self.emb_all = _W(torch.cat(self._emb_w, 0).contiguous(), torch.cat(self._emb_b, 0).contiguous())
+        self.kv_all = _W(torch.cat(self._kv_w, 0).contiguous())
+        del self._emb_w, self._emb_b, self._kv_w
+
+    # ------------------------------------------------------------------------------------------------------------
+    # GEMM helper with the small-M split-K heuristic
+    # ------------------------------------------------------------------------------------------------------------
+    def _gemm(self, a, w: _W, **kw):
+        M = a.shape[0]
+        N = w.w.shape[0]
+        bn = w.bn or (160 if N % 160 == 0 else 128)
+        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        nkb = w.w.shape[1] // 64
+        split = 0
+        if kw.get("act", 0) != ops.ACT_GEGLU and tiles * 2 <= SM_COUNT and nkb >= 16:
+            split = min(nkb // 8, max(1, SM_COUNT // tiles))
+            if split >= 2:
+                need = split * M * N * 4
+                if self._ws is None or self._ws.numel() < need:
+                    self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
+                kw["workspace"] = self._ws
+            else:
+                split = 0
+        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, **kw)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # blocks
+    # ------------------------------------------------------------------------------------------------------------
+    def _res(self, d, x, skip, S):
+        B, Fr, H, W = S["B"], S["F"], S["H"], S["W"]
+        HW = H * W
+        emb = S["emb_all"][:, d["emb_off"]:d["emb_off"] + d["cout"]]
+        a0 = ops.groupnorm(x, *d["gn1"], rows_per_batch=HW, eps=1e-5, silu=True, x2=skip)
+        h = self._gemm(a0, d["c1"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), rowbias=emb, rows_per_group=HW)
+        a1 = ops.groupnorm(h, *d["gn2"], rows_per_batch=HW, eps=1e-5, silu=True)
+        if d["skip"] is not None:
+            res = self._gemm(x, d["skip"], a2=skip)
+        else:
+            res = x
+        h2 = self._gemm(a1, d["c2"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), residual=res)
+        cur = h2
+        for i, (gn, wt) in enumerate(d["t"]):
+            a = ops.groupnorm(cur, *gn, rows_per_batch=Fr * HW, eps=1e-5, silu=True)
+            cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Fr, H, W), residual=h2 if i == 3 else None)
+        return cur
+
+    def _tblock(self, tb, h, S, heads, temporal: bool, kv=None):
+        B, Fr, H, W = S["B"], S["F"], S["H"], S["W"]
+        HW = H * W
+        C = heads * self.head_dim
+        M = h.shape[0]
+
+        def self_attn(qkv):
+            o = torch.empty((M, C), dtype=torch.float16, device=h.device)
+            ld = 3 * C
+            if temporal:
+                st = (Fr * HW * ld, ld, HW * ld)
+                ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, outer=B, inner=HW, heads=heads, nq=Fr, nk=Fr,
+                              q_strides=st, k_strides=st, v_strides=st, o_strides=(Fr * HW * C, C, HW * C))
+            else:
+                st = (HW * ld, 0, ld)
+                ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], o, outer=B * Fr, inner=1, heads=heads, nq=HW, nk=HW,
+                              q_strides=st, k_strides=st, v_strides=st, o_strides=(HW * C, 0, C))
+            return o
+
+        n = ops.layernorm(h, *tb["ln1"])
+        h = self._gemm(self_attn(self._gemm(n, tb["qkv1"])), tb["o1"], residual=h)
+        n = ops.layernorm(h, *tb["ln2"])
+        if temporal:
+            h = self._gemm(self_attn(self._gemm(n, tb["qkv2"])), tb["o2"], residual=h)
+        else:
+            q = self._gemm(n, tb["q2"])
+            kview, vview, L, ldkv = kv
+            o = torch.empty((M, C), dtype=torch.float16, device=h.device)
+            ops.attention(q, kview, vview, o, outer=B * Fr, inner=1, heads=heads, nq=HW, nk=L,
+                          q_strides=(HW * C, 0, C), k_strides=(L * ldkv, 0, ldkv), v_strides=(L * ldkv, 0, ldkv),
+                          o_strides=(HW * C, 0, C), kv_group=Fr)
+            h = self._gemm(o, tb["o2"], residual=h)
+        n = ops.layernorm(h, *tb["ln3"])
+        g = self._gemm(n, tb["ff1"], act=ops.ACT_GEGLU)
+        return self._gemm(g, tb["ff2"], residual=h)
+
+    def _spatial(self, d, x, S):
+        HW = S["H"] * S["W"]
+        a = ops.groupnorm(x, *d["gn"], rows_per_batch=HW, eps=1e-6, silu=False)
+        h = self._gemm(a, d["pin"])
+        C = d["heads"] * self.head_dim
+        kvall = S["kv_all"]
+        off = d["kv_off"]
+        kv = (kvall[:, off:off + C], kvall[:, off + C:off + 2 * C], S["L"], kvall.stride(0))
+        h = self._tblock(d["tb"], h, S, d["heads"], temporal=False, kv=kv)
+        return self._gemm(h, d["pout"], residual=x)
+
+    def _temporal(self, d, x, S):
+        rows = S["F"] * S["H"] * S["W"]
+        a = ops.groupnorm(x, *d["gn"], rows_per_batch=rows, eps=1e-6, silu=False)
+        h = self._gemm(a, d["pin"])
+        h = self._tblock(d["tb"], h, S, d["heads"], temporal=True)
+        return self._gemm(h, d["pout"], residual=x)
+
+    def _run_block(self, d, x, skip, S):
+        k = d["kind"]
+        if k == "list":
+            for it in d["items"]:
+                x = self._run_block(it, x, skip, S)
+                skip = None
+            return x
+        if k == "res":
+            return self._res(d, x, skip, S)
+        if k == "spatial":
+            return self._spatial(d, x, S)
+        if k == "temporal":
+            return self._temporal(d, x, S)
+        if k == "down":
+            n, H, W = S["B"] * S["F"], S["H"], S["W"]
+            out = self._gemm(ops.im2col_3x3_s2(x, n, H, W), d["w"])
+            S["H"], S["W"] = H // 2, W // 2
+            return out
+        if k == "up":
+            n, H, W = S["B"] * S["F"], S["H"], S["W"]
+            up = ops.upsample_nearest2x(x, n, H, W)
+            S["H"], S["W"] = 2 * H, 2 * W
+            return self._gemm(up, d["w"], mode=ops.CONV3X3, geom=(1, n, 2 * H, 2 * W))
+        if k == "stem":
+            return ops.conv3x3_in(S["x_in"], d["w"], d["b"], S.get("x_in2"))
+        raise RuntimeError(k)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # conditioning
+    # ------------------------------------------------------------------------------------------------------------
+    def _mlp(self, mlp, x16):
+        h = self._gemm(x16, mlp[0], act=ops.ACT_SILU)
+        return self._gemm(h, mlp[1])
+
+    def _embeddings(self, t, fps, cam, B, Fr):
+        dim = self.m.dim
+        te = self._mlp(self.time_mlp, ops.sinusoidal_embedding(t.to(torch.int64).contiguous(), dim))
+        fe = None
+        if fps is not None and self.fps_mlp is not None:
+            fe = self._mlp(self.fps_mlp, ops.sinusoidal_embedding(fps.to(torch.int64).contiguous(), dim))
+        ce = None
+        if cam is not None and self.cam_mlp is not None:
+            c16 = torch.zeros((B * Fr, 64), dtype=torch.float16, device=self.device)
+            c16[:, :cam.shape[-1]] = cam.reshape(B * Fr, -1)
+            ce = self._mlp(self.cam_mlp, c16)
+        e_silu = ops.embed_combine_silu(te, fe, ce, B, Fr)
+        return self._gemm(e_silu, self.emb_all)
+
+    def _context_kv(self, ctx: torch.Tensor):
+        """K/V of every cross-attention layer for context [B, L, 1024]: one GEMM, B*L rows (the reference recomputes
+        them per frame per layer per step: util.py:233-234 on a context repeated F times, unet_t2v.py:346)."""
+        Bc, L, Dc = ctx.shape
+        c16 = ctx.reshape(Bc * L, Dc).to(torch.float16).contiguous()
+        return self._gemm(c16, self.kv_all), L
+
+    # ------------------------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, t, y, camera_data, fps, image=None, local_image=None):
+        if x.dim() != 5:
+            raise ValueError("videomv_b200: x must be [B, C, F, h, w]")
+        dev = self.device
+        out_dtype = x.dtype
+        B, _, Fr, H, W = x.shape
+        x32 = x.detach().to(device=dev, dtype=torch.float32).contiguous()
+        t = t.to(dev)
+        y = y.to(dev)
+        cam = None if camera_data is None else camera_data.to(device=dev, dtype=torch.float32)   # arrives on CPU in the
+        fps = None if fps is None else fps.to(dev)                                               # reference engine
+        S = {"B": B, "F": Fr, "H": H, "W": W, "x_in": x32}
+        if self.variant == "i2v":
+            concat, ctx = self._i2v_condition(x32, y, image, local_image)
+            S["x_in2"] = concat
+        else:
+            ctx = y
+        S["emb_all"] = self._embeddings(t, fps, cam, B, Fr)
+        S["kv_all"], S["L"] = self._context_kv(ctx)
+        skips = []
+        h = None
+        for blk in self.enc:
+            h = self._run_block(blk, h, None, S)
+            skips.append(h)
+        for blk in self.mid:
+            h = self._run_block(blk, h, None, S)
+        for blk in self.dec:
+            h = self._run_block(blk, h, skips.pop(), S)
+        a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True)
+        out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
+        return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+    # ------------------------------------------------------------------------------------------------------------
+    # I2V conditioning glue (step-invariant; depends only on local_image / image / y)
+    # ------------------------------------------------------------------------------------------------------------
+    def _i2v_condition(self, x32, y, image, local_image):
+        """unet_i2vgen.py:314-346 (concat branch) and :361-382 (context).  Tiny 4..32-channel convolutions and a
+        2-head d=4 transformer over frames whose inputs do not change across the 50 DDIM steps: evaluated with torch
+        ops as host-side glue (like the VAE/CLIP), not part of the per-step hot path."""
+        m = self.m
+        B, _, Fr, H, W = x32.shape
+        li = local_image.to(device=self.device, dtype=torch.float32)
+        if li.ndim == 5 and li.size(2) > 1:
+            li = li[:, :, :1]
+        elif li.ndim != 5:
+            li = li.unsqueeze(2)
+        if Fr > 1:
+            pos = torch.cat([torch.ones_like(li[:, :, :1]) * ((tp + 1) / (Fr - 1)) for tp in range(Fr - 1)], dim=2)
+            ximg = torch.cat([li[:, :, :1], pos], dim=2)
+        else:
+            ximg = li
+        ximg = ximg.permute(0, 2, 1, 3, 4).reshape(B * ximg.shape[2], -1, H, W)
+
+        def run_seq(seq, z):                       # eval semantics (Dropout = identity), true fp32 convolutions
+            with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+                for layer in seq:
+                    if not isinstance(layer, torch.nn.Dropout):
+                        z = layer(z)
+            return z
+
+        ximg = run_seq(m.local_image_concat, ximg)
+        cd = ximg.shape[1]
+        tok = ximg.reshape(B, Fr, cd, H, W).permute(0, 3, 4, 1, 2).reshape(B * H * W, Fr, cd)
+        enc = m.local_temporal_encoder
+        for attn, ff in enc.layers:
+            n = attn.norm(tok)
+            q, k, v = attn.fn.to_qkv(n).chunk(3, dim=-1)
+            hd = attn.fn.heads
+
+            def sp(z):
+                return z.reshape(z.shape[0], z.shape[1], hd, -1).transpose(1, 2)
+            o = F.scaled_dot_product_attention(sp(q), sp(k), sp(v)).transpose(1, 2).reshape(tok.shape[0], Fr, -1)
+            if not isinstance(attn.fn.to_out, torch.nn.Identity):
+                o = attn.fn.to_out[0](o)
+            tok = o + tok
+            tok = ff.net[2](ff.net[0](tok)) + tok
+        ximg = tok.reshape(B, H, W, Fr, cd).permute(0, 4, 3, 1, 2)
+        concat = (ximg + ximg).contiguous()                                   # :345-346 (kept double add)
+        ctx = y.to(torch.float32)
+        lc = run_seq(m.local_image_embedding, li[:, :, 0])
+        ctx = torch.cat([ctx, lc.flatten(2).transpose(1, 2)], dim=1)
+        if image is not None:
+            ic = run_seq(m.context_embedding, image.to(device=self.device, dtype=torch.float32))
+            ctx = torch.cat([ctx, ic.view(-1, m.num_tokens, m.context_dim)], dim=1)
+        return concat, ctx

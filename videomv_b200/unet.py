@@ -1,0 +1,419 @@
+"""Drop-in video-UNet modules for VideoMV: `UNetSD_T2VBase` and `UNetSD_I2VGen`.
+
+Boundary: same class names (registered in the reference `MODEL` registry when it is
+importable), same constructor kwargs, same `forward` signature, and a parameter tree whose `state_dict()` keys and
+shapes equal the reference's (tools/modules/unet/unet_t2v.py:56-265, unet_i2vgen.py:28-285, util.py) so released
+checkpoints load with `load_state_dict(strict=False)` and `configs/*_infer.yaml` drop in unchanged.
+
+The modules below only *hold* parameters (standard nn layers are used as typed containers so names, shapes, init and
+`.to()` behave as usual); none of their `forward`s run.  `forward()` hands the call to `engine.UNetEngine`, which
+executes the whole network with the library's sm_100a kernels in channels-last fp16.  There is no PyTorch or CPU
+fallback: without CUDA + the built library the call raises.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from .engine import UNetEngine
+
+GN_GROUPS = 32
+
+
+def _seq(*mods) -> nn.Sequential:
+    return nn.Sequential(*mods)
+
+
+def _mlp(i: int, h: int, o: int) -> nn.Sequential:
+    return _seq(nn.Linear(i, h), nn.SiLU(), nn.Linear(h, o))
+
+
+class _Holder(nn.Module):
+    """Parameter container with a `kind` tag the engine dispatches on (never called)."""
+    kind = "holder"
+
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("videomv_b200 parameter holders are not callable; the UNet runs through UNetEngine")
+
+
+class TemporalConvParams(_Holder):
+    """util.py:1347-1379 TemporalConvBlock_v2: 4 x [GN, SiLU, (Dropout,) Conv3d(3,1,1)]."""
+    kind = "tconv"
+
+    def __init__(self, c: int):
+        super().__init__()
+        def stage(first):
+            layers = [nn.GroupNorm(GN_GROUPS, c), nn.SiLU()]
+            if not first:
+                layers.append(nn.Dropout(0.1))
+            layers.append(nn.Conv3d(c, c, (3, 1, 1), padding=(1, 0, 0)))
+            return _seq(*layers)
+        self.conv1, self.conv2, self.conv3, self.conv4 = stage(True), stage(False), stage(False), stage(False)
+        nn.init.zeros_(self.conv4[-1].weight)
+        nn.init.zeros_(self.conv4[-1].bias)
+
+
+class ResBlockParams(_Holder):
+    """util.py:610-701 ResBlock (use_scale_shift_norm=False, no up/down) + temporal conv tail."""
+    kind = "res"
+
+    def __init__(self, cin: int, emb: int, cout: int, dropout: float):
+        super().__init__()
+        self.channels, self.out_channels = cin, cout
+        self.in_layers = _seq(nn.GroupNorm(GN_GROUPS, cin), nn.SiLU(), nn.Conv2d(cin, cout, 3, padding=1))
+        self.h_upd = self.x_upd = nn.Identity()
+        self.emb_layers = _seq(nn.SiLU(), nn.Linear(emb, cout))
+        self.out_layers = _seq(nn.GroupNorm(GN_GROUPS, cout), nn.SiLU(), nn.Dropout(dropout),
+                               nn.Conv2d(cout, cout, 3, padding=1))
+        for p in self.out_layers[-1].parameters():
+            nn.init.zeros_(p)
+        self.skip_connection = nn.Identity() if cin == cout else nn.Conv2d(cin, cout, 1)
+        self.temopral_conv = TemporalConvParams(cout)          # [sic] util.py:691
+
+
+class _AttnParams(nn.Module):
+    """util.py:212-228 MemoryEfficientCrossAttention parameters."""
+
+    def __init__(self, qdim: int, ctx: Optional[int], heads: int, dh: int):
+        super().__init__()
+        inner = heads * dh
+        ctx = ctx or qdim
+        self.heads, self.dim_head = heads, dh
+        self.to_q = nn.Linear(qdim, inner, bias=False)
+        self.to_k = nn.Linear(ctx, inner, bias=False)
+        self.to_v = nn.Linear(ctx, inner, bias=False)
+        self.to_out = _seq(nn.Linear(inner, qdim), nn.Dropout(0.0))
+
+
+class _GEGLUParams(nn.Module):
+    def __init__(self, i: int, o: int):
+        super().__init__()
+        self.proj = nn.Linear(i, o * 2)
+
+
+class _FFParams(nn.Module):
+    """util.py:560-577 FeedForward(glu=True): GEGLU(dim -> 4 dim) ; Dropout ; Linear(4 dim -> dim)."""
+
+    def __init__(self, dim: int):
+        super().__init__()
+        self.net = _seq(_GEGLUParams(dim, 4 * dim), nn.Dropout(0.0), nn.Linear(4 * dim, dim))
+
+
+class _TBlockParams(nn.Module):
+    """util.py:510-531 BasicTransformerBlock: attn1 (self), attn2 (ctx or self), GEGLU ff, 3 LayerNorms."""
+
+    def __init__(self, dim: int, heads: int, dh: int, ctx: Optional[int]):
+        super().__init__()
+        self.attn1 = _AttnParams(dim, None, heads, dh)
+        self.ff = _FFParams(dim)
+        self.attn2 = _AttnParams(dim, ctx, heads, dh)
+        self.norm1, self.norm2, self.norm3 = nn.LayerNorm(dim), nn.LayerNorm(dim), nn.LayerNorm(dim)
+
+
+class SpatialTransformerParams(_Holder):
+    """util.py:311-352 SpatialTransformer(use_linear=True, depth=1)."""
+    kind = "spatial"
+
+    def __init__(self, c: int, heads: int, dh: int, ctx: int):
+        super().__init__()
+        inner = heads * dh
+        self.in_channels, self.heads = c, heads
+        self.norm = nn.GroupNorm(GN_GROUPS, c, eps=1e-6, affine=True)
+        self.proj_in = nn.Linear(c, inner)
+        self.transformer_blocks = nn.ModuleList([_TBlockParams(inner, heads, dh, ctx)])
+        self.proj_out = nn.Linear(c, inner)
+        for p in self.proj_out.parameters():
+            nn.init.zeros_(p)
+
+
+class TemporalTransformerParams(_Holder):
+    """util.py:992-1041 TemporalTransformer(only_self_att=True, use_linear=False): Conv1d k=1 projections."""
+    kind = "temporal"
+
+    def __init__(self, c: int, heads: int, dh: int):
+        super().__init__()
+        inner = heads * dh
+        self.in_channels, self.heads = c, heads
+        self.norm = nn.GroupNorm(GN_GROUPS, c, eps=1e-6, affine=True)
+        self.proj_in = nn.Conv1d(c, inner, kernel_size=1)
+        self.transformer_blocks = nn.ModuleList([_TBlockParams(inner, heads, dh, None)])
+        self.proj_out = nn.Conv1d(inner, c, kernel_size=1)
+        for p in self.proj_out.parameters():
+            nn.init.zeros_(p)
+
+
+class DownsampleParams(_Holder):
+    """util.py:732-756 Downsample(use_conv=True): Conv2d 3x3 stride 2."""
+    kind = "down"
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.op = nn.Conv2d(c, c, 3, stride=2, padding=1)
+
+
+class UpsampleParams(_Holder):
+    """util.py:579-607 Upsample(use_conv=True): nearest x2 then Conv2d 3x3."""
+    kind = "up"
+
+    def __init__(self, c: int):
+        super().__init__()
+        self.conv = nn.Conv2d(c, c, 3, padding=1)
+
+
+class _VideoUNetBase(nn.Module):
+    """Trunk shared by both models: encoder / middle / decoder / head parameter tree + engine plumbing."""
+
+    variant = "t2v"
+
+    def _build_trunk(self, first_in: int, dim: int, out_dim: int, dim_mult: List[int], num_heads: int, head_dim: int,
+                     num_res_blocks: int, attn_scales, dropout: float, context_dim: int, temporal_attention: bool):
+        embed_dim = dim * 4
+        widths = [dim * m for m in dim_mult]
+        enc = [dim] + widths
+        dec = [widths[-1]] + widths[::-1]
+        skips: List[int] = []
+        scale = 1.0
+
+        def attn_pair(c):
+            mods = [SpatialTransformerParams(c, c // head_dim, head_dim, context_dim)]
+            if temporal_attention:
+                mods.append(TemporalTransformerParams(c, c // head_dim, head_dim))
+            return mods
+
+        # encoder (unet_t2v.py:168-206)
+        self.input_blocks = nn.ModuleList()
+        stem = [nn.Conv2d(first_in, dim, 3, padding=1)]
+        if temporal_attention:
+            stem.append(TemporalTransformerParams(dim, num_heads, head_dim))    # 8 heads x 64 = 512 inner
+        self.input_blocks.append(nn.ModuleList(stem))
+        skips.append(dim)
+        for i, (cin, cout) in enumerate(zip(enc[:-1], enc[1:])):
+            for j in range(num_res_blocks):
+                blk = [ResBlockParams(cin, embed_dim, cout, dropout)]
+                if scale in attn_scales:
+                    blk += attn_pair(cout)
+                cin = cout
+                self.input_blocks.append(nn.ModuleList(blk))
+                skips.append(cout)
+                if i != len(dim_mult) - 1 and j == num_res_blocks - 1:
+                    self.input_blocks.append(DownsampleParams(cout))
+                    skips.append(cout)
+                    scale /= 2.0
+        # middle (unet_t2v.py:208-227)
+        mid = [ResBlockParams(cout, embed_dim, cout, dropout), SpatialTransformerParams(cout, cout // head_dim, head_dim, context_dim)]
+        if temporal_attention:
+            mid.append(TemporalTransformerParams(cout, cout // head_dim, head_dim))
+        mid.append(ResBlockParams(cout, embed_dim, cout, dropout))
+        self.middle_block = nn.ModuleList(mid)
+        # decoder (unet_t2v.py:229-258); decoder cross-attention hard-codes context_dim=1024 (:237)
+        self.output_blocks = nn.ModuleList()
+        for i, (cin, cout) in enumerate(zip(dec[:-1], dec[1:])):
+            for j in range(num_res_blocks + 1):
+                blk = [ResBlockParams(cin + skips.pop(), embed_dim, cout, dropout)]
+                if scale in attn_scales:
+                    blk.append(SpatialTransformerParams(cout, cout // head_dim, head_dim, 1024))
+                    if temporal_attention:
+                        blk.append(TemporalTransformerParams(cout, cout // head_dim, head_dim))
+                cin = cout
+                if i != len(dim_mult) - 1 and j == num_res_blocks:
+                    blk.append(UpsampleParams(cout))
+                    scale *= 2.0
+                self.output_blocks.append(nn.ModuleList(blk))
+        # head (unet_t2v.py:261-265)
+        self.out = _seq(nn.GroupNorm(GN_GROUPS, cout), nn.SiLU(), nn.Conv2d(cout, out_dim, 3, padding=1))
+        nn.init.zeros_(self.out[-1].weight)
+
+    # ---- engine plumbing ---------------------------------------------------------------------------------------
+    def _engine(self) -> UNetEngine:
+        eng = self.__dict__.get("_eng")
+        if eng is None:
+            eng = UNetEngine(self)
+            self.__dict__["_eng"] = eng
+        return eng
+
+    def invalidate_engine(self):
+        """Drop packed weights / captured graphs (called automatically after load_state_dict and .to())."""
+        self.__dict__["_eng"] = None
+
+    def _apply(self, fn, *a, **k):
+        self.invalidate_engine()
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, state_dict, strict: bool = True, **k):
+        self.invalidate_engine()
+        return super().load_state_dict(state_dict, strict=strict, **k)
+
+    def _check_call(self, x, masked, autoencoder, x0):
+        assert self.inpainting or masked is None, "inpainting is not supported"
+        if autoencoder is not None or x0 is not None:
+            raise NotImplementedError(
+                "videomv_b200: the LGM 3D-aware refinement tail (reference unet_t2v.py:370-433) is outside the "
+                "accelerated hot path (SURVEY.md section 8f row N4); call with autoencoder=None / x0=None")
+        if not x.is_cuda:
+            raise RuntimeError("videomv_b200: the UNet hot path only runs on a CUDA (sm_100a) device; there is no CPU fallback")
+
+
+class UNetSD_T2VBase(_VideoUNetBase):
+    """Text -> multi-view video UNet. Reference: tools/modules/unet/unet_t2v.py:56 (ctor :57-265, forward :283-403)."""
+
+    variant = "t2v"
+
+    def __init__(self, config=None, in_dim=4, dim=512, y_dim=512, context_dim=512, hist_dim=156, dim_condition=4,
+                 out_dim=6, num_tokens=4, dim_mult=(1, 2, 3, 4), num_heads=None, head_dim=64, camera_dim=16,
+                 num_res_blocks=3, attn_scales=(1 / 2, 1 / 4, 1 / 8), use_scale_shift_norm=True, dropout=0.1,
+                 temporal_attn_times=1, temporal_attention=True, use_checkpoint=False, use_image_dataset=False,
+                 use_sim_mask=False, training=True, inpainting=True, use_fps_condition=False,
+                 use_camera_condition=False, use_lgm_refine=False, p_all_zero=0.1, p_all_keep=0.1, zero_y=None,
+                 adapter_transformer_layers=1, **kwargs):
+        super().__init__()
+        embed_dim = dim * 4
+        num_heads = num_heads if num_heads else dim // 32
+        self.zero_y = zero_y
+        self.in_dim, self.dim, self.y_dim, self.context_dim = in_dim, dim, y_dim, context_dim
+        self.embed_dim, self.out_dim, self.dim_mult = embed_dim, out_dim, list(dim_mult)
+        self.num_heads, self.head_dim, self.num_res_blocks = num_heads, head_dim, num_res_blocks
+        self.attn_scales = list(attn_scales)
+        self.temporal_attention = temporal_attention
+        self.use_checkpoint = use_checkpoint            # accepted, irrelevant (no autograd on this path)
+        self.inpainting = inpainting
+        self.use_fps_condition, self.use_camera_condition = use_fps_condition, use_camera_condition
+        self.camera_dim = camera_dim
+        # The LGM refine network (core/models.py) is glue outside this path; keep the flag for callers that read it
+        # (diffusion_ddim.py:390) but do not construct it here.
+        self.use_lgm_refine = use_lgm_refine
+        self.time_embed = _mlp(dim, embed_dim, embed_dim)
+        if use_camera_condition:
+            self.camera_embedding = _mlp(camera_dim, embed_dim, embed_dim)
+            nn.init.zeros_(self.camera_embedding[-1].weight)
+            nn.init.zeros_(self.camera_embedding[-1].bias)
+        if use_fps_condition:
+            self.fps_embedding = _mlp(dim, embed_dim, embed_dim)
+            nn.init.zeros_(self.fps_embedding[-1].weight)
+            nn.init.zeros_(self.fps_embedding[-1].bias)
+        self._build_trunk(in_dim, dim, out_dim, list(dim_mult), num_heads, head_dim, num_res_blocks,
+                          list(attn_scales), dropout, context_dim, temporal_attention)
+
+    def forward(self, x, t, x0=None, gs_data=None, sqrt_alphas_cumprod=None, sqrt_one_minus_alphas_cumprod=None,
+                sqrt_recip_alphas_cumprod=None, sqrt_recipm1_alphas_cumprod=None, autoencoder=None, y=None, fps=None,
+                masked=None, camera_data=None, video_mask=None, focus_present_mask=None, prob_focus_present=0.,
+                mask_last_frame_num=0, **kwargs):
+        """Same call contract as the reference (diffusion_ddim.py:149-155). Returns [B, out_dim, F, h, w] like x."""
+        self._check_call(x, masked, autoencoder, x0)
+        if y is None:
+            if self.zero_y is None:
+                raise ValueError("videomv_b200: forward needs `y` (or a `zero_y` given at construction)")
+            y = self.zero_y.repeat(x.shape[0], 1, 1)[:, :1, :]          # unet_t2v.py:344
+        use_fps = self.use_fps_condition and fps is not None
+        use_cam = self.use_camera_condition and camera_data is not None
+        return self._engine().forward(x, t, y, camera_data if use_cam else None, fps if use_fps else None)
+
+
+class UNetSD_I2VGen(_VideoUNetBase):
+    """Image -> multi-view video UNet. Reference: tools/modules/unet/unet_i2vgen.py:28 (forward :287-439)."""
+
+    variant = "i2v"
+
+    def __init__(self, config=None, in_dim=7, dim=512, y_dim=512, context_dim=512, hist_dim=156, concat_dim=8,
+                 dim_condition=4, out_dim=6, num_tokens=4, dim_mult=(1, 2, 3, 4), num_heads=None, head_dim=64,
+                 num_res_blocks=3, attn_scales=(1 / 2, 1 / 4, 1 / 8), use_scale_shift_norm=True, dropout=0.1,
+                 temporal_attn_times=1, camera_dim=16, temporal_attention=True, use_checkpoint=False,
+                 use_image_dataset=False, use_sim_mask=False, use_camera_condition=False, use_lgm_refine=False,
+                 training=True, inpainting=True, p_all_zero=0.1, p_all_keep=0.1, zero_y=None,
+                 adapter_transformer_layers=1, **kwargs):
+        super().__init__()
+        embed_dim = dim * 4
+        num_heads = num_heads if num_heads else dim // 32
+        self.zero_y = zero_y
+        self.in_dim, self.dim, self.y_dim, self.context_dim = in_dim, dim, y_dim, context_dim
+        self.num_tokens = num_tokens
+        self.embed_dim, self.out_dim, self.dim_mult = embed_dim, out_dim, list(dim_mult)
+        self.num_heads, self.head_dim, self.num_res_blocks = num_heads, head_dim, num_res_blocks
+        self.attn_scales = list(attn_scales)
+        self.temporal_attention = temporal_attention
+        self.use_checkpoint = use_checkpoint
+        self.inpainting = inpainting
+        self.use_fps_condition = True                     # fps embedding is unconditional here (unet_i2vgen.py:349)
+        self.use_camera_condition, self.camera_dim = use_camera_condition, camera_dim
+        self.use_lgm_refine = use_lgm_refine
+        cd = self.concat_dim = in_dim                     # unet_i2vgen.py:93 overwrites concat_dim with in_dim
+        self.time_embed = _mlp(dim, embed_dim, embed_dim)
+        self.context_embedding = _mlp(y_dim, embed_dim, context_dim * num_tokens)
+        if use_camera_condition:
+            self.camera_embedding = _mlp(camera_dim, embed_dim, embed_dim)
+            nn.init.zeros_(self.camera_embedding[-1].weight)
+            nn.init.zeros_(self.camera_embedding[-1].bias)
+        self.fps_embedding = _mlp(dim, embed_dim, embed_dim)
+        nn.init.zeros_(self.fps_embedding[-1].weight)
+        nn.init.zeros_(self.fps_embedding[-1].bias)
+        # conditioning glue, step-invariant (unet_i2vgen.py:145-162); executed once per sample by the engine
+        self.local_image_concat = _seq(nn.Conv2d(4, cd * 4, 3, padding=1), nn.SiLU(),
+                                       nn.Conv2d(cd * 4, cd * 4, 3, stride=1, padding=1), nn.SiLU(),
+                                       nn.Conv2d(cd * 4, cd, 3, stride=1, padding=1))
+        self.local_temporal_encoder = _LocalTemporalEncoderParams(cd, heads=2, depth=adapter_transformer_layers)
+        self.local_image_embedding = _seq(nn.Conv2d(4, cd * 8, 3, padding=1), nn.SiLU(),
+                                          nn.AdaptiveAvgPool2d((32, 32)),
+                                          nn.Conv2d(cd * 8, cd * 16, 3, stride=2, padding=1), nn.SiLU(),
+                                          nn.Conv2d(cd * 16, 1024, 3, stride=2, padding=1))
+        self._build_trunk(in_dim + cd, dim, out_dim, list(dim_mult), num_heads, head_dim, num_res_blocks,
+                          list(attn_scales), dropout, context_dim, temporal_attention)
+
+    def forward(self, x, t, x0=None, gs_data=None, sqrt_alphas_cumprod=None, sqrt_one_minus_alphas_cumprod=None,
+                sqrt_recip_alphas_cumprod=None, sqrt_recipm1_alphas_cumprod=None, autoencoder=None, y=None, image=None,
+                local_image=None, camera_data=None, masked=None, fps=None, video_mask=None, focus_present_mask=None,
+                prob_focus_present=0., mask_last_frame_num=0, **kwargs):
+        self._check_call(x, masked, autoencoder, x0)
+        if local_image is None or fps is None:
+            raise ValueError("videomv_b200: UNetSD_I2VGen.forward needs `local_image` and `fps` (unet_i2vgen.py:314,349)")
+        if y is None:
+            if self.zero_y is None:
+                raise ValueError("videomv_b200: forward needs `y` (or a `zero_y` given at construction)")
+            y = self.zero_y.repeat(x.shape[0], 1, 1)[:, :1, :]
+        use_cam = self.use_camera_condition and camera_data is not None
+        return self._engine().forward(x, t, y, camera_data if use_cam else None, fps, image=image, local_image=local_image)
+
+
+class _PreNormAttnParams(nn.Module):
+    def __init__(self, dim: int, heads: int, dh: int):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+        fn = nn.Module()
+        fn.to_qkv = nn.Linear(dim, heads * dh * 3, bias=False)
+        fn.to_out = _seq(nn.Linear(heads * dh, dim), nn.Dropout(0.05)) if not (heads == 1 and dh == dim) else nn.Identity()
+        fn.heads = heads
+        self.fn = fn
+
+
+class _PlainFFParams(nn.Module):
+    """util.py:560-577 FeedForward(glu=False): Linear -> GELU -> Dropout -> Linear."""
+
+    def __init__(self, dim: int, dim_out: int):
+        super().__init__()
+        self.net = _seq(_seq(nn.Linear(dim, dim * 4), nn.GELU()), nn.Dropout(0.05), nn.Linear(dim * 4, dim_out))
+
+
+class _LocalTemporalEncoderParams(nn.Module):
+    """util.py:1129-1148 TransformerV2(heads=2, dim=dim_head=mlp_dim=concat_dim)."""
+
+    def __init__(self, dim: int, heads: int, depth: int):
+        super().__init__()
+        self.depth = depth
+        self.layers = nn.ModuleList([nn.ModuleList([_PreNormAttnParams(dim, heads, dim), _PlainFFParams(dim, dim)])
+                                     for _ in range(depth)])
+
+
+def register_with_reference() -> bool:
+    """Register both classes in the reference's MODEL registry (utils/registry_class.py:16) under the reference
+    names, replacing the stock implementations (utils/registry.py:116-119 allows re-registration). Returns False when
+    the reference package is not importable (e.g. on the GPU box)."""
+    try:
+        from utils.registry_class import MODEL  # type: ignore
+    except Exception:
+        return False
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")               # "already registered ... will be replaced" is the point
+        for cls in (UNetSD_T2VBase, UNetSD_I2VGen):
+            MODEL.register_class()(cls)
+    return True
