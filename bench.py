@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- VideoMV headline benchmark on B200: multi-view frames/s of the UNet denoising hot path.
+
+metric   : multi-view frames / second = 24 * samples / time of `ddim_sample_loop` (50 DDIM steps, eta 0,
+           classifier-free guidance => 100 UNet evaluations + 50 scheduler updates per sample; autoencoder=None).
+           SURVEY.md section 8(d), BASELINE.json `metric`.
+step     : ONE full 50-step sample of one prompt (24 frames).  N GPUs = N independent samples (the reference's own
+           multi-GPU mode: one prompt stream per rank, tools/inferences/inference_text2video_entrance.py:79,152-170);
+           no data-path collective => "scaling": "weak".
+value    : device-resident inputs, CUDA-event timed, max over ranks.
+e2e      : the same loop through the reference-facing API (module registry class + DiffusionDDIM.ddim_sample_loop) with
+           HOST (pinned) inputs: H2D of noise / text embeddings / cameras and D2H of the final latent inside the timed
+           region, every step.
+roofline : the tcgen05 GEMM / implicit-conv kernel family (97% of the FLOPs): algorithmic FLOPs / CUDA-event time of
+           every launch of one CFG-batched forward, vs MEASURED_PEAKS.json bf16 sustained TFLOP/s.
+cpu_baseline / --impl reference : the CPU oracle port of the reference UNet (oracle/unet_oracle.py) on the host cores,
+           bounded sample, extrapolated to the same metric.
+
+Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload t2v256|t2v512|i2v256]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# Resolved UNet kwargs: tools/modules/config.py:88-106 overlaid by configs/t2v_infer.yaml:20-41.
+T2V_KWARGS = dict(in_dim=4, dim=320, y_dim=1024, context_dim=1024, out_dim=4, dim_mult=[1, 2, 4, 4], num_heads=8,
+                  head_dim=64, num_res_blocks=2, attn_scales=[1.0, 0.5, 0.25], dropout=0.1, misc_dropout=0.4,
+                  temporal_attention=True, temporal_attn_times=1, use_checkpoint=True, use_fps_condition=False,
+                  use_camera_condition=True, use_lgm_refine=True, use_sim_mask=False, upper_len=128, default_fps=8)
+WORKLOADS = {
+    # name: (kind, latent hw, guide_scale, mean_type, algorithmic TFLOP per forward [SURVEY 8d])
+    "t2v256": ("t2v", 32, 9.0, "eps", 7.467),
+    "t2v512": ("t2v", 64, 9.0, "eps", 34.26),
+    "i2v256": ("i2v", 32, 6.0, "v", 7.51),
+}
+FRAMES = 24
+DDIM_STEPS = 50
+
+
+def _peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(tflops=float(d.get("bf16_tflops_sustained", d.get("bf16_tflops", 1406.8))),
+                    tflops_burst=float(d.get("bf16_tflops", 1674.6)), hbm=float(d.get("hbm_gbs", 6579.0)), src="measured")
+    return dict(tflops=1400.0, tflops_burst=1590.0, hbm=6650.0, src="fallback")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock + throttle reasons through NVML during the timed region."""
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz, self._stop_evt = index, [], set(), None, threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                     nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                     nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap"}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                time.sleep(0.1)
+        except Exception as e:  # noqa: BLE001
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_host_inputs(kind: str, hw: int, seed: int):
+    """Synthetic inputs exactly as SURVEY.md 8(d): pinned HOST tensors."""
+    from videomv_b200 import synth
+    g = torch.Generator().manual_seed(seed)
+    pin = lambda z: z.pin_memory() if torch.cuda.is_available() else z
+    d = dict(noise=pin(torch.randn(1, 4, FRAMES, hw, hw, generator=g)),
+             y=pin(torch.randn(1, 77, 1024, generator=g)), y_neg=pin(torch.randn(1, 77, 1024, generator=g)),
+             cam=synth.orbit_cameras(FRAMES), fps=torch.tensor([8], dtype=torch.long))
+    if kind == "i2v":
+        d["image"] = pin(torch.randn(1, 1, 1024, generator=g))
+        d["local_image"] = pin((torch.randn(1, 4, 1, hw, hw, generator=g) * 0.18215).repeat(1, 1, FRAMES, 1, 1).contiguous())
+    return d
+
+
+def to_kwargs(kind: str, d: dict, dev):
+    cam = d["cam"]                                     # stays on CPU like the reference engine (moved inside forward)
+    cond = dict(y=d["y"].to(dev, non_blocking=True), camera_data=cam, fps=d["fps"].to(dev))
+    unc = dict(y=d["y_neg"].to(dev, non_blocking=True), camera_data=cam, fps=d["fps"].to(dev))
+    if kind == "i2v":
+        li = d["local_image"].to(dev, non_blocking=True)
+        cond.update(image=d["image"].to(dev, non_blocking=True), local_image=li)
+        unc.update(image=torch.zeros_like(d["image"]).to(dev), local_image=li)   # use_zero_infer (i2vgen entrance :128,268)
+    return [cond, unc]
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_reference(args, kind, hw, tflop_fwd):
+    """CPU arm: the oracle port of the reference UNet on the host cores, bounded sample, same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import unet_oracle
+    from videomv_b200 import synth, unet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = dict(T2V_KWARGS, use_lgm_refine=False)
+    cls = unet.UNetSD_T2VBase if kind == "t2v" else unet.UNetSD_I2VGen
+    if kind == "i2v":
+        kw = dict(kw, concat_dim=4)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in cls(**kw).state_dict().items()}
+    t0 = time.time()
+    sd = synth.synth_state_dict(shapes, seed=0)
+    t_w = time.time() - t0
+    d = make_host_inputs(kind, hw, seed=11)
+
+    def fwd(frames):
+        x = d["noise"][:, :, :frames].contiguous()
+        t = torch.tensor([981])
+        cam = d["cam"][:, :frames]
+        t0 = time.time()
+        if kind == "t2v":
+            unet_oracle.unet_t2v_forward(sd, x, t, d["y"], cam)
+        else:
+            unet_oracle.unet_i2v_forward(sd, x, t, d["y"], d["image"], d["local_image"][:, :, :frames], cam, fps=d["fps"])
+        return time.time() - t0
+
+    # bounded sample: probe with 4 frames; use full 24-frame forwards only if the whole run stays within ~4 minutes
+    t4 = fwd(4)
+    n = args.steps + args.warmup
+    frames = FRAMES if t4 * 6 * n < 240 else 4
+    scale = FRAMES / frames
+    times = [fwd(frames) for _ in range(n)][args.warmup:]
+    t_fwd = sum(times) / len(times) * scale                      # one 24-frame UNet forward
+    t_sample = t_fwd * 2 * DDIM_STEPS
+    value = FRAMES / t_sample
+    sample = (f"{len(times)} oracle forward(s) of 1x4x{frames}x{hw}x{hw} (fp32, {cores} threads), scaled x{scale:g} "
+              f"to 24 frames, x100 to a 50-step CFG sample; weights generated in {t_w:.0f}s")
+    line = {"impl": "reference", "metric": "multi-view frames/sec (24-view, 50-step DDIM, CFG)", "value": value,
+            "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": t_sample * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "fp32", "data": "synthetic",
+            "config": {"workload": args.workload, "frames": FRAMES, "latent": [4, FRAMES, hw, hw], "ddim_steps": DDIM_STEPS,
+                       "guidance": "cfg"},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------------------------
+def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
+    import torch.distributed as dist
+    from videomv_b200 import ops, synth, unet
+    from videomv_b200.sampler import DiffusionDDIM
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the native arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    unet.register_with_reference()                       # no-op on the GPU box (reference tree absent)
+    cls = unet.UNetSD_T2VBase if kind == "t2v" else unet.UNetSD_I2VGen
+    kw = dict(T2V_KWARGS) if kind == "t2v" else dict(T2V_KWARGS, concat_dim=4)
+    with torch.device(dev):
+        model = cls(**kw)
+    synth.fill_module_fast(model, seed=rank)
+    model.eval()
+    model.enable_cuda_graphs(not args.no_graphs)
+    diffusion = DiffusionDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085,
+                              last_beta=0.0120, zero_terminal_snr=False), mean_type=mean_type, var_type="fixed_small")
+    host = make_host_inputs(kind, hw, seed=11 + rank)    # yaml seed 11, + rank like the reference engine (:79)
+
+    def sample_from_host():
+        noise = host["noise"].to(dev, non_blocking=True)
+        kwargs = to_kwargs(kind, host, dev)
+        out = diffusion.ddim_sample_loop(noise, model, model_kwargs=kwargs, guide_scale=gs, ddim_timesteps=DDIM_STEPS,
+                                         eta=0.0, batch_cfg=not args.two_call)
+        return out.to("cpu", non_blocking=False)
+
+    dev_noise = host["noise"].to(dev)
+    dev_kwargs = to_kwargs(kind, host, dev)
+
+    def sample_resident():
+        return diffusion.ddim_sample_loop(dev_noise, model, model_kwargs=dev_kwargs, guide_scale=gs,
+                                          ddim_timesteps=DDIM_STEPS, eta=0.0, batch_cfg=not args.two_call)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        sample_resident()
+    sample_from_host()
+    n0 = ops.launch_count()
+    r0 = sum(getattr(g, "replays", 0) for g in model._engine()._graphs.values())
+    clocks = ClockSampler(local)
+    clocks.start()
+    ms = timed(sample_resident, args.steps)
+    clk = clocks.stop()
+    eager_launches = ops.launch_count() - n0
+    replays = sum(getattr(g, "replays", 0) for g in model._engine()._graphs.values()) - r0
+    per_replay = max([g.launches for g in model._engine()._graphs.values()] or [0])
+    launches = eager_launches + replays * per_replay
+    ms_e2e = timed(sample_from_host, args.steps)
+
+    value = FRAMES * args.steps * world / (ms / 1e3)
+    e2e_value = FRAMES * args.steps * world / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k not in ("cam", "fps"))
+    d2h = host["noise"].numel() * 4
+
+    line = {"metric": "multi-view frames/sec (24-view, 50-step DDIM, CFG)", "value": value, "unit": "frames/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16 (fp32 accumulate)",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "model": cls.__name__ + " 1.41B (configs/t2v_infer.yaml)" if kind == "t2v"
+                       else cls.__name__ + " (configs/i2vgen_xl_infer.yaml)",
+                       "frames": FRAMES, "latent": [4, FRAMES, hw, hw], "ddim_steps": DDIM_STEPS,
+                       "guidance": f"cfg {gs}, cond+uncond as one batch-2 UNet call" if not args.two_call else f"cfg {gs}, two calls",
+                       "parallelism": f"replicas x{world} (one sample per GPU, no collective)",
+                       "cuda_graphs": not args.no_graphs,
+                       "l2": "working set > L2: 2.83 GB of fp16 weights streamed per UNet call (no explicit flush)"},
+            "clocks": clk,
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches)}
+
+    if rank == 0:
+        # ---- roofline leg: one instrumented (eager, per-launch CUDA events) CFG-batched forward
+        pk = _peaks()
+        model.enable_cuda_graphs(False)
+        xt = dev_noise
+        t = torch.full((1,), 981, dtype=torch.long, device=dev)
+        for _ in range(2):
+            model.forward_cfg_pair(xt, t, dev_kwargs[0], dev_kwargs[1])
+        ops.PROFILE = []
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        model.forward_cfg_pair(xt, t, dev_kwargs[0], dev_kwargs[1])
+        ev1.record()
+        torch.cuda.synchronize()
+        prof, ops.PROFILE = ops.PROFILE, None
+        fam = {}
+        for name, fl, by, a, b in prof:
+            f = fam.setdefault(name, [0, 0.0, 0.0, 0.0])
+            f[0] += 1; f[1] += fl; f[2] += by; f[3] += a.elapsed_time(b)
+        g = fam.get("gemm_tc", [0, 0.0, 0.0, 1e-9])
+        achieved = g[1] / (g[3] * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,STAGES> (tcgen05 GEMM / implicit conv family)",
+                            "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
+                            "traffic": None, "peak_source": pk["src"] + " bf16_tflops_sustained",
+                            "launches_per_forward": g[0], "algorithmic_tflop_per_forward_b2": g[1] / 1e12,
+                            "kernel_ms_per_forward_b2": g[3]}
+        line["breakdown_ms_per_forward_b2"] = {k: round(v[3], 3) for k, v in fam.items()}
+        line["breakdown_ms_per_forward_b2"]["eager_wall_total"] = round(ev0.elapsed_time(ev1), 3)
+        hb = {k: v for k, v in fam.items() if k in ("groupnorm", "layernorm")}
+        if hb:
+            by = sum(v[2] for v in hb.values()); tms = sum(v[3] for v in hb.values())
+            line["roofline_hbm_norms"] = {"bound": "hbm", "achieved": by / (tms * 1e-3) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                                          "frac": by / (tms * 1e-3) / 1e9 / pk["hbm"]}
+        t_fwd_alg = 2 * tflop_fwd                               # cond + uncond
+        line["forward_tflops"] = {"algorithmic_tflop_per_step": t_fwd_alg * DDIM_STEPS,
+                                  "achieved_tflops": t_fwd_alg * DDIM_STEPS * args.steps / (ms / 1e3) * 1.0,
+                                  "frac_of_peak": t_fwd_alg * DDIM_STEPS * args.steps / (ms / 1e3) / pk["tflops"]}
+        # ---- cpu baseline leg (N=1 only): bounded oracle sample on the host cores
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(kind, hw)
+            except Exception as e:  # noqa: BLE001
+                line["cpu_baseline"] = {"error": repr(e)}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def cpu_baseline(kind, hw):
+    from oracle import unet_oracle
+    from videomv_b200 import synth, unet
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    kw = dict(T2V_KWARGS, use_lgm_refine=False)
+    cls = unet.UNetSD_T2VBase if kind == "t2v" else unet.UNetSD_I2VGen
+    if kind == "i2v":
+        kw = dict(kw, concat_dim=4)
+    with torch.device("meta"):
+        shapes = {k: tuple(v.shape) for k, v in cls(**kw).state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed=0)
+    d = make_host_inputs(kind, hw, seed=11)
+    frames = 4                                                      # bounded sample: 4 of 24 frames, one forward
+    x, cam, t = d["noise"][:, :, :frames].contiguous(), d["cam"][:, :frames], torch.tensor([981])
+    best = None
+    for _ in range(2):
+        t0 = time.time()
+        if kind == "t2v":
+            unet_oracle.unet_t2v_forward(sd, x, t, d["y"], cam)
+        else:
+            unet_oracle.unet_i2v_forward(sd, x, t, d["y"], d["image"], d["local_image"][:, :, :frames], cam, fps=d["fps"])
+        dt = time.time() - t0
+        best = dt if best is None else min(best, dt)
+    t_sample = best * (FRAMES / frames) * 2 * DDIM_STEPS
+    return {"value": FRAMES / t_sample, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"best of 2 oracle UNet forwards of 1x4x{frames}x{hw}x{hw} fp32 ({best:.2f}s), x{FRAMES // frames} frames x100 calls"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="t2v256", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-graphs", action="store_true")
+    ap.add_argument("--two-call", action="store_true", help="cond and uncond as two B=1 UNet calls (reference call pattern)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    kind, hw, gs, mean_type, tflop = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference(args, kind, hw, tflop)
+    else:
+        run_native(args, kind, hw, gs, mean_type, tflop)
+
+
+if __name__ == "__main__":
+    main()

@@ -141,10 +141,13 @@ int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out
  * that opens every ResBlock.emb_layers, util.py:665).  fp16 in/out. */
 int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, const void* cam_emb, int32_t B, int32_t F,
                            int32_t E, void* out, void* stream);
-/* classifier-free guidance + DDIM update (diffusion_ddim.py:157-160,193-195,233-243), eta = 0:
- *   eps = u + s*(y-u);  x0 = c_recip*xt - c_recipm1*eps (clamped if clamp>0);  x_prev = sqrt(a_prev)*x0 + sqrt(1-a_prev)*eps'
- * all tensors fp32, n elements. coef = {sqrt_recip_ac, sqrt_recipm1_ac, sqrt_ac_prev, sqrt_1m_ac_prev, guide_scale} */
-int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef5, int64_t n,
+/* classifier-free guidance + DDIM update (diffusion_ddim.py:157-160,193-199,233-243), eta = 0, one launch:
+ *   out    = u + s*(y-u)                         (y == u and s == 1 when there is no guidance)
+ *   x0     = kx*xt - ko*out                      (eps-pred: kx=sqrt(1/ac), ko=sqrt(1/ac-1); v-pred: kx=sqrt(ac), ko=sqrt(1-ac))
+ *   eps    = (sqrt(1/ac)*xt - x0) / sqrt(1/ac-1)
+ *   x_prev = sqrt(ac_prev)*x0 + sqrt(1-ac_prev)*eps
+ * all tensors fp32, n elements; coef7 (device) = {kx, ko, sqrt(1/ac), sqrt(1/ac-1), sqrt(ac_prev), sqrt(1-ac_prev), s} */
+int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef7, int64_t n,
                       float* x_prev, void* stream);
 
 /* sizeof() of the two parameter structs as compiled, so a foreign-language binding can verify its mirror. */

@@ -85,8 +85,43 @@ def make_case(name, kind, kwargs, frames, hw, seed_w, seed_x, t_value, real_cam=
     del model
 
 
+def make_ddim_case():
+    """Pin oracle/ddim_oracle.py against the reference DiffusionDDIM (imported unmodified) with a closed-form model."""
+    import importlib.util
+    from oracle import ddim_oracle
+    ref_import.load_reference()          # sets sys.path / stubs
+    pk = "tools.modules.diffusions"
+    import types
+    if pk not in sys.modules:
+        m = types.ModuleType(pk); m.__path__ = [os.path.join(ref_import.REF_ROOT, "tools/modules/diffusions")]
+        sys.modules[pk] = m
+    for name in ("schedules", "losses", "diffusion_ddim"):
+        spec = importlib.util.spec_from_file_location(f"{pk}.{name}", os.path.join(ref_import.REF_ROOT, "tools/modules/diffusions", name + ".py"))
+        mod = importlib.util.module_from_spec(spec); sys.modules[f"{pk}.{name}"] = mod; spec.loader.exec_module(mod)
+    RefDDIM = sys.modules[f"{pk}.diffusion_ddim"].DiffusionDDIM
+    g = torch.Generator().manual_seed(5)
+    noise = torch.randn(1, 4, 6, 8, 8, generator=g)
+    yc, yu = torch.randn(1, 77, 16, generator=g), torch.randn(1, 77, 16, generator=g)
+    out = {}
+    for mean_type, gs in (("eps", 9.0), ("v", 6.0)):
+        ref = RefDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.0120,
+                      zero_terminal_snr=False), mean_type=mean_type, var_type="fixed_small", loss_type="mse")
+        fm = lambda x, t, **kw: ddim_oracle.fake_model(x, t, y=kw["y"])
+        r = ref.ddim_sample_loop(noise.clone(), fm, model_kwargs=[dict(y=yc), dict(y=yu)], guide_scale=gs,
+                                 ddim_timesteps=50, eta=0.0)
+        o = ddim_oracle.DDIMOracle(mean_type=mean_type).ddim_sample_loop(noise.clone(), fm, [dict(y=yc), dict(y=yu)], gs, 50)
+        err = (r - o).abs().max().item()
+        print(f"[ddim_fake {mean_type}] max|oracle-ref|={err:.3e} max|ref|={r.abs().max().item():.3f}")
+        assert err < 1e-5
+        out[mean_type] = r.numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "ddim_fake.npz"), noise=noise.numpy(), yc=yc.numpy(), yu=yu.numpy(),
+                        eps=out["eps"], v=out["v"])
+
+
 def main():
     which = sys.argv[1:] or ["small", "full"]
+    if "ddim" in which:
+        make_ddim_case()
     if "small" in which:
         make_case("t2v_small", "t2v", ref_import.SMALL_KWARGS, frames=4, hw=16, seed_w=3, seed_x=1, t_value=500)
         make_case("t2v_small_t981_cam", "t2v", ref_import.SMALL_KWARGS, frames=24, hw=8, seed_w=3, seed_x=2,

@@ -161,9 +161,10 @@ def test_embeddings_and_ddim():
     assert_close("embed_combine", o, ref)
     xt, y, u = (torch.randn(1, 4, 24, 32, 32, device="cuda") for _ in range(3))
     a_t, a_prev, gs = 0.37, 0.52, 9.0
-    coef = torch.tensor([a_t ** -0.5, (1 / a_t - 1) ** 0.5, a_prev ** 0.5, (1 - a_prev) ** 0.5, gs], device="cuda")
+    coef = torch.tensor([a_t ** -0.5, (1 / a_t - 1) ** 0.5, a_t ** -0.5, (1 / a_t - 1) ** 0.5, a_prev ** 0.5,
+                         (1 - a_prev) ** 0.5, gs], device="cuda")
     xp = ops.cfg_ddim_step(xt, y, u, coef)
     eps = u + gs * (y - u)
     x0 = coef[0] * xt - coef[1] * eps
-    ref = a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * ((coef[0] * xt - x0) / coef[1])
+    ref = a_prev ** 0.5 * x0 + (1 - a_prev) ** 0.5 * ((coef[2] * xt - x0) / coef[3])
     assert_close("cfg_ddim", xp, ref, rtol=1e-5, atol=1e-5)

@@ -169,10 +169,11 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
                                 const float* __restrict__ coef, long long n, float* __restrict__ xprev) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float c_recip = coef[0], c_recipm1 = coef[1], sa_prev = coef[2], s1a_prev = coef[3], gs = coef[4];
+    const float kx = coef[0], ko = coef[1], c_recip = coef[2], c_recipm1 = coef[3], sa_prev = coef[4],
+                s1a_prev = coef[5], gs = coef[6];
     const float uu = u[i];
-    const float eps_hat = uu + gs * (y[i] - uu);                   // diffusion_ddim.py:157-160
-    const float x0 = c_recip * xt[i] - c_recipm1 * eps_hat;        // :193-195
+    const float out = uu + gs * (y[i] - uu);                       // diffusion_ddim.py:157-160
+    const float x0 = kx * xt[i] - ko * out;                        // :193-199
     const float eps = (c_recip * xt[i] - x0) / c_recipm1;          // :233-234
     xprev[i] = sa_prev * x0 + s1a_prev * eps;                      // :240-243 (eta = 0)
 }
@@ -252,10 +253,10 @@ extern "C" int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, con
     return VMV_OK;
 }
 
-extern "C" int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef5, int64_t n,
+extern "C" int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef7, int64_t n,
                                  float* x_prev, void* stream) {
-    VMV_CHECK_ARG(xt && y_out && u_out && coef5 && x_prev && n > 0, "vmv_cfg_ddim_step: bad args");
-    cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, y_out, u_out, coef5, n, x_prev);
+    VMV_CHECK_ARG(xt && y_out && u_out && coef7 && x_prev && n > 0, "vmv_cfg_ddim_step: bad args");
+    cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, y_out, u_out, coef7, n, x_prev);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_cfg_ddim_step");
     return VMV_OK;

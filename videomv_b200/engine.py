@@ -304,22 +304,55 @@ class UNetEngine:
     # ------------------------------------------------------------------------------------------------------------
     @torch.no_grad()
     def forward(self, x, t, y, camera_data, fps, image=None, local_image=None):
+        """One UNet evaluation with the reference's tensor conventions: x [B,C,F,h,w],
+        t [B] int64, y [B,L,1024], camera_data [B,F,16] (may arrive on CPU), fps [B] int64."""
         if x.dim() != 5:
             raise ValueError("videomv_b200: x must be [B, C, F, h, w]")
         dev = self.device
         out_dtype = x.dtype
-        B, _, Fr, H, W = x.shape
         x32 = x.detach().to(device=dev, dtype=torch.float32).contiguous()
-        t = t.to(dev)
-        y = y.to(dev)
-        cam = None if camera_data is None else camera_data.to(device=dev, dtype=torch.float32)   # arrives on CPU in the
-        fps = None if fps is None else fps.to(dev)                                               # reference engine
-        S = {"B": B, "F": Fr, "H": H, "W": W, "x_in": x32}
+        t = t.to(device=dev, dtype=torch.int64).contiguous()
+        cam = None if camera_data is None else camera_data.to(device=dev, dtype=torch.float32).contiguous()
+        fps = None if fps is None else fps.to(device=dev, dtype=torch.int64).contiguous()
+        ctx, concat = self.prepare_condition(x32.shape, y, image, local_image)
+        out = self.forward_core(x32, t, ctx, cam, fps, concat)
+        return out if out_dtype == torch.float32 else out.to(out_dtype)
+
+    def prepare_condition(self, xshape, y, image=None, local_image=None):
+        """Step-invariant conditioning: context tokens [B,L,1024] fp32 (+ the I2V concat planes). Cached on the
+        identity of the caller's tensors, which the sampler passes unchanged for all 50 steps."""
+        key = tuple((id(z), z.data_ptr(), z._version, tuple(z.shape)) if z is not None else None
+                    for z in (y, image, local_image)) + (tuple(xshape),)
+        hit = self._ctx_cache.get(key)
+        if hit is not None:
+            return hit
+        dev = self.device
         if self.variant == "i2v":
-            concat, ctx = self._i2v_condition(x32, y, image, local_image)
-            S["x_in2"] = concat
+            concat, ctx = self._i2v_condition(xshape, y.to(dev), image, local_image)
         else:
-            ctx = y
+            concat, ctx = None, y.to(device=dev, dtype=torch.float32)
+        ctx = ctx.contiguous()
+        if len(self._ctx_cache) >= 8:
+            self._ctx_cache.clear()
+        self._ctx_cache[key] = (ctx, concat)
+        return ctx, concat
+
+    def forward_core(self, x32, t, ctx, cam, fps, concat):
+        """The per-step hot path on device-resident inputs. Replays a captured CUDA graph when enabled."""
+        if not self.use_graphs:
+            return self._forward_impl(x32, t, ctx, cam, fps, concat)
+        key = (tuple(x32.shape), tuple(ctx.shape), cam is not None, fps is not None, concat is not None)
+        g = self._graphs.get(key)
+        if g is None:
+            g = _Graph(self, x32, t, ctx, cam, fps, concat)
+            self._graphs[key] = g
+        return g.run(x32, t, ctx, cam, fps, concat)
+
+    def _forward_impl(self, x32, t, ctx, cam, fps, concat):
+        B, _, Fr, H, W = x32.shape
+        S = {"B": B, "F": Fr, "H": H, "W": W, "x_in": x32}
+        if concat is not None:
+            S["x_in2"] = concat
         S["emb_all"] = self._embeddings(t, fps, cam, B, Fr)
         S["kv_all"], S["L"] = self._context_kv(ctx)
         skips = []
@@ -332,18 +365,17 @@ class UNetEngine:
         for blk in self.dec:
             h = self._run_block(blk, h, skips.pop(), S)
         a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True)
-        out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
-        return out if out_dtype == torch.float32 else out.to(out_dtype)
+        return ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
 
     # ------------------------------------------------------------------------------------------------------------
     # I2V conditioning glue (step-invariant; depends only on local_image / image / y)
     # ------------------------------------------------------------------------------------------------------------
-    def _i2v_condition(self, x32, y, image, local_image):
+    def _i2v_condition(self, xshape, y, image, local_image):
         """unet_i2vgen.py:314-346 (concat branch) and :361-382 (context).  Tiny 4..32-channel convolutions and a
         2-head d=4 transformer over frames whose inputs do not change across the 50 DDIM steps: evaluated with torch
         ops as host-side glue (like the VAE/CLIP), not part of the per-step hot path."""
         m = self.m
-        B, _, Fr, H, W = x32.shape
+        B, _, Fr, H, W = xshape
         li = local_image.to(device=self.device, dtype=torch.float32)
         if li.ndim == 5 and li.size(2) > 1:
             li = li[:, :, :1]
@@ -388,3 +420,33 @@ class UNetEngine:
             ic = run_seq(m.context_embedding, image.to(device=self.device, dtype=torch.float32))
             ctx = torch.cat([ctx, ic.view(-1, m.num_tokens, m.context_dim)], dim=1)
         return concat, ctx
+
+
+class _Graph:
+    """One captured CUDA graph of `_forward_impl` for a fixed set of shapes; inputs are copied into static buffers.
+    Every library launch lands on the capturing stream (ops._stream), TMA descriptors are baked into the kernel
+    parameters, and all intermediates live in the graph's private memory pool."""
+
+    def __init__(self, eng: UNetEngine, *inputs):
+        self.static = [None if z is None else z.clone() for z in inputs]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):                      # warm up: func attributes, workspace, allocator
+                eng._forward_impl(*self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        n0 = ops.launch_count()
+        with torch.cuda.graph(self.graph):
+            self.out = eng._forward_impl(*self.static)
+        self.launches = ops.launch_count() - n0     # kernels per replay (bench `gpu_launches`)
+
+    def run(self, *inputs):
+        self.replays = getattr(self, "replays", 0) + 1
+        for dst, src in zip(self.static, inputs):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self.graph.replay()
+        return self.out.clone()

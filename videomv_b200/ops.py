@@ -16,6 +16,25 @@ from ._lib import AttnParams, GemmParams, check
 LINEAR, CONV3X3, TCONV3 = 0, 1, 2
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 
+# Optional per-call timing hook (bench.py roofline leg): when set to a list, every op appends
+# (kernel family, algorithmic FLOPs, algorithmic bytes, start event, end event).
+PROFILE = None
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    e = torch.cuda.Event(enable_timing=True)
+    e.record()
+    return e
+
+
+def _prof_end(e0, family, flops, nbytes):
+    if e0 is not None:
+        e1 = torch.cuda.Event(enable_timing=True)
+        e1.record()
+        PROFILE.append((family, flops, nbytes, e0, e1))
+
 
 def _stream() -> int:
     return torch.cuda.current_stream().cuda_stream
@@ -77,7 +96,11 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         if workspace is None or workspace.numel() * workspace.element_size() < need:
             workspace = torch.empty(max(need, 16), dtype=torch.uint8, device=a1.device)
         p.workspace, p.workspace_bytes = workspace.data_ptr(), workspace.numel() * workspace.element_size()
+    e0 = _prof_begin()
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
+    if e0 is not None:
+        ktot = w.shape[1]
+        _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out))
     return out
 
 
@@ -100,11 +123,13 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
         out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
     L = _lib.lib()
     st = _stream()
+    e0 = _prof_begin()
     check(L.vmv_groupnorm_stats(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
                                 rows_per_batch, nbatch, stats.data_ptr(), st), "vmv_groupnorm_stats")
     check(L.vmv_groupnorm_apply(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
                                 rows_per_batch, nbatch, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
                                 float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
+    _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))     # stats read + apply read + write
     return out
 
 
@@ -113,9 +138,11 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
     _rows(x, "layernorm x")
     if out is None:
         out = torch.empty_like(x)
+    e0 = _prof_begin()
     check(_lib.lib().vmv_layernorm(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], gamma.data_ptr(),
                                    beta.data_ptr(), float(eps), out.data_ptr(), out.stride(0), _stream()),
           "vmv_layernorm")
+    _prof_end(e0, "layernorm", 0.0, 2.0 * 2 * x.shape[0] * x.shape[1])
     return out
 
 
@@ -132,7 +159,10 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.v_bs_outer, p.v_bs_inner, p.v_rs = v_strides
     p.o_bs_outer, p.o_bs_inner, p.o_rs = o_strides
     p.kv_group, p.scale = kv_group, scale
+    e0 = _prof_begin()
     check(_lib.lib().vmv_attention(ctypes.byref(p), _stream()), "vmv_attention")
+    nb = outer * inner * heads
+    _prof_end(e0, "attention", 4.0 * nb * nq * nk * 64, 2.0 * 64 * nb * (2 * nq + 2 * nk / kv_group))
     return out
 
 
@@ -200,13 +230,13 @@ def embed_combine_silu(t_emb: torch.Tensor, t_emb2: Optional[torch.Tensor], cam_
     return out
 
 
-def cfg_ddim_step(xt: torch.Tensor, y_out: torch.Tensor, u_out: torch.Tensor, coef5: torch.Tensor,
+def cfg_ddim_step(xt: torch.Tensor, y_out: torch.Tensor, u_out: torch.Tensor, coef7: torch.Tensor,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     for t in (xt, y_out, u_out):
         assert t.dtype == torch.float32 and t.is_contiguous() and t.is_cuda
     if out is None:
         out = torch.empty_like(xt)
-    check(_lib.lib().vmv_cfg_ddim_step(xt.data_ptr(), y_out.data_ptr(), u_out.data_ptr(), coef5.data_ptr(),
+    check(_lib.lib().vmv_cfg_ddim_step(xt.data_ptr(), y_out.data_ptr(), u_out.data_ptr(), coef7.data_ptr(),
                                        xt.numel(), out.data_ptr(), _stream()), "vmv_cfg_ddim_step")
     return out
 

@@ -43,6 +43,20 @@ def synth_state_dict(shapes: Mapping[str, Iterable[int]], seed: int = 0) -> Dict
     return {k: synth_tensor(k, tuple(v), seed) for k, v in shapes.items()}
 
 
+def fill_module_fast(module: torch.nn.Module, seed: int = 0, gain: float = 0.7) -> None:
+    """Same distribution as synth_state_dict but generated on the module's own device (seconds instead of a minute
+    for 1.4 B parameters). Values differ from the CPU recipe; use it where only the distribution matters (bench)."""
+    with torch.no_grad():
+        for name, p in module.state_dict().items():
+            g = torch.Generator(device=p.device)
+            g.manual_seed((zlib.crc32(name.encode()) ^ (seed * 0x9E3779B1)) & 0x7FFFFFFF)
+            r = torch.randn(p.shape, generator=g, device=p.device, dtype=torch.float32)
+            if p.dim() == 1:
+                p.copy_(1.0 + 0.1 * r if name.endswith(".weight") else 0.05 * r)
+            else:
+                p.copy_(r * (gain / math.sqrt(p[0].numel())))
+
+
 def synth_inputs(batch: int, frames: int, h: int, w: int, ctx_len: int = 77, ctx_dim: int = 1024,
                  in_dim: int = 4, seed: int = 1, t_value: int = 500):
     """Random (x, t, y, camera_data) shaped like the sampler's call (diffusion_ddim.py:149-155)."""

@@ -245,6 +245,52 @@ class _VideoUNetBase(nn.Module):
         self.invalidate_engine()
         return super().load_state_dict(state_dict, strict=strict, **k)
 
+    def enable_cuda_graphs(self, on: bool = True):
+        """Replay the whole forward as one CUDA graph per input-shape set (kills ~1.2k launch overheads per call)."""
+        self._engine().use_graphs = bool(on)
+        return self
+
+    def graph_launches(self) -> int:
+        """Kernels per graph replay, summed over captured graphs (0 when none)."""
+        eng = self.__dict__.get("_eng")
+        return 0 if eng is None else sum(g.launches for g in eng._graphs.values())
+
+    @torch.no_grad()
+    def forward_cfg_pair(self, x, t, kw_cond, kw_uncond):
+        """Classifier-free-guidance pair (diffusion_ddim.py:149-155) as ONE batch-2B evaluation: rows [0,B) use the
+        conditional kwargs, rows [B,2B) the unconditional ones. Per-sample arithmetic is unchanged (all norms and
+        attentions are per sample). Returns (y_out, u_out) fp32."""
+        eng = self._engine()
+        b = x.shape[0]
+        key = tuple((k, id(v), getattr(v, "_version", 0)) for kw in (kw_cond, kw_uncond) for k, v in sorted(kw.items())
+                    if torch.is_tensor(v)) + (tuple(x.shape),)
+        cache = self.__dict__.setdefault("_pair_cache", {})
+        hit = cache.get(key)
+        if hit is None:
+            def both(name, dtype=None):
+                a, c = kw_cond.get(name), kw_uncond.get(name)
+                if a is None or c is None:
+                    return None
+                z = torch.cat([a.to(eng.device), c.to(eng.device)], dim=0)
+                return z if dtype is None else z.to(dtype)
+            y2 = both("y")
+            if y2 is None:
+                raise ValueError("videomv_b200: forward_cfg_pair needs `y` in both kwargs dicts")
+            cam2 = both("camera_data", torch.float32) if self.use_camera_condition else None
+            fps2 = both("fps", torch.int64) if (self.use_fps_condition or self.variant == "i2v") else None
+            img2, loc2 = both("image"), both("local_image")
+            ctx, concat = eng.prepare_condition((2 * b,) + tuple(x.shape[1:]), y2, img2, loc2)
+            hit = (ctx, None if cam2 is None else cam2.contiguous(), None if fps2 is None else fps2.contiguous(), concat,
+                   (y2, img2, loc2))                 # keep the cat'ed tensors alive: prepare_condition keys on them
+            if len(cache) >= 4:
+                cache.clear()
+            cache[key] = hit
+        ctx, cam2, fps2, concat, _ = hit
+        x2 = torch.cat([x, x], dim=0).to(device=eng.device, dtype=torch.float32).contiguous()
+        t2 = torch.cat([t, t], dim=0).to(device=eng.device, dtype=torch.int64).contiguous()
+        out = eng.forward_core(x2, t2, ctx, cam2, fps2, concat)
+        return out[:b].contiguous(), out[b:].contiguous()
+
     def _check_call(self, x, masked, autoencoder, x0):
         assert self.inpainting or masked is None, "inpainting is not supported"
         if autoencoder is not None or x0 is not None:
