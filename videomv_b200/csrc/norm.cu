@@ -61,8 +61,7 @@ gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
         float s[8], q[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-        for (long long r = r_begin + ty; r < r_end; r += lanes) {
-            uint4 u = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+        auto acc = [&](const uint4& u) {
             uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -70,7 +69,16 @@ gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
                 s[2 * j] += f.x; q[2 * j] += f.x * f.x;
                 s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
             }
+        };
+        long long r = r_begin + ty;
+        for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {       // 4 independent 16B loads in flight per thread
+            uint4 u0 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+            uint4 u1 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0));
+            uint4 u2 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0));
+            uint4 u3 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0));
+            acc(u0); acc(u1); acc(u2); acc(u3);
         }
+        for (; r < r_end; r += lanes) acc(__ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0)));
         // fold the 8 channels into their groups (a vector may straddle two groups)
         int g_prev = c0 / cpg;
         float as = 0.f, aq = 0.f;
@@ -128,8 +136,7 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     long long r_end = r_begin + rows_per_cta;
     if (r_end > rows_per_batch) r_end = rows_per_batch;
     const long long base = (long long)batch * rows_per_batch;
-    for (long long r = r_begin + ty; r < r_end; r += lanes) {
-        uint4 u = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+    auto apply = [&](const uint4& u, long long r) {
         uint32_t w[4] = {u.x, u.y, u.z, u.w};
         uint32_t o[4];
 #pragma unroll
@@ -141,7 +148,16 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
             o[j] = pack_half2(a, b);
         }
         *reinterpret_cast<uint4*>(out + (base + r) * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    long long r = r_begin + ty;
+    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+        uint4 u0 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+        uint4 u1 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0));
+        uint4 u2 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0));
+        uint4 u3 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0));
+        apply(u0, r); apply(u1, r + lanes); apply(u2, r + 2LL * lanes); apply(u3, r + 3LL * lanes);
     }
+    for (; r < r_end; r += lanes) apply(__ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0)), r);
 }
 
 // One warp per row; the row lives in registers (<= 8 vectors of 8 halfs per lane => C <= 2048).
