@@ -67,9 +67,10 @@ typedef struct vmv_gemm_params {
     const void* residual; int64_t ldr;                                /* fp16 [M, N_out] or NULL */
     int32_t act;
     /* tuning (0 = auto) */
-    int32_t block_n;            /* 64, 128, 160 or 256 */
+    int32_t block_n;            /* 64 (variant 1 only), 128, 160 or 256 */
     int32_t stages;             /* smem pipeline depth */
     int32_t split_k;            /* >1: K split across CTAs, fp32 partials in workspace, reduced by a 2nd kernel */
+    int32_t variant;            /* 0 auto | 1 one tile per CTA (cta_group::1) | 2 persistent CTA pairs (cta_group::2) */
     void* workspace; int64_t workspace_bytes;
 } vmv_gemm_params;
 

@@ -8,6 +8,12 @@ from tests.util import assert_close
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[1, 2], ids=["cta1", "cta2-persistent"])
+def variant(request):
+    """1 = one tile per CTA (cta_group::1); 2 = persistent CTA pairs (cta_group::2, double-buffered TMEM)."""
+    return request.param
+
+
 def _r(*shape, scale=1.0, seed=0):
     g = torch.Generator(device="cuda").manual_seed(seed)
     return (torch.randn(*shape, generator=g, device="cuda") * scale).half()
@@ -17,17 +23,18 @@ def _r(*shape, scale=1.0, seed=0):
     (128, 128, 64, 128, 3), (128, 160, 64, 160, 3), (256, 320, 320, 0, 0), (24576, 320, 320, 0, 0),
     (384, 1280, 1280, 0, 0), (1000, 512, 320, 0, 0), (24, 1280, 320, 0, 0), (1536, 1280, 1280, 160, 6),
     (300, 64, 128, 64, 0), (512, 256, 2560, 256, 0), (6144, 640, 640, 128, 6),
+    (49152, 320, 320, 0, 0), (49152, 2560, 320, 0, 0), (385, 480, 1280, 0, 0), (129, 160, 4096, 0, 0),
 ])
-def test_linear(M, N, K, bn, stages):
+def test_linear(M, N, K, bn, stages, variant):
     from videomv_b200 import ops
     a, w = _r(M, K, seed=1), _r(N, K, scale=K ** -0.5, seed=2)
     bias = torch.randn(N, device="cuda")
-    out = ops.gemm(a, w, bias=bias, block_n=bn, stages=stages)
+    out = ops.gemm(a, w, bias=bias, block_n=bn, stages=stages, variant=variant)
     ref = a.float() @ w.float().t() + bias
     assert_close(f"linear M{M} N{N} K{K} bn{bn}", out, ref)
 
 
-def test_linear_dual_source_residual_rowbias():
+def test_linear_dual_source_residual_rowbias(variant):
     from videomv_b200 import ops
     M, N, K1, K2, rpg = 6144, 640, 1280, 640, 256
     a1, a2 = _r(M, K1, seed=1), _r(M, K2, seed=2)
@@ -35,33 +42,33 @@ def test_linear_dual_source_residual_rowbias():
     bias = torch.randn(N, device="cuda")
     res = _r(M, N, seed=4)
     rb = _r(M // rpg, N, seed=5)
-    out = ops.gemm(a1, w, a2=a2, bias=bias, residual=res, rowbias=rb, rows_per_group=rpg)
+    out = ops.gemm(a1, w, a2=a2, bias=bias, residual=res, rowbias=rb, rows_per_group=rpg, variant=variant)
     ref = torch.cat([a1, a2], 1).float() @ w.float().t() + bias + rb.float().repeat_interleave(rpg, 0) + res.float()
     assert_close("linear dual+res+rowbias", out, ref)
 
 
-def test_linear_silu_and_strided_views():
+def test_linear_silu_and_strided_views(variant):
     from videomv_b200 import ops
     M, N, K = 500, 320, 192
     big_a = _r(M, 3 * K, seed=1)
     a = big_a[:, K:2 * K]                      # strided view (lda = 3K)
     w = _r(N, K, scale=K ** -0.5, seed=2)
     big_out = torch.zeros(M, 2 * N, dtype=torch.float16, device="cuda")
-    ops.gemm(a, w, out=big_out[:, N:], act=ops.ACT_SILU)
+    ops.gemm(a, w, out=big_out[:, N:], act=ops.ACT_SILU, variant=variant)
     ref = F.silu(a.float() @ w.float().t())
     assert_close("linear silu strided", big_out[:, N:], ref)
     assert (big_out[:, :N] == 0).all()
 
 
 @pytest.mark.parametrize("C", [320, 512])
-def test_geglu(C):
+def test_geglu(C, variant):
     from videomv_b200 import ops, packing
     M = 1024
     a = _r(M, C, seed=1)
     w = torch.randn(8 * C, C, device="cuda") * C ** -0.5
     b = torch.randn(8 * C, device="cuda")
     wp, bp, bn = packing.pack_geglu(w, b)
-    out = ops.gemm(a, wp, bias=bp, act=ops.ACT_GEGLU, block_n=bn)
+    out = ops.gemm(a, wp, bias=bp, act=ops.ACT_GEGLU, block_n=bn, variant=variant)
     h = a.float() @ w.half().float().t() + b
     val, gate = h.chunk(2, dim=-1)
     assert_close(f"geglu C{C}", out, val * F.gelu(gate))
@@ -71,14 +78,14 @@ def test_geglu(C):
     (4, 32, 32, 64, 64), (24, 32, 32, 320, 320), (24, 16, 16, 640, 640), (24, 8, 8, 1280, 1280),
     (24, 4, 4, 1280, 1280), (4, 4, 4, 128, 64), (3, 8, 8, 64, 128), (2, 64, 64, 64, 64), (5, 2, 2, 64, 64),
 ])
-def test_conv3x3(NF, H, W, Cin, Cout):
+def test_conv3x3(NF, H, W, Cin, Cout, variant):
     from videomv_b200 import ops, packing
     x = _r(NF * H * W, Cin, seed=1)
     w = torch.randn(Cout, Cin, 3, 3, device="cuda") * (9 * Cin) ** -0.5
     b = torch.randn(Cout, device="cuda")
     rb = _r(NF, Cout, seed=3)
     out = ops.gemm(x, packing.pack_conv3x3(w), bias=b, mode=ops.CONV3X3, geom=(1, NF, H, W), rowbias=rb,
-                   rows_per_group=H * W)
+                   rows_per_group=H * W, variant=variant)
     xi = x.float().reshape(NF, H, W, Cin).permute(0, 3, 1, 2)
     ref = F.conv2d(xi, w.half().float(), b, padding=1) + rb.float()[:, :, None, None]
     ref = ref.permute(0, 2, 3, 1).reshape(NF * H * W, Cout)
@@ -89,26 +96,26 @@ def test_conv3x3(NF, H, W, Cin, Cout):
     (1, 24, 32, 32, 320), (2, 24, 16, 16, 640), (1, 24, 8, 8, 1280), (2, 24, 4, 4, 1280), (1, 4, 4, 4, 64),
     (2, 5, 2, 2, 64), (1, 4, 16, 16, 128),
 ])
-def test_tconv3(B, Fr, H, W, C):
+def test_tconv3(B, Fr, H, W, C, variant):
     from videomv_b200 import ops, packing
     M = B * Fr * H * W
     x = _r(M, C, seed=1)
     w = torch.randn(C, C, 3, 1, 1, device="cuda") * (3 * C) ** -0.5
     b = torch.randn(C, device="cuda")
     res = _r(M, C, seed=2)
-    out = ops.gemm(x, packing.pack_tconv3(w), bias=b, mode=ops.TCONV3, geom=(B, Fr, H, W), residual=res)
+    out = ops.gemm(x, packing.pack_tconv3(w), bias=b, mode=ops.TCONV3, geom=(B, Fr, H, W), residual=res, variant=variant)
     x5 = x.float().reshape(B, Fr, H, W, C).permute(0, 4, 1, 2, 3)
     ref = F.conv3d(x5, w.half().float(), b, padding=(1, 0, 0)).permute(0, 2, 3, 4, 1).reshape(M, C) + res.float()
     assert_close(f"tconv3 B{B} F{Fr} {H}x{W} C{C}", out, ref)
 
 
 @pytest.mark.parametrize("M,N,K,split", [(384, 1280, 11520, 6), (768, 1280, 3840, 4), (130, 64, 640, 3)])
-def test_split_k(M, N, K, split):
+def test_split_k(M, N, K, split, variant):
     from videomv_b200 import ops
     a, w = _r(M, K, seed=1), _r(N, K, scale=K ** -0.5, seed=2)
     bias = torch.randn(N, device="cuda")
     res = _r(M, N, seed=3)
-    out = ops.gemm(a, w, bias=bias, residual=res, split_k=split)
+    out = ops.gemm(a, w, bias=bias, residual=res, split_k=split, variant=variant)
     ref = a.float() @ w.float().t() + bias + res.float()
     assert_close(f"splitk M{M} N{N} K{K} s{split}", out, ref)
 

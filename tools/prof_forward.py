@@ -22,9 +22,13 @@ def main():
     kw = bench.to_kwargs("t2v", host, dev)
     x = host["noise"].to(dev)
     t = torch.full((1,), 981, dtype=torch.long, device=dev)
-    for _ in range(n):
+    for i in range(n):
+        if i == n - 1:                       # profile only the last forward: run ncu with --profile-from-start off
+            torch.cuda.synchronize()
+            torch.cuda.cudart().cudaProfilerStart()
         model.forward_cfg_pair(x, t, kw[0], kw[1])
     torch.cuda.synchronize()
+    torch.cuda.cudart().cudaProfilerStop()
     print("done")
 
 

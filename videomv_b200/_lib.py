@@ -75,7 +75,7 @@ class GemmParams(ctypes.Structure):
         ("B", c_i32), ("F", c_i32), ("H", c_i32), ("Wd", c_i32),
         ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
         ("residual", c_vp), ("ldr", c_i64), ("act", c_i32),
-        ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32),
+        ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32), ("variant", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
 

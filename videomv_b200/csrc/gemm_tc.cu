@@ -17,6 +17,7 @@
 #include "../../include/videomv_b200.h"
 
 #include <mutex>
+#include <stdlib.h>
 #include <string.h>
 
 namespace vmv {
@@ -76,6 +77,135 @@ __device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int m
         int f = tf * a.bf + rf;
         if (f >= a.F) return -1;
         return ((long long)b * a.F + f) * a.HW + (tp * a.bp + rp);
+    }
+}
+
+// Drain one 128 x BN fp32 accumulator tile from TMEM (this thread: one row, `trow` = TMEM address of its lane,
+// column 0 of the tile) through the fused epilogue into global memory.  Warp-uniform control flow around tcgen05.ld.
+template <int BN>
+__device__ __forceinline__ void epilogue_store(const GemmArgs& a, int nt, int split, long long grow, bool valid,
+                                               uint32_t trow) {
+    const int n0 = nt * BN;
+    if (a.partial != nullptr) {
+        // split-K: raw fp32 partial sums, reduced by splitk_finish_kernel
+        float* prow = a.partial + ((long long)split * a.M + (valid ? grow : 0)) * a.N;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            if (n0 + c >= a.N) break;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(trow + c, v);
+            tmem_ld_wait();
+            if (valid) {
+                float4* dst = reinterpret_cast<float4*>(prow + n0 + c);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                         __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            }
+        }
+    } else if (a.act == VMV_ACT_GEGLU) {
+        constexpr int HB = BN / 2;
+        const int o0 = nt * HB;
+#pragma unroll 1
+        for (int c = 0; c < HB; c += 16) {
+            if (n0 + c >= a.N) break;
+            uint32_t v[16], g[16];
+            tmem_ld_32x32b_x16(trow + c, v);
+            tmem_ld_32x32b_x16(trow + HB + c, g);
+            tmem_ld_wait();
+            if (valid) {
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
+                    if (a.bias) {
+                        val += __ldg(a.bias + n0 + c + j);
+                        gate += __ldg(a.bias + n0 + HB + c + j);
+                    }
+                    x[j] = val * gelu_erf_f(gate);
+                }
+                if (a.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + o0 + c);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 u = __ldg(rp + h);
+                        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = unpack_half2(w[j]);
+                            x[8 * h + 2 * j] += f.x;
+                            x[8 * h + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + o0 + c);
+                dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                                   pack_half2(x[6], x[7]));
+                dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
+                                   pack_half2(x[14], x[15]));
+            }
+        }
+    } else {
+        const __half* rb = nullptr;
+        if (a.rowbias && valid) rb = a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 16) {
+            if (n0 + c >= a.N) break;
+            uint32_t v[16];
+            tmem_ld_32x32b_x16(trow + c, v);
+            tmem_ld_wait();
+            if (valid) {
+                const int n = n0 + c;
+                float x[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+                if (a.bias) {
+                    const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        float4 b4 = __ldg(bp + j);
+                        x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                    }
+                }
+                if (rb) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 u = __ldg(rp + h);
+                        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = unpack_half2(w[j]);
+                            x[8 * h + 2 * j] += f.x;
+                            x[8 * h + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                if (a.act == VMV_ACT_SILU) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = silu_f(x[j]);
+                }
+                if (a.residual) {
+                    const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + n);
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        uint4 u = __ldg(rp + h);
+                        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            float2 f = unpack_half2(w[j]);
+                            x[8 * h + 2 * j] += f.x;
+                            x[8 * h + 2 * j + 1] += f.y;
+                        }
+                    }
+                }
+                uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + n);
+                dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                                   pack_half2(x[6], x[7]));
+                dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
+                                   pack_half2(x[14], x[15]));
+            }
+        }
     }
 }
 
@@ -201,137 +331,195 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
         const int q = warp & 3;                 // TMEM lane quarter this warp may access
         const int r = q * 32 + lane;
         const long long grow = tile_row_to_global(a, mt, r);
-        const bool valid = grow >= 0;
         mbar_wait(tmem_full_bar, 0);
         tc_fence_after();
-        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-
-        if (a.partial != nullptr) {
-            // split-K: raw fp32 partial sums, reduced by splitk_finish_kernel
-            float* prow = a.partial + ((long long)split * a.M + (valid ? grow : 0)) * a.N;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                if (n0 + c >= a.N) break;
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(trow + c, v);
-                tmem_ld_wait();
-                if (valid) {
-                    float4* dst = reinterpret_cast<float4*>(prow + n0 + c);
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
-                                             __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
-                }
-            }
-        } else if (a.act == VMV_ACT_GEGLU) {
-            constexpr int HB = BN / 2;
-            const int o0 = nt * HB;
-#pragma unroll 1
-            for (int c = 0; c < HB; c += 16) {
-                if (n0 + c >= a.N) break;
-                uint32_t v[16], g[16];
-                tmem_ld_32x32b_x16(trow + c, v);
-                tmem_ld_32x32b_x16(trow + HB + c, g);
-                tmem_ld_wait();
-                if (valid) {
-                    float x[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
-                        if (a.bias) {
-                            val += __ldg(a.bias + n0 + c + j);
-                            gate += __ldg(a.bias + n0 + HB + c + j);
-                        }
-                        x[j] = val * gelu_erf_f(gate);
-                    }
-                    if (a.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + o0 + c);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 u = __ldg(rp + h);
-                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = unpack_half2(w[j]);
-                                x[8 * h + 2 * j] += f.x;
-                                x[8 * h + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                    uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + o0 + c);
-                    dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
-                                       pack_half2(x[6], x[7]));
-                    dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
-                                       pack_half2(x[14], x[15]));
-                }
-            }
-        } else {
-            const __half* rb = nullptr;
-            if (a.rowbias && valid) rb = a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias;
-#pragma unroll 1
-            for (int c = 0; c < BN; c += 16) {
-                if (n0 + c >= a.N) break;
-                uint32_t v[16];
-                tmem_ld_32x32b_x16(trow + c, v);
-                tmem_ld_wait();
-                if (valid) {
-                    const int n = n0 + c;
-                    float x[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
-                    if (a.bias) {
-                        const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            float4 b4 = __ldg(bp + j);
-                            x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
-                        }
-                    }
-                    if (rb) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 u = __ldg(rp + h);
-                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = unpack_half2(w[j]);
-                                x[8 * h + 2 * j] += f.x;
-                                x[8 * h + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                    if (a.act == VMV_ACT_SILU) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) x[j] = silu_f(x[j]);
-                    }
-                    if (a.residual) {
-                        const uint4* rp = reinterpret_cast<const uint4*>(a.residual + grow * a.ldr + n);
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint4 u = __ldg(rp + h);
-                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                float2 f = unpack_half2(w[j]);
-                                x[8 * h + 2 * j] += f.x;
-                                x[8 * h + 2 * j + 1] += f.y;
-                            }
-                        }
-                    }
-                    uint4* dp = reinterpret_cast<uint4*>(a.D + grow * a.ldd + n);
-                    dp[0] = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
-                                       pack_half2(x[6], x[7]));
-                    dp[1] = make_uint4(pack_half2(x[8], x[9]), pack_half2(x[10], x[11]), pack_half2(x[12], x[13]),
-                                       pack_half2(x[14], x[15]));
-                }
-            }
-        }
+        epilogue_store<BN>(a, nt, split, grow, grow >= 0, tmem_base + (static_cast<uint32_t>(q * 32) << 16));
     }
 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc<TCOLS>(tmem_base);
+}
+
+// ------------------------------------------------------------------------------------------------
+// v2: persistent CTA-pair kernel.  A cluster of 2 CTAs (one SM each) owns 256 x BN output tiles:
+//   * tcgen05.mma.cta_group::2, M = 256: each CTA stages its own 128 A rows and HALF of the W rows, so per K block the
+//     pair moves (256 + BN) x 128 B through L2 for 2*256*BN*64 FLOP -- 1.4-1.6x the arithmetic intensity of the 1-CTA
+//     kernel, which is L2-bandwidth bound on this part;
+//   * persistent: grid = one cluster per SM pair, static round-robin tile scheduler, so barrier init / TMEM allocation
+//     / descriptor prefetch are paid once per launch instead of once per tile;
+//   * two TMEM accumulator buffers (2 x BN columns): the 8 epilogue warps of the pair drain tile i while the MMA
+//     thread already accumulates tile i+1 (tmem_full / tmem_empty mbarriers).
+// Barrier topology (DeepGEMM-style): full[s] lives in the leader CTA (count 2: leader arrive.expect_tx for both CTAs'
+// bytes + the peer's remote arrive; both CTAs' TMA complete_tx are routed to it), empty[s] and tmem_full[b] exist in
+// both CTAs and are signalled by multicast tcgen05.commit, tmem_empty[b] lives in the leader (count 8 = epilogue
+// warps of both CTAs).
+// ------------------------------------------------------------------------------------------------
+template <int BN, int STAGES>
+struct SmemLayout2 {
+    static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
+    static constexpr int A_OFF = 0;
+    static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
+    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 4;
+    static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
+    static constexpr int DYN_BYTES = TOTAL + 1024;
+};
+
+template <int BN, int STAGES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
+                const __grid_constant__ CUtensorMap tmW, const GemmArgs a, const int m_pairs, const int n_tiles,
+                const int splits) {
+    using L = SmemLayout2<BN, STAGES>;
+    constexpr int TCOLS = TmemCols<2 * BN>::value;
+    static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
+    uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int cluster_id = blockIdx.x >> 1;
+    const int num_clusters = gridDim.x >> 1;
+    const int tiles_mn = m_pairs * n_tiles;
+    const int total_tiles = tiles_mn * splits;
+
+    cluster_sync_all();                                 // both CTAs resident before the pair-wide TMEM allocation
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA1);
+        tma_prefetch_desc(&tmW);
+        if (a.nkb1 < a.nkb && a.mode == VMV_GEMM_LINEAR) tma_prefetch_desc(&tmA2);
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full_bar[s], 2);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&tmem_full_bar[b], 1);
+            mbar_init(&tmem_empty_bar[b], 8);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc_2sm<TCOLS>(tmem_ptr_smem);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ------------------------------ TMA producer (both CTAs) ------------------------------
+            constexpr uint32_t tx_bytes = 2u * (A_STAGE_BYTES + L::B_STAGE_BYTES);
+            int it = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+                const int split = t / tiles_mn;
+                const int rem = t - split * tiles_mn;
+                const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
+                const int mt = 2 * mp + (int)rank;
+                const int nrow = nt * BN + (int)rank * (BN / 2);
+                int c1 = 0, c2 = 0, c3 = 0;
+                if (a.mode == VMV_GEMM_LINEAR) {
+                    c1 = mt * BM;
+                } else if (a.mode == VMV_GEMM_CONV3X3) {
+                    c1 = (mt % a.tiles_w) * a.bw;
+                    c2 = ((mt / a.tiles_w) % a.tiles_h) * a.bh;
+                    c3 = (mt / (a.tiles_w * a.tiles_h)) * a.bf;
+                } else {
+                    int ts = mt % a.tiles_per_sample;
+                    c1 = (ts % a.tiles_p) * a.bp;
+                    c2 = (ts / a.tiles_p) * a.bf;
+                    c3 = mt / a.tiles_per_sample;
+                }
+                const int kb_begin = split * a.kb_per_split;
+                const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                    else mbar_arrive_remote(&full_bar[s], 0);
+                    void* sa = smem + L::A_OFF + s * A_STAGE_BYTES;
+                    void* sb = smem + L::B_OFF + s * L::B_STAGE_BYTES;
+                    if (a.mode == VMV_GEMM_LINEAR) {
+                        if (kb < a.nkb1) tma_load_2d_2sm(sa, &tmA1, &full_bar[s], kb * BK, c1);
+                        else tma_load_2d_2sm(sa, &tmA2, &full_bar[s], (kb - a.nkb1) * BK, c1);
+                    } else if (a.mode == VMV_GEMM_CONV3X3) {
+                        const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+                        const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        tma_load_4d_2sm(sa, &tmA1, &full_bar[s], cb * BK, c1 + dx, c2 + dy, c3);
+                    } else {
+                        const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
+                        tma_load_4d_2sm(sa, &tmA1, &full_bar[s], cb * BK, c1, c2 + tap - 1, c3);
+                    }
+                    tma_load_2d_2sm(sb, &tmW, &full_bar[s], kb * BK, nrow);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && rank == 0) {
+            // ------------------------------ MMA issuer (leader CTA only) ------------------------------
+            constexpr uint32_t idesc = umma_idesc_f16_f32(2 * BM, BN);
+            int it = 0, acc_it = 0;
+            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
+                const int split = t / tiles_mn;
+                const int kb_begin = split * a.kb_per_split;
+                const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
+                const int buf = acc_it & 1;
+                const uint32_t aph = (acc_it >> 1) & 1;
+                mbar_wait(&tmem_empty_bar[buf], aph ^ 1);      // epilogues of both CTAs drained this buffer
+                tc_fence_after();
+                const uint32_t dcol = tmem_base + buf * BN;
+                for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
+                    const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + L::B_OFF + s * L::B_STAGE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_f16_ss_2sm(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    umma_commit_2sm(&empty_bar[s]);
+                }
+                umma_commit_2sm(&tmem_full_bar[buf]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------------------------- epilogue (both CTAs) ----------------------------------
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        int acc_it = 0;
+        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
+            const int split = t / tiles_mn;
+            const int rem = t - split * tiles_mn;
+            const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
+            const int mt = 2 * mp + (int)rank;
+            const int buf = acc_it & 1;
+            const uint32_t aph = (acc_it >> 1) & 1;
+            const long long grow = tile_row_to_global(a, mt, r);
+            mbar_wait(&tmem_full_bar[buf], aph);
+            tc_fence_after();
+            epilogue_store<BN>(a, nt, split, grow, grow >= 0,
+                               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (rank == 0) mbar_arrive(&tmem_empty_bar[buf]);
+                else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_2sm<TCOLS>(tmem_base);
 }
 
 // Reduce split-K partials and apply the (non-GEGLU) epilogue.  One thread per 8 output columns.
@@ -438,9 +626,44 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
     return VMV_OK;
 }
 
-static int pick_block_n(const vmv_gemm_params* p) {
+template <int BN, int STAGES>
+static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
+                            int m_pairs, int n_tiles, int splits, cudaStream_t st) {
+    using L = SmemLayout2<BN, STAGES>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             L::DYN_BYTES);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(v2 smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(e));
+            return VMV_ERR_CUDA;
+        }
+        attr_set = true;
+    }
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    const long long total = (long long)m_pairs * n_tiles * splits;
+    int clusters = num_sms / 2;
+    if (total < clusters) clusters = (int)total;
+    gemm_tc2_kernel<BN, STAGES><<<dim3(2 * clusters), 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, a, m_pairs, n_tiles, splits);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
+    return VMV_OK;
+}
+
+static int pick_block_n(const vmv_gemm_params* p, int variant) {
     if (p->block_n) return p->block_n;
     const int N = p->N;
+    if (variant == 2) {
+        if (N % 160 == 0) return 160;
+        if (p->act != VMV_ACT_GEGLU && N % 256 == 0) return 256;
+        return 128;
+    }
     if (p->act == VMV_ACT_GEGLU) return (N % 160 == 0) ? 160 : 128;
     if (N % 160 == 0) return 160;
     if (N % 128 == 0) return 128;
@@ -450,8 +673,17 @@ static int pick_block_n(const vmv_gemm_params* p) {
 
 struct Plan {
     GemmArgs a;
-    int bn, stages, splits, m_tiles, n_tiles;
+    int bn, stages, splits, m_tiles, n_tiles, variant;
 };
+
+static int default_variant() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VMV_GEMM_VARIANT");      // 1 = 1-CTA per-tile kernel, 2 = persistent CTA-pair kernel
+        v = (e && e[0] == '1') ? 1 : 2;
+    }
+    return v;
+}
 
 static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     GemmArgs& a = pl->a;
@@ -519,7 +751,10 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
         set_error("vmv_gemm: unknown mode %d", p->mode);
         return VMV_ERR_INVALID;
     }
-    pl->bn = pick_block_n(p);
+    pl->variant = p->variant ? p->variant : default_variant();
+    VMV_CHECK_ARG(pl->variant == 1 || pl->variant == 2, "vmv_gemm: variant=%d unsupported", pl->variant);
+    if (pl->variant == 2 && p->block_n == 64) pl->variant = 1;      // 64-wide tiles exist only in the 1-CTA kernel
+    pl->bn = pick_block_n(p, pl->variant);
     VMV_CHECK_ARG(pl->bn == 64 || pl->bn == 128 || pl->bn == 160 || pl->bn == 256, "vmv_gemm: block_n=%d unsupported", pl->bn);
     if (p->act == VMV_ACT_GEGLU)
         VMV_CHECK_ARG(p->N % pl->bn == 0 && (pl->bn / 2) % 16 == 0, "vmv_gemm: GEGLU needs N %% block_n == 0");
@@ -559,7 +794,7 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
     {
         cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->N};
         cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
-        cuuint32_t box[2] = {BK, (cuuint32_t)BN};
+        cuuint32_t box[2] = {BK, (cuuint32_t)(pl.variant == 2 ? BN / 2 : BN)};   // a CTA pair splits the W rows
         if ((rc = make_map(&tW, p->W, 2, dims, strides, box)) != VMV_OK) return rc;
     }
     if (p->mode == VMV_GEMM_LINEAR) {
@@ -598,24 +833,29 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
         a.partial = static_cast<float*>(p->workspace);
     }
 
-    dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
-    // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one
-    // CTA's epilogue overlaps the other's main loop.
-    int stages = pl.stages;
-    const int nkb_cta = a.kb_per_split;
-    if (stages == 0) stages = (nkb_cta <= 3) ? 3 : (BN == 256 ? 4 : (BN == 160 ? 3 : 3));
-
-#define VMV_LAUNCH(BN_, ST_) rc = launch_instance<BN_, ST_>(tA1, tA2, tW, a, grid, st)
-    if (BN == 64) {
-        if (stages <= 4) VMV_LAUNCH(64, 4); else VMV_LAUNCH(64, 8);
-    } else if (BN == 128) {
-        if (stages <= 3) VMV_LAUNCH(128, 3); else VMV_LAUNCH(128, 6);
-    } else if (BN == 160) {
-        if (stages <= 3) VMV_LAUNCH(160, 3); else VMV_LAUNCH(160, 6);
+    if (pl.variant == 2) {
+        const int m_pairs = (pl.m_tiles + 1) / 2;
+        if (BN == 128) rc = launch_instance2<128, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (BN == 160) rc = launch_instance2<160, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else rc = launch_instance2<256, 6>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
-        VMV_LAUNCH(256, 4);
-    }
+        dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
+        // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one
+        // CTA's epilogue overlaps the other's main loop.
+        int stages = pl.stages;
+        if (stages == 0) stages = 3;
+#define VMV_LAUNCH(BN_, ST_) rc = launch_instance<BN_, ST_>(tA1, tA2, tW, a, grid, st)
+        if (BN == 64) {
+            if (stages <= 4) VMV_LAUNCH(64, 4); else VMV_LAUNCH(64, 8);
+        } else if (BN == 128) {
+            if (stages <= 3) VMV_LAUNCH(128, 3); else VMV_LAUNCH(128, 6);
+        } else if (BN == 160) {
+            if (stages <= 3) VMV_LAUNCH(160, 3); else VMV_LAUNCH(160, 6);
+        } else {
+            VMV_LAUNCH(256, 4);
+        }
 #undef VMV_LAUNCH
+    }
     if (rc != VMV_OK) return rc;
 
     if (pl.splits > 1) {

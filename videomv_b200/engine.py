@@ -157,11 +157,12 @@ class UNetEngine:
         M = a.shape[0]
         N = w.w.shape[0]
         bn = w.bn or (160 if N % 160 == 0 else 128)
-        tiles = ((M + 127) // 128) * ((N + bn - 1) // bn)
+        # the persistent kernel runs 74 CTA pairs, each on 256 x bn tiles; split K when there are too few tiles
+        tiles = ((M + 255) // 256) * ((N + bn - 1) // bn)
         nkb = w.w.shape[1] // 64
         split = 0
-        if kw.get("act", 0) != ops.ACT_GEGLU and tiles * 2 <= SM_COUNT and nkb >= 16:
-            split = min(nkb // 8, max(1, SM_COUNT // tiles))
+        if kw.get("act", 0) != ops.ACT_GEGLU and tiles * 2 <= SM_COUNT // 2 and nkb >= 16:
+            split = min(nkb // 8, max(1, (SM_COUNT // 2) // tiles))
             if split >= 2:
                 need = split * M * N * 4
                 if self._ws is None or self._ws.numel() < need:

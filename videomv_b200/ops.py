@@ -54,7 +54,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_group: int = 0,
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
-         workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+         workspace: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -88,7 +88,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     if residual is not None:
         _rows(residual, "gemm residual")
         p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
-    p.act, p.block_n, p.stages, p.split_k = act, block_n, stages, split_k
+    p.act, p.block_n, p.stages, p.split_k, p.variant = act, block_n, stages, split_k, variant
     if split_k > 1:
         need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
         if need < 0:
