@@ -50,6 +50,8 @@ struct GemmArgs {
     long long ldr;
     int act;
     float* partial;   // split-K: fp32 [splits, M, N]
+    int tma_epi;      // v2: epilogue stores (and residual loads) go through TMA + swizzled smem staging
+    int d3d;          // TMA epilogue maps are (n, F*HW, B) (temporal conv: tiles never straddle samples)
 };
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
@@ -76,8 +78,30 @@ __device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int m
         int rf = r / a.bp;
         int f = tf * a.bf + rf;
         if (f >= a.F) return -1;
-        return ((long long)b * a.F + f) * a.HW + (tp * a.bp + rp);
+        long long g = ((long long)b * a.F + f) * a.HW + (tp * a.bp + rp);
+        return g < a.M ? g : -1;          // b == B for the phantom second tile of an odd CTA pair
     }
+}
+
+// First TMA row coordinate of tile rows [r, r+32) (r multiple of 32): rows of a tile are contiguous in memory for every
+// tiling make_plan accepts.  For the temporal conv the coordinate is sample-local and *b is the sample index.
+__device__ __forceinline__ long long tile_row0(const GemmArgs& a, int mt, int r, int* b) {
+    *b = 0;
+    if (a.mode == VMV_GEMM_LINEAR) return (long long)mt * BM + r;
+    if (a.mode == VMV_GEMM_CONV3X3) {
+        int tw = mt % a.tiles_w;
+        int th = (mt / a.tiles_w) % a.tiles_h;
+        int tf = mt / (a.tiles_w * a.tiles_h);
+        int rw = r % a.bw;
+        int rh = (r / a.bw) % a.bh;
+        int rf = r / (a.bw * a.bh);
+        return (((long long)tf * a.bf + rf) * a.H + (th * a.bh + rh)) * a.W + (tw * a.bw + rw);
+    }
+    *b = mt / a.tiles_per_sample;
+    int ts = mt % a.tiles_per_sample;
+    int tp = ts % a.tiles_p;
+    int tf = ts / a.tiles_p;
+    return ((long long)tf * a.bf + r / a.bp) * a.HW + (tp * a.bp + r % a.bp);
 }
 
 // Drain one 128 x BN fp32 accumulator tile from TMEM (this thread: one row, `trow` = TMEM address of its lane,
@@ -355,21 +379,29 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 // both CTAs and are signalled by multicast tcgen05.commit, tmem_empty[b] lives in the leader (count 8 = epilogue
 // warps of both CTAs).
 // ------------------------------------------------------------------------------------------------
+constexpr int EPI_BLK_COLS = 32;                 // epilogue column block: 32 fp16 = 64 B rows, SWIZZLE_64B boxes
+constexpr int EPI_BLK_BYTES = 32 * 64;            // 32 rows x 64 B per warp per block
+
 template <int BN, int STAGES>
 struct SmemLayout2 {
     static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
+    static constexpr int NBLK = BN / EPI_BLK_COLS;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int NBARS = 2 * STAGES + 4;
+    static constexpr int DST_OFF = B_OFF + STAGES * B_STAGE_BYTES;            // 4 warps x 2 buffers
+    static constexpr int RES_OFF = DST_OFF + 4 * 2 * EPI_BLK_BYTES;           // 4 warps x NBLK blocks
+    static constexpr int BAR_OFF = RES_OFF + 4 * NBLK * EPI_BLK_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 4 + 4;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
+    static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
 template <int BN, int STAGES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmW, const GemmArgs a, const int m_pairs, const int n_tiles,
+                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD,
+                const __grid_constant__ CUtensorMap tmR, const GemmArgs a, const int m_pairs, const int n_tiles,
                 const int splits) {
     using L = SmemLayout2<BN, STAGES>;
     constexpr int TCOLS = TmemCols<2 * BN>::value;
@@ -380,7 +412,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint64_t* res_bar = tmem_empty_bar + 2;            // [4], one per epilogue warp (residual tile landed)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -402,6 +435,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
             mbar_init(&tmem_empty_bar[b], 8);
+        }
+        for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+        if (a.tma_epi) {
+            tma_prefetch_desc(&tmD);
+            if (a.residual) tma_prefetch_desc(&tmR);
         }
         fence_barrier_init();
     }
@@ -495,6 +533,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         // ---------------------------------- epilogue (both CTAs) ----------------------------------
         const int q = warp & 3;
         const int r = q * 32 + lane;
+        uint8_t* dstage = smem + L::DST_OFF + q * 2 * EPI_BLK_BYTES;
+        uint8_t* rstage = smem + L::RES_OFF + q * L::NBLK * EPI_BLK_BYTES;
+        uint64_t* rbar = &res_bar[q];
+        uint32_t res_phase = 0, dbuf = 0;
+        const bool geglu = a.act == VMV_ACT_GEGLU;
+        const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
+        const int swz = (lane >> 1) & 3;                        // SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
         int acc_it = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
             const int split = t / tiles_mn;
@@ -504,10 +549,123 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int buf = acc_it & 1;
             const uint32_t aph = (acc_it >> 1) & 1;
             const long long grow = tile_row_to_global(a, mt, r);
+            const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+            int cb = 0, nvalid = 0;
+            long long row0 = 0;
+            const int col0 = nt * out_bn;
+            if (a.tma_epi) {
+                row0 = tile_row0(a, mt, q * 32, &cb);
+                nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
+                if (nvalid < 0) nvalid = 0;
+                if (a.residual && lane == 0 && nvalid > 0) {
+                    // prefetch this warp's 32 x out_bn residual slab; it lands while the MMAs of this tile run
+                    mbar_arrive_expect_tx(rbar, (uint32_t)nvalid * EPI_BLK_BYTES);
+                    for (int blk = 0; blk < nvalid; ++blk) {
+                        if (a.d3d) tma_load_3d(rstage + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0, cb);
+                        else tma_load_2d(rstage + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0);
+                    }
+                }
+            }
             mbar_wait(&tmem_full_bar[buf], aph);
             tc_fence_after();
-            epilogue_store<BN>(a, nt, split, grow, grow >= 0,
-                               tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN);
+            if (!a.tma_epi) {
+                epilogue_store<BN>(a, nt, split, grow, grow >= 0, trow);
+            } else {
+                const bool valid = grow >= 0;
+                if (a.residual && nvalid > 0) {
+                    mbar_wait(rbar, res_phase);
+                    res_phase ^= 1;
+                }
+                const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
+#pragma unroll 1
+                for (int blk = 0; blk < nvalid; ++blk) {
+                    const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
+                    float x[32];
+                    if (geglu) {
+                        uint32_t v[16], g[16];
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            tmem_ld_32x32b_x16(trow + c + 16 * h, v);
+                            tmem_ld_32x32b_x16(trow + BN / 2 + c + 16 * h, g);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
+                                if (a.bias) {
+                                    val += __ldg(a.bias + nt * BN + c + 16 * h + j);
+                                    gate += __ldg(a.bias + nt * BN + BN / 2 + c + 16 * h + j);
+                                }
+                                x[16 * h + j] = val * gelu_erf_f(gate);
+                            }
+                        }
+                    } else {
+                        uint32_t v[32];
+                        tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                        tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                        tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
+                        const int n = col0 + c;
+                        if (a.bias) {
+                            const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float4 b4 = __ldg(bp + j);
+                                x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                            }
+                        }
+                        if (rb) {
+                            const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
+#pragma unroll
+                            for (int h = 0; h < 4; ++h) {
+                                uint4 u = __ldg(rp + h);
+                                uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    float2 f = unpack_half2(w[j]);
+                                    x[8 * h + 2 * j] += f.x;
+                                    x[8 * h + 2 * j + 1] += f.y;
+                                }
+                            }
+                        }
+                        if (a.act == VMV_ACT_SILU) {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+                        }
+                    }
+                    if (a.residual) {
+                        const uint8_t* rrow = rstage + blk * EPI_BLK_BYTES + lane * 64;
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            uint4 u = *reinterpret_cast<const uint4*>(rrow + ((h ^ swz) << 4));
+                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                float2 f = unpack_half2(w[j]);
+                                x[8 * h + 2 * j] += f.x;
+                                x[8 * h + 2 * j + 1] += f.y;
+                            }
+                        }
+                    }
+                    // stage the 32 x 32 fp16 block (swizzled) and hand it to the TMA engine
+                    uint8_t* dptr = dstage + (dbuf & 1) * EPI_BLK_BYTES;
+                    if (lane == 0) bulk_wait_group_read<1>();        // the store that last read this buffer is done
+                    __syncwarp();
+#pragma unroll
+                    for (int h = 0; h < 4; ++h)
+                        *reinterpret_cast<uint4*>(dptr + lane * 64 + ((h ^ swz) << 4)) =
+                            make_uint4(pack_half2(x[8 * h], x[8 * h + 1]), pack_half2(x[8 * h + 2], x[8 * h + 3]),
+                                       pack_half2(x[8 * h + 4], x[8 * h + 5]), pack_half2(x[8 * h + 6], x[8 * h + 7]));
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (a.d3d) tma_store_3d(&tmD, dptr, col0 + c, (int)row0, cb);
+                        else tma_store_2d(&tmD, dptr, col0 + c, (int)row0);
+                        bulk_commit_group();
+                    }
+                    ++dbuf;
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -515,6 +673,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
             }
         }
+        if (lane == 0) bulk_wait_group<0>();                         // all TMA stores of this warp have completed
     }
 
     tc_fence_before();
@@ -584,7 +743,7 @@ static EncodeTiledFn get_encode_fn() {
 // fp16 tensor map, 128B swizzle, inner box = 64 elements.  dims/strides innermost first; strides in bytes
 // for dims 1..rank-1.
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                    const cuuint32_t* box) {
+                    const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -592,7 +751,7 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank %d dims [%llu,%llu,%llu,%llu] box [%u,%u,%u,%u] "
@@ -627,8 +786,9 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
 }
 
 template <int BN, int STAGES>
-static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
-                            int m_pairs, int n_tiles, int splits, cudaStream_t st) {
+static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const CUtensorMap& tD,
+                            const CUtensorMap& tR, const GemmArgs& a, int m_pairs, int n_tiles, int splits,
+                            cudaStream_t st) {
     using L = SmemLayout2<BN, STAGES>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -650,7 +810,8 @@ static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, cons
     const long long total = (long long)m_pairs * n_tiles * splits;
     int clusters = num_sms / 2;
     if (total < clusters) clusters = (int)total;
-    gemm_tc2_kernel<BN, STAGES><<<dim3(2 * clusters), 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, a, m_pairs, n_tiles, splits);
+    gemm_tc2_kernel<BN, STAGES><<<dim3(2 * clusters), 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, tD, tR, a, m_pairs, n_tiles,
+                                                                               splits);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
     return VMV_OK;
@@ -660,8 +821,9 @@ static int pick_block_n(const vmv_gemm_params* p, int variant) {
     if (p->block_n) return p->block_n;
     const int N = p->N;
     if (variant == 2) {
+        if (p->act == VMV_ACT_GEGLU) return (N % 256 == 0) ? 256 : 128;   // BN/2 must be a multiple of 32
         if (N % 160 == 0) return 160;
-        if (p->act != VMV_ACT_GEGLU && N % 256 == 0) return 256;
+        if (N % 256 == 0) return 256;
         return 128;
     }
     if (p->act == VMV_ACT_GEGLU) return (N % 160 == 0) ? 160 : 128;
@@ -757,7 +919,8 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     pl->bn = pick_block_n(p, pl->variant);
     VMV_CHECK_ARG(pl->bn == 64 || pl->bn == 128 || pl->bn == 160 || pl->bn == 256, "vmv_gemm: block_n=%d unsupported", pl->bn);
     if (p->act == VMV_ACT_GEGLU)
-        VMV_CHECK_ARG(p->N % pl->bn == 0 && (pl->bn / 2) % 16 == 0, "vmv_gemm: GEGLU needs N %% block_n == 0");
+        VMV_CHECK_ARG(p->N % pl->bn == 0 && (pl->bn / 2) % (pl->variant == 2 ? 32 : 16) == 0,
+                      "vmv_gemm: GEGLU needs N %% block_n == 0 and block_n in {128, 256} for the CTA-pair kernel");
     pl->n_tiles = (p->N + pl->bn - 1) / pl->bn;
     pl->splits = p->split_k > 1 ? p->split_k : 1;
     if (pl->splits > a.nkb) pl->splits = a.nkb;
@@ -835,9 +998,30 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
 
     if (pl.variant == 2) {
         const int m_pairs = (pl.m_tiles + 1) / 2;
-        if (BN == 128) rc = launch_instance2<128, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else rc = launch_instance2<256, 6>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        CUtensorMap tD = tW, tR = tW;
+        if (pl.splits <= 1) {
+            // epilogue through TMA: 32-column x 32-row fp16 boxes, 64B swizzle (see epilogue in gemm_tc2_kernel)
+            VMV_CHECK_ARG(!(p->act == VMV_ACT_GEGLU && p->residual), "vmv_gemm: GEGLU with residual is not supported");
+            a.tma_epi = 1;
+            a.d3d = p->mode == VMV_GEMM_TCONV3;
+            cuuint32_t box[3] = {EPI_BLK_COLS, 32, 1};
+            auto epi_map = [&](CUtensorMap* m, const void* base, long long ld) -> int {
+                if (a.d3d) {
+                    const cuuint64_t rows = (cuuint64_t)a.F * a.HW;
+                    cuuint64_t dims[3] = {(cuuint64_t)a.n_out, rows, (cuuint64_t)p->B};
+                    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * rows};
+                    return make_map(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+                }
+                cuuint64_t dims[2] = {(cuuint64_t)a.n_out, (cuuint64_t)p->M};
+                cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+                return make_map(m, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+            };
+            if ((rc = epi_map(&tD, p->D, p->ldd)) != VMV_OK) return rc;
+            if (p->residual && (rc = epi_map(&tR, p->residual, p->ldr)) != VMV_OK) return rc;
+        }
+        if (BN == 128) rc = launch_instance2<128, 6>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (BN == 160) rc = launch_instance2<160, 6>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else rc = launch_instance2<256, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
         // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one

@@ -55,87 +55,118 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int H, int W, int 
     out[i] = v;
 }
 
-// Input conv: tiny Cin (4 or 8).  One thread per (pixel, 8 output channels); weights via the read-only cache.
-__global__ void conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int B,
-                                  int F, int H, int W, const float* __restrict__ w, const float* __restrict__ bias,
-                                  int Cout, __half* __restrict__ out) {
-    const int cov = Cout / 8;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long total = (long long)B * F * H * W * cov;
-    if (i >= total) return;
-    const int co0 = (int)(i % cov) * 8;
-    long long pix = i / cov;
-    const int xw = (int)(pix % W);
-    const int yh = (int)((pix / W) % H);
-    const int f = (int)((pix / ((long long)W * H)) % F);
-    const int b = (int)(pix / ((long long)W * H * F));
-    const int Cin = C1 + C2;
-    float acc[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) acc[j] = bias[co0 + j];
-    for (int ci = 0; ci < Cin; ++ci) {
-        const float* src = ci < C1 ? x1 + (((long long)b * C1 + ci) * F + f) * H * W
-                                   : x2 + (((long long)b * C2 + (ci - C1)) * F + f) * H * W;
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-            const int ih = yh + ky - 1;
-            if (ih < 0 || ih >= H) continue;
-#pragma unroll
-            for (int kx = 0; kx < 3; ++kx) {
-                const int iw = xw + kx - 1;
-                if (iw < 0 || iw >= W) continue;
-                const float v = __ldg(src + ih * W + iw);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += v * __ldg(w + (((long long)(co0 + j) * Cin + ci) * 3 + ky) * 3 + kx);
+// Input conv: tiny Cin (4 or 8), K = 9*Cin <= 72.  A CTA owns IN_PIX consecutive pixels of one frame row-major; the
+// weights live in smem transposed to [k][Cout] so a thread reads its 8 output channels as two 16B loads per k, and the
+// K input taps of a pixel are gathered once into smem and broadcast to the Cout/8 threads that share the pixel.
+constexpr int IN_PIX = 128;
+constexpr int IN_MAXK = 72;
+__global__ void __launch_bounds__(256)
+conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int B, int F, int H, int W,
+                  const float* __restrict__ w, const float* __restrict__ bias, int Cout, __half* __restrict__ out) {
+    extern __shared__ float sm[];
+    const int Cin = C1 + C2, K = 9 * Cin;
+    float* sw = sm;                         // [K][Cout]
+    float* sx = sm + K * Cout;              // [IN_PIX][K]
+    const long long npix = (long long)B * F * H * W;
+    const long long pix0 = (long long)blockIdx.x * IN_PIX;
+    for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
+        const int k = i / Cout, co = i % Cout;          // k = (ci*3 + ky)*3 + kx, matching w[co][ci][ky][kx]
+        sw[i] = w[(long long)co * K + k];
+    }
+    for (int i = threadIdx.x; i < IN_PIX * K; i += blockDim.x) {
+        const int p = i / K, k = i % K;
+        const long long pix = pix0 + p;
+        float v = 0.f;
+        if (pix < npix) {
+            const int xw = (int)(pix % W), yh = (int)((pix / W) % H);
+            const int f = (int)((pix / ((long long)W * H)) % F), b = (int)(pix / ((long long)W * H * F));
+            const int ci = k / 9, ky = (k % 9) / 3, kx = k % 3;
+            const int ih = yh + ky - 1, iw = xw + kx - 1;
+            if (ih >= 0 && ih < H && iw >= 0 && iw < W) {
+                const float* src = ci < C1 ? x1 + (((long long)b * C1 + ci) * F + f) * H * W
+                                           : x2 + (((long long)b * C2 + (ci - C1)) * F + f) * H * W;
+                v = __ldg(src + ih * W + iw);
             }
         }
+        sx[i] = v;
     }
-    uint4 o = make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]), pack_half2(acc[4], acc[5]),
-                         pack_half2(acc[6], acc[7]));
-    *reinterpret_cast<uint4*>(out + pix * Cout + co0) = o;
+    __syncthreads();
+    const int cov = Cout / 8;
+    for (int i = threadIdx.x; i < IN_PIX * cov; i += blockDim.x) {
+        const int p = i / cov, co0 = (i % cov) * 8;
+        const long long pix = pix0 + p;
+        if (pix >= npix) continue;
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = bias[co0 + j];
+        const float* xp = sx + p * K;
+        for (int k = 0; k < K; ++k) {
+            const float v = xp[k];
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + co0);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + co0 + 4);
+            acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
+            acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+        }
+        *reinterpret_cast<uint4*>(out + pix * Cout + co0) =
+            make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]), pack_half2(acc[4], acc[5]),
+                       pack_half2(acc[6], acc[7]));
+    }
 }
 
-// Head conv: tiny Cout (4).  One warp per output pixel: lanes stride the (tap, channel-vector) reduction.
+// Head conv: tiny Cout (4).  One warp per output pixel, lanes stride the (tap, 8-channel vector) reduction; the weights
+// are staged once per CTA in smem as [tap][c][COUT] so each (tap, c) is one 16B broadcast-free load.
+constexpr int OUT_PIX_PER_WARP = 8;
 template <int COUT>
-__global__ void conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int C,
-                                   const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ out) {
-    const int lane = threadIdx.x & 31;
-    const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+__global__ void __launch_bounds__(256)
+conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int C, const float* __restrict__ w,
+                   const float* __restrict__ bias, float* __restrict__ out) {
+    extern __shared__ float sm[];                       // [9][C][COUT]
+    for (int i = threadIdx.x; i < 9 * C * COUT; i += blockDim.x) {
+        const int co = i % COUT, c = (i / COUT) % C, tap = i / (COUT * C);
+        sm[i] = w[((long long)co * C + c) * 9 + tap];
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long npix = (long long)B * F * H * W;
-    if (pix >= npix) return;
-    const int xw = (int)(pix % W);
-    const int yh = (int)((pix / W) % H);
-    const long long n = pix / ((long long)W * H);     // b*F + f
     const int cv = C / 8;
-    float acc[COUT];
+    for (int pp = 0; pp < OUT_PIX_PER_WARP; ++pp) {
+        const long long pix = ((long long)blockIdx.x * (blockDim.x >> 5) + warp) * OUT_PIX_PER_WARP + pp;
+        if (pix >= npix) break;
+        const int xw = (int)(pix % W);
+        const int yh = (int)((pix / W) % H);
+        const long long n = pix / ((long long)W * H);     // b*F + f
+        float acc[COUT];
 #pragma unroll
-    for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
-    for (int i = lane; i < 9 * cv; i += 32) {
-        const int tap = i / cv, c0 = (i % cv) * 8;
-        const int ih = yh + tap / 3 - 1, iw = xw + tap % 3 - 1;
-        if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
-        uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * C + c0));
-        uint32_t ww[4] = {u.x, u.y, u.z, u.w};
-        float v[8];
+        for (int j = 0; j < COUT; ++j) acc[j] = 0.f;
+        for (int i = lane; i < 9 * cv; i += 32) {
+            const int tap = i / cv, c0 = (i % cv) * 8;
+            const int ih = yh + tap / 3 - 1, iw = xw + tap % 3 - 1;
+            if (ih < 0 || ih >= H || iw < 0 || iw >= W) continue;
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + ((n * H + ih) * W + iw) * C + c0));
+            uint32_t ww[4] = {u.x, u.y, u.z, u.w};
+            const float* wp = sm + ((long long)tap * C + c0) * COUT;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { float2 f2 = unpack_half2(ww[j]); v[2 * j] = f2.x; v[2 * j + 1] = f2.y; }
+            for (int j = 0; j < 4; ++j) {
+                float2 f2 = unpack_half2(ww[j]);
+#pragma unroll
+                for (int co = 0; co < COUT; ++co) {
+                    acc[co] += f2.x * wp[(2 * j) * COUT + co];
+                    acc[co] += f2.y * wp[(2 * j + 1) * COUT + co];
+                }
+            }
+        }
 #pragma unroll
         for (int co = 0; co < COUT; ++co) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[co] += v[j] * __ldg(w + ((long long)co * C + c0 + j) * 9 + tap);
+            for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
         }
-    }
+        if (lane == 0) {
+            const int f = (int)(n % F);
+            const long long b = n / F;
 #pragma unroll
-    for (int co = 0; co < COUT; ++co) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc[co] += __shfl_xor_sync(0xffffffffu, acc[co], o);
-    }
-    if (lane == 0) {
-        const int f = (int)(n % F);
-        const long long b = n / F;
-#pragma unroll
-        for (int co = 0; co < COUT; ++co)
-            out[(((b * COUT + co) * F + f) * H + yh) * W + xw] = acc[co] + bias[co];
+            for (int co = 0; co < COUT; ++co)
+                out[(((b * COUT + co) * F + f) * H + yh) * W + xw] = acc[co] + bias[co];
+        }
     }
 }
 
@@ -211,8 +242,17 @@ extern "C" int vmv_im2col_3x3_s2(const void* x, int32_t n, int32_t H, int32_t W,
 extern "C" int vmv_conv3x3_in(const float* x1, int32_t C1, const float* x2, int32_t C2, int32_t B, int32_t F, int32_t H,
                               int32_t W, const float* w, const float* bias, int32_t Cout, void* out, void* stream) {
     VMV_CHECK_ARG(x1 && w && bias && out && C1 > 0 && (C2 == 0 || x2) && Cout % 8 == 0, "vmv_conv3x3_in: bad args");
-    const long long total = (long long)B * F * H * W * (Cout / 8);
-    conv3x3_in_kernel<<<(unsigned)((total + 127) / 128), 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    const int K = 9 * (C1 + C2);
+    VMV_CHECK_ARG(K <= IN_MAXK, "vmv_conv3x3_in: Cin=%d too large for the stem kernel (max %d)", C1 + C2, IN_MAXK / 9);
+    const long long npix = (long long)B * F * H * W;
+    const size_t smem = sizeof(float) * ((size_t)K * Cout + (size_t)IN_PIX * K);
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_in_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("vmv_conv3x3_in: smem attribute: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+        smem_set = smem;
+    }
+    conv3x3_in_kernel<<<(unsigned)((npix + IN_PIX - 1) / IN_PIX), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         x1, C1, x2, C2, B, F, H, W, w, bias, Cout, static_cast<__half*>(out));
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_in");
@@ -224,7 +264,15 @@ extern "C" int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, i
     VMV_CHECK_ARG(x && w && bias && out && C % 8 == 0, "vmv_conv3x3_out: bad args");
     VMV_CHECK_ARG(Cout == 4, "vmv_conv3x3_out: only out_dim=4 is instantiated (got %d)", Cout);
     const long long npix = (long long)B * F * H * W;
-    conv3x3_out_kernel<4><<<(unsigned)((npix + 7) / 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    const size_t smem = sizeof(float) * 9 * (size_t)C * 4;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv3x3_out_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) { set_error("vmv_conv3x3_out: smem attribute: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+        smem_set = smem;
+    }
+    const int pix_per_cta = 8 * OUT_PIX_PER_WARP;
+    conv3x3_out_kernel<4><<<(unsigned)((npix + pix_per_cta - 1) / pix_per_cta), 256, smem, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(x), B, F, H, W, C, w, bias, out);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_out");

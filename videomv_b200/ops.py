@@ -29,11 +29,11 @@ def _prof_begin():
     return e
 
 
-def _prof_end(e0, family, flops, nbytes):
+def _prof_end(e0, family, flops, nbytes, desc=""):
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        PROFILE.append((family, flops, nbytes, e0, e1))
+        PROFILE.append((family, flops, nbytes, e0, e1, desc))
 
 
 def _stream() -> int:
@@ -100,7 +100,9 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
     if e0 is not None:
         ktot = w.shape[1]
-        _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out))
+        _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out),
+                  f"mode{mode} M{M} N{N} K{ktot} act{act} res{int(residual is not None)} rb{int(rowbias is not None)} "
+                  f"split{split_k}")
     return out
 
 

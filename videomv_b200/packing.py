@@ -26,8 +26,9 @@ def pack_tconv3(w: torch.Tensor) -> torch.Tensor:
 
 
 def geglu_block_n(n: int) -> int:
-    """N tile used for a GEGLU GEMM with N = 8C columns (must divide N; mirrors pick_block_n in gemm_tc.cu)."""
-    return 160 if n % 160 == 0 else 128
+    """N tile used for a GEGLU GEMM with N = 8C columns: must divide N and BN/2 must be a multiple of the 32-column
+    epilogue block of the CTA-pair kernel (mirrors pick_block_n in gemm_tc.cu)."""
+    return 256 if n % 256 == 0 else 128
 
 
 def pack_geglu(w: torch.Tensor, b: torch.Tensor):
