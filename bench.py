@@ -297,7 +297,7 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         torch.cuda.synchronize()
         prof, ops.PROFILE = ops.PROFILE, None
         fam = {}
-        for name, fl, by, a, b, _desc in prof:
+        for name, fl, by, a, b, _desc, _replay in prof:
             f = fam.setdefault(name, [0, 0.0, 0.0, 0.0])
             f[0] += 1; f[1] += fl; f[2] += by; f[3] += a.elapsed_time(b)
         g = fam.get("gemm_tc", [0, 0.0, 0.0, 1e-9])

@@ -86,12 +86,14 @@ int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p);
  * consecutive chunks of `rows_per_batch` rows; statistics are per (chunk, group): a chunk is one frame
  * (4-D GroupNorm) or one whole sample (5-D GroupNorm: statistics span frames, util.py:1358,1014).
  *   vmv_groupnorm_stats: stats[nbatch*32*2] (fp64 sum, sum of squares); zeroed by the call.
- *   vmv_groupnorm_apply: out[rows, C1+C2] fp16 = (x-mean)*rstd*gamma+beta, optional SiLU.
+ *   vmv_groupnorm_apply: out[rows, C1+C2] fp16 = (x-mean)*rstd*gamma+beta, optional SiLU.  `stat_rows` (0 = rows_per_batch)
+ *                        is the number of rows the statistics cover: larger than rows_per_batch when the caller summed the
+ *                        partial statistics of several row shards (multi-GPU pixel sharding) between the two calls.
  * ---------------------------------------------------------------------------------------------- */
 int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                         int64_t rows_per_batch, int32_t nbatch, double* stats, void* stream);
 int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                        int64_t rows_per_batch, int32_t nbatch, const double* stats,
+                        int64_t rows_per_batch, int32_t nbatch, const double* stats, int64_t stat_rows,
                         const float* gamma, const float* beta, float eps, int32_t silu,
                         void* out, int64_t ldo, void* stream);
 

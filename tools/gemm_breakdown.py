@@ -30,18 +30,43 @@ def main():
     torch.cuda.synchronize()
     prof, ops.PROFILE = ops.PROFILE, None
     fam = collections.OrderedDict()
-    agg = collections.OrderedDict()
-    for name, fl, by, a, b, desc in prof:
+    shapes = collections.OrderedDict()
+    for name, fl, by, a, b, desc, replay in prof:
         ms = a.elapsed_time(b)
         f = fam.setdefault(name, [0, 0.0, 0.0]); f[0] += 1; f[1] += fl; f[2] += ms
         if name == "gemm_tc":
-            g = agg.setdefault(desc, [0, 0.0, 0.0]); g[0] += 1; g[1] += fl; g[2] += ms
-    print("family totals (ms):", {k: (v[0], round(v[2], 3)) for k, v in fam.items()})
-    tot = sum(v[2] for v in agg.values())
-    print(f"| shape | n | total ms | share | us each | TFLOP/s |\n|---|---:|---:|---:|---:|---:|")
-    for desc, (n, fl, ms) in sorted(agg.items(), key=lambda kv: -kv[1][2]):
-        print(f"| {desc} | {n} | {ms:.3f} | {100 * ms / tot:.1f}% | {1e3 * ms / n:.1f} | {fl / ms / 1e9:.0f} |")
-    print(f"gemm total {tot:.3f} ms, {sum(v[1] for v in agg.values()) / tot / 1e9:.0f} TFLOP/s")
+            g = shapes.setdefault(desc, [0, fl, replay]); g[0] += 1
+    print("family totals, eager event-to-event (ms; small kernels are CPU-launch bound here):",
+          {k: (v[0], round(v[2], 3)) for k, v in fam.items()})
+    # true device time per shape: 8 back-to-back launches captured in a CUDA graph, replayed 3x, L2-warm
+    rows = []
+    for desc, (n, fl, replay) in shapes.items():
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            replay()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(8):
+                replay()
+        g.replay()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / 24
+        rows.append((desc, n, fl, us))
+    tot = sum(n * us for _, n, _, us in rows)
+    print("| shape | n | us each | total ms | share | TFLOP/s |\n|---|---:|---:|---:|---:|---:|")
+    for desc, n, fl, us in sorted(rows, key=lambda r: -r[1] * r[3]):
+        print(f"| {desc} | {n} | {us:.1f} | {n * us / 1e3:.3f} | {100 * n * us / tot:.1f}% | {fl / us / 1e6:.0f} |")
+    print(f"gemm total {tot / 1e3:.3f} ms per B=2 forward, {sum(n * fl for _, n, fl, _ in rows) / tot / 1e6:.0f} TFLOP/s "
+          f"({len(rows)} distinct shapes, {sum(r[1] for r in rows)} launches)")
 
 
 if __name__ == "__main__":

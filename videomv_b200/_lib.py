@@ -103,7 +103,7 @@ SYMBOLS = {
     "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
     "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
-    "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+    "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
     "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
     "vmv_attention": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),

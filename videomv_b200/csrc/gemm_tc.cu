@@ -588,15 +588,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             tmem_ld_32x32b_x16(trow + c + 16 * h, v);
                             tmem_ld_32x32b_x16(trow + BN / 2 + c + 16 * h, g);
                             tmem_ld_wait();
+                            float bv[16], bg[16];
+                            if (a.bias) {
+                                const float4* pv = reinterpret_cast<const float4*>(a.bias + nt * BN + c + 16 * h);
+                                const float4* pg = reinterpret_cast<const float4*>(a.bias + nt * BN + BN / 2 + c + 16 * h);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
-                                if (a.bias) {
-                                    val += __ldg(a.bias + nt * BN + c + 16 * h + j);
-                                    gate += __ldg(a.bias + nt * BN + BN / 2 + c + 16 * h + j);
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 x4 = __ldg(pv + j), y4 = __ldg(pg + j);
+                                    bv[4 * j] = x4.x; bv[4 * j + 1] = x4.y; bv[4 * j + 2] = x4.z; bv[4 * j + 3] = x4.w;
+                                    bg[4 * j] = y4.x; bg[4 * j + 1] = y4.y; bg[4 * j + 2] = y4.z; bg[4 * j + 3] = y4.w;
                                 }
-                                x[16 * h + j] = val * gelu_erf_f(gate);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) { bv[j] = 0.f; bg[j] = 0.f; }
                             }
+#pragma unroll
+                            for (int j = 0; j < 16; ++j)
+                                x[16 * h + j] = (__uint_as_float(v[j]) + bv[j]) * gelu_erf_f(__uint_as_float(g[j]) + bg[j]);
                         }
                     } else {
                         uint32_t v[32];

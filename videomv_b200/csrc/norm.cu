@@ -106,7 +106,7 @@ gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
 
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
-                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes,
+                int C, long long rows_per_batch, long long stat_rows, int rows_per_cta, int vw, int lanes,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int silu, __half* __restrict__ out, long long ldo) {
     const int t = threadIdx.x;
@@ -116,7 +116,7 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     const int c0 = vec * 8;
     if (ty >= lanes || c0 >= C) return;
     const int cpg = C / GN_GROUPS;
-    const double cnt = (double)rows_per_batch * cpg;
+    const double cnt = (double)stat_rows * cpg;       // > rows_per_batch when the statistics were all-reduced over shards
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -253,8 +253,9 @@ extern "C" int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, con
 }
 
 extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                                   int64_t rows_per_batch, int32_t nbatch, const double* stats, const float* gamma,
-                                   const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
+                                   int64_t rows_per_batch, int32_t nbatch, const double* stats, int64_t stat_rows,
+                                   const float* gamma, const float* beta, float eps, int32_t silu, void* out, int64_t ldo,
+                                   void* stream) {
     int rc = gn_check("vmv_groupnorm_apply", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
     if (rc) return rc;
     VMV_CHECK_ARG(stats && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_apply: bad stats/gamma/beta/out");
@@ -263,7 +264,8 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
     dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
     gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
-                                                 g.rows_per_cta, g.vw, g.lanes, stats, gamma, beta, eps, silu,
+                                                 stat_rows > 0 ? stat_rows : rows_per_batch, g.rows_per_cta, g.vw,
+                                                 g.lanes, stats, gamma, beta, eps, silu,
                                                  static_cast<__half*>(out), ldo);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_apply");

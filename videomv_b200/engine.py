@@ -18,7 +18,7 @@ from typing import Dict, List, Optional, Tuple
 import torch
 import torch.nn.functional as F
 
-from . import ops, packing
+from . import ops, packing, parallel
 
 SM_COUNT = 148
 
@@ -48,6 +48,7 @@ class UNetEngine:
         self._i2v_cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._graphs: Dict[Tuple, "_Graph"] = {}
         self.use_graphs = False
+        self.shard: Optional[parallel.ShardCtx] = None     # frame sharding of one sample over the ranks of a group
         self._pack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -187,15 +188,40 @@ class UNetEngine:
         else:
             res = x
         h2 = self._gemm(a1, d["c2"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), residual=res)
-        cur = h2
+        # temporal tail (util.py:1381-1392) on the pixel-sharded layout when the sample is spread over ranks
+        Ff, HWt, to_frames = self._enter_temporal(S)
+        h2t = self._to_pixels(h2, S)
+        cur = h2t
         for i, (gn, wt) in enumerate(d["t"]):
-            a = ops.groupnorm(cur, *gn, rows_per_batch=Fr * HW, eps=1e-5, silu=True)
-            cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Fr, H, W), residual=h2 if i == 3 else None)
-        return cur
+            a = ops.groupnorm(cur, *gn, rows_per_batch=Ff * HWt, eps=1e-5, silu=True, **self._gn5d_kw(S))
+            cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Ff, HWt, 1), residual=h2t if i == 3 else None)
+        return to_frames(cur)
 
-    def _tblock(self, tb, h, S, heads, temporal: bool, kv=None):
-        B, Fr, H, W = S["B"], S["F"], S["H"], S["W"]
-        HW = H * W
+    # ---- frame-shard <-> pixel-shard plumbing (identity on a single GPU) -----------------------------------------
+    def _enter_temporal(self, S):
+        """Returns (frames, pixels per rank, fn back to the frame layout) for a temporal segment."""
+        HW = S["H"] * S["W"]
+        if self.shard is None:
+            return S["F"], HW, (lambda z: z)
+        ctx = self.shard
+        return S["F"] * ctx.world, HW // ctx.world, (lambda z: parallel.pixels_to_frames(z, S["B"], S["F"], HW, ctx))
+
+    def _to_pixels(self, x, S):
+        if self.shard is None:
+            return x
+        return parallel.frames_to_pixels(x, S["B"], S["F"], S["H"] * S["W"], self.shard)
+
+    def _gn5d_kw(self, S):
+        if self.shard is None:
+            return {}
+        ctx = self.shard
+        return dict(reduce_fn=lambda st: parallel.allreduce_stats(st, ctx),
+                    stat_rows=S["F"] * ctx.world * S["H"] * S["W"])
+
+    def _tblock(self, tb, h, S, heads, temporal: bool, kv=None, Fr=None, HW=None):
+        B = S["B"]
+        Fr = S["F"] if Fr is None else Fr
+        HW = S["H"] * S["W"] if HW is None else HW
         C = heads * self.head_dim
         M = h.shape[0]
 
@@ -241,11 +267,12 @@ class UNetEngine:
         return self._gemm(h, d["pout"], residual=x)
 
     def _temporal(self, d, x, S):
-        rows = S["F"] * S["H"] * S["W"]
-        a = ops.groupnorm(x, *d["gn"], rows_per_batch=rows, eps=1e-6, silu=False)
+        Ff, HWt, to_frames = self._enter_temporal(S)
+        xt = self._to_pixels(x, S)
+        a = ops.groupnorm(xt, *d["gn"], rows_per_batch=Ff * HWt, eps=1e-6, silu=False, **self._gn5d_kw(S))
         h = self._gemm(a, d["pin"])
-        h = self._tblock(d["tb"], h, S, d["heads"], temporal=True)
-        return self._gemm(h, d["pout"], residual=x)
+        h = self._tblock(d["tb"], h, S, d["heads"], temporal=True, Fr=Ff, HW=HWt)
+        return to_frames(self._gemm(h, d["pout"], residual=xt))
 
     def _run_block(self, d, x, skip, S):
         k = d["kind"]
@@ -351,6 +378,17 @@ class UNetEngine:
 
     def _forward_impl(self, x32, t, ctx, cam, fps, concat):
         B, _, Fr, H, W = x32.shape
+        sh = self.shard
+        if sh is not None:
+            # every rank receives the full [B,C,F,h,w] latent (as the sampler holds it) and computes its F/P frames
+            sh.check(Fr, (H >> (len(self.m.dim_mult) - 1)) * (W >> (len(self.m.dim_mult) - 1)))
+            sh.collectives = 0
+            Fl = Fr // sh.world
+            lo = sh.rank * Fl
+            x32 = x32[:, :, lo:lo + Fl].contiguous()
+            cam = None if cam is None else cam[:, lo:lo + Fl].contiguous()
+            concat = None if concat is None else concat[:, :, lo:lo + Fl].contiguous()
+            Fr = Fl
         S = {"B": B, "F": Fr, "H": H, "W": W, "x_in": x32}
         if concat is not None:
             S["x_in2"] = concat
@@ -366,7 +404,8 @@ class UNetEngine:
         for blk in self.dec:
             h = self._run_block(blk, h, skips.pop(), S)
         a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True)
-        return ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
+        out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
+        return out if sh is None else parallel.gather_frames(out, sh)
 
     # ------------------------------------------------------------------------------------------------------------
     # I2V conditioning glue (step-invariant; depends only on local_image / image / y)

@@ -29,11 +29,11 @@ def _prof_begin():
     return e
 
 
-def _prof_end(e0, family, flops, nbytes, desc=""):
+def _prof_end(e0, family, flops, nbytes, desc="", replay=None):
     if e0 is not None:
         e1 = torch.cuda.Event(enable_timing=True)
         e1.record()
-        PROFILE.append((family, flops, nbytes, e0, e1, desc))
+        PROFILE.append((family, flops, nbytes, e0, e1, desc, replay))
 
 
 def _stream() -> int:
@@ -100,16 +100,20 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
     if e0 is not None:
         ktot = w.shape[1]
+        keep = (a1, a2, w, out, bias, rowbias, residual, workspace)          # keep the operands alive for replays
+        replay = lambda p=p, keep=keep: check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
         _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out),
                   f"mode{mode} M{M} N{N} K{ktot} act{act} res{int(residual is not None)} rb{int(rowbias is not None)} "
-                  f"split{split_k}")
+                  f"split{split_k}", replay)
     return out
 
 
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
               silu: bool, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """GroupNorm(32) over [x1 | x2] rows, statistics per chunk of `rows_per_batch` rows, optional SiLU."""
+              stats: Optional[torch.Tensor] = None, reduce_fn=None, stat_rows: int = 0) -> torch.Tensor:
+    """GroupNorm(32) over [x1 | x2] rows, statistics per chunk of `rows_per_batch` rows, optional SiLU.
+    `reduce_fn(stats)` (e.g. an all-reduce over pixel shards) runs between the statistics and apply kernels;
+    `stat_rows` is then the global number of rows per chunk."""
     _rows(x1, "groupnorm x1")
     rows, C1 = x1.shape
     C2 = 0
@@ -128,8 +132,10 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
     e0 = _prof_begin()
     check(L.vmv_groupnorm_stats(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
                                 rows_per_batch, nbatch, stats.data_ptr(), st), "vmv_groupnorm_stats")
+    if reduce_fn is not None:
+        reduce_fn(stats)
     check(L.vmv_groupnorm_apply(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
-                                rows_per_batch, nbatch, stats.data_ptr(), gamma.data_ptr(), beta.data_ptr(),
+                                rows_per_batch, nbatch, stats.data_ptr(), stat_rows, gamma.data_ptr(), beta.data_ptr(),
                                 float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
     _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))     # stats read + apply read + write
     return out

@@ -250,6 +250,16 @@ class _VideoUNetBase(nn.Module):
         self._engine().use_graphs = bool(on)
         return self
 
+    def set_frame_sharding(self, group=None, enable: bool = True):
+        """Spread ONE sample's frames over the ranks of `group` (default: WORLD): rank r computes frames
+        [r*F/P, (r+1)*F/P); see videomv_b200/parallel.py. Every rank must make the same calls with the same inputs and
+        receives the full output."""
+        from . import parallel
+        eng = self._engine()
+        eng.shard = parallel.ShardCtx(group) if enable else None
+        eng._graphs.clear()
+        return self
+
     def graph_launches(self) -> int:
         """Kernels per graph replay, summed over captured graphs (0 when none)."""
         eng = self.__dict__.get("_eng")
