@@ -1,0 +1,50 @@
+"""torchrun worker: frame-sharded forward (P ranks, NCCL) must equal the single-GPU forward.
+Launched by tests/test_sharded_gpu.py (needs >= 2 GPUs)."""
+import os
+import sys
+
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests.test_oracle_cpu import load_case  # noqa: E402
+from tests.test_unet_gpu import build  # noqa: E402
+
+
+def main():
+    rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    meta, d, _ = load_case("t2v_small_t981_cam")                  # 24 frames, 8x8 latent -> 1x1 at the deepest level
+    world = dist.get_world_size()
+    # deepest level must have >= world pixels: use a 16x16 latent (-> 2x2) for 2..4 ranks
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(1, 4, 24, 16, 16, generator=g).cuda()
+    model, _ = build(meta, meta["seed_w"])
+    kw = dict(y=d["y"].cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
+    ref = model(x, d["t"].cuda(), **kw)
+    model.set_frame_sharding()
+    out = model(x, d["t"].cuda(), **kw)
+    rel = ((out - ref).norm() / ref.norm()).item()
+    ncoll = model._engine().shard.collectives
+    print(f"[sharded] rank {rank}/{world}: rel_l2 vs single-GPU {rel:.3e}, {ncoll} collectives per forward", flush=True)
+    ok = torch.tensor([1 if rel < 6e-3 else 0], device="cuda")
+    # graphs with captured NCCL collectives
+    try:
+        model.enable_cuda_graphs(True)
+        og = model(x, d["t"].cuda(), **kw)
+        og2 = model(x, d["t"].cuda(), **kw)
+        relg = ((og2 - ref).norm() / ref.norm()).item()
+        print(f"[sharded] rank {rank}: graph replay rel_l2 {relg:.3e}", flush=True)
+        ok *= 1 if relg < 6e-3 else 0
+    except Exception as e:  # noqa: BLE001
+        print(f"[sharded] rank {rank}: graph capture with NCCL failed: {e!r}", flush=True)
+        ok *= 0
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if int(ok.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
