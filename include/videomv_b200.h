@@ -66,6 +66,10 @@ typedef struct vmv_gemm_params {
     const void* rowbias; int64_t ld_rowbias; int32_t rows_per_group;  /* fp16 [M/rows_per_group, N] or NULL */
     const void* residual; int64_t ldr;                                /* fp16 [M, N_out] or NULL */
     int32_t act;
+    /* LayerNorm folded into this GEMM (nn.LayerNorm util.py:528-530 feeding nn.Linear): A holds the RAW rows, W holds
+     * W*gamma, bias holds bias + W@beta, and the epilogue computes  rstd[m]*(acc - mean[m]*ln_colsum[n]) + bias[n]
+     * with ln_stats[m] = {mean, rstd} (vmv_layernorm_stats) and ln_colsum[n] = sum_k W'[n,k].  NULL = off. */
+    const void* ln_stats; const float* ln_colsum;
     /* tuning (0 = auto) */
     int32_t block_n;            /* 64 (variant 1 only), 128, 160 or 256 */
     int32_t stages;             /* smem pipeline depth */
@@ -97,6 +101,8 @@ int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2
                         const float* gamma, const float* beta, float eps, int32_t silu,
                         void* out, int64_t ldo, void* stream);
 
+/* Per-row LayerNorm statistics only: stats[m] = {mean, 1/sqrt(var+eps)} fp32 (for the folded form in vmv_gemm). */
+int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float eps, void* stats, void* stream);
 /* LayerNorm over the last dim (eps 1e-5): nn.LayerNorm util.py:528-530.  x,out fp16 [M,C]. */
 int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,
                   float eps, void* out, int64_t ldo, void* stream);

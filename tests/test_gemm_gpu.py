@@ -120,6 +120,32 @@ def test_split_k(M, N, K, split, variant):
     assert_close(f"splitk M{M} N{N} K{K} s{split}", out, ref)
 
 
+@pytest.mark.parametrize("M,C,N,geglu", [(24576, 320, 960, False), (1536, 1280, 1280, False), (1000, 512, 4096, True),
+                                         (6144, 640, 5120, True)])
+def test_folded_layernorm(M, C, N, geglu, variant):
+    """LayerNorm folded into the consumer GEMM == nn.LayerNorm -> nn.Linear (-> GEGLU) on the same fp16 rows."""
+    from videomv_b200 import ops, packing
+    h = _r(M, C, seed=1, scale=1.7) + 0.3
+    w = torch.randn(N, C, device="cuda") * C ** -0.5
+    b = torch.randn(N, device="cuda")
+    gamma = 1 + 0.2 * torch.randn(C, device="cuda")
+    beta = 0.2 * torch.randn(C, device="cuda")
+    wg, bf = packing.fold_layernorm(w, b, gamma, beta)
+    if geglu:
+        wp, bp, bn = packing.pack_geglu(wg, bf)
+    else:
+        wp, bp, bn = wg.half().contiguous(), bf, 0
+    colsum = wp.float().sum(1).contiguous()
+    out = ops.gemm(h, wp, bias=bp, ln_stats=ops.layernorm_stats(h), ln_colsum=colsum, block_n=bn,
+                   act=ops.ACT_GEGLU if geglu else ops.ACT_NONE, variant=variant)
+    ref = F.linear(F.layer_norm(h.float(), (C,), gamma, beta, 1e-5), w, b)
+    if geglu:
+        val, gate = ref.chunk(2, dim=-1)
+        ref = val * F.gelu(gate)
+    # the folded form rounds W*gamma (not LN(h)) to fp16: same error budget as the unfused pair, different roundings
+    assert_close(f"folded LN M{M} C{C} N{N} geglu{int(geglu)}", out, ref, rtol=2e-3, atol=2e-3)
+
+
 def test_bad_args_raise():
     from videomv_b200 import ops
     a, w = _r(128, 100), _r(64, 100)

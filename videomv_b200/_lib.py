@@ -74,7 +74,7 @@ class GemmParams(ctypes.Structure):
         ("W", c_vp), ("ldw", c_i64), ("D", c_vp), ("ldd", c_i64),
         ("B", c_i32), ("F", c_i32), ("H", c_i32), ("Wd", c_i32),
         ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
-        ("residual", c_vp), ("ldr", c_i64), ("act", c_i32),
+        ("residual", c_vp), ("ldr", c_i64), ("act", c_i32), ("ln_stats", c_vp), ("ln_colsum", c_vp),
         ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32), ("variant", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
@@ -105,6 +105,7 @@ SYMBOLS = {
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
     "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
+    "vmv_layernorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
     "vmv_attention": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),
     "vmv_upsample_nearest2x": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),

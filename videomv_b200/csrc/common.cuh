@@ -36,13 +36,13 @@ void set_error(const char* fmt, ...);   // api.cu: stores the message for vmv_la
 // ----------------------------------------------------------------------------
 // small math
 // ----------------------------------------------------------------------------
-__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // 2 MUFU + 2 FP ops
 // exact (erf) GELU: F.gelu default, reference util.py:550.
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 output rounding): two MUFU ops (ex2, rcp)
 // plus a 5-term Horner polynomial instead of erff()'s branchy ~30-instruction sequence.
 __device__ __forceinline__ float erf_as_f(float x) {
     const float ax = fabsf(x);
-    const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
     float p = fmaf(1.061405429f, t, -1.453152027f);
     p = fmaf(p, t, 1.421413741f);
     p = fmaf(p, t, -0.284496736f);

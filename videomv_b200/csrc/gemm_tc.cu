@@ -50,6 +50,8 @@ struct GemmArgs {
     long long ldr;
     int act;
     float* partial;   // split-K: fp32 [splits, M, N]
+    const float2* ln_stats;   // folded LayerNorm: per-row {mean, rstd}
+    const float* ln_colsum;   // folded LayerNorm: per-column sum of the gamma-scaled weights
     int tma_epi;      // v2: epilogue stores (and residual loads) go through TMA + swizzled smem staging
     int d3d;          // TMA epilogue maps are (n, F*HW, B) (temporal conv: tiles never straddle samples)
 };
@@ -142,6 +144,11 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& a, int nt, int sp
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
+                    if (a.ln_stats) {
+                        const float2 ms = a.ln_stats[grow];
+                        val = ms.y * (val - ms.x * __ldg(a.ln_colsum + n0 + c + j));
+                        gate = ms.y * (gate - ms.x * __ldg(a.ln_colsum + n0 + HB + c + j));
+                    }
                     if (a.bias) {
                         val += __ldg(a.bias + n0 + c + j);
                         gate += __ldg(a.bias + n0 + HB + c + j);
@@ -183,6 +190,11 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& a, int nt, int sp
                 float x[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
+                if (a.ln_stats) {
+                    const float2 ms = a.ln_stats[grow];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) x[j] = ms.y * (x[j] - ms.x * __ldg(a.ln_colsum + n + j));
+                }
                 if (a.bias) {
                     const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
 #pragma unroll
@@ -382,28 +394,33 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 constexpr int EPI_BLK_COLS = 32;                 // epilogue column block: 32 fp16 = 64 B rows, SWIZZLE_64B boxes
 constexpr int EPI_BLK_BYTES = 32 * 64;            // 32 rows x 64 B per warp per block
 
-template <int BN, int STAGES>
+constexpr int V2_THREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int V2_EPI_WARPS = 8;
+
+template <int BN, int STAGES, int NBLK_>
 struct SmemLayout2 {
     static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
-    static constexpr int NBLK = BN / EPI_BLK_COLS;
+    static constexpr int NBLK = NBLK_;                                        // max output blocks per tile
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    static constexpr int DST_OFF = B_OFF + STAGES * B_STAGE_BYTES;            // 4 warps x 2 buffers
-    static constexpr int RES_OFF = DST_OFF + 4 * 2 * EPI_BLK_BYTES;           // 4 warps x NBLK blocks
-    static constexpr int BAR_OFF = RES_OFF + 4 * NBLK * EPI_BLK_BYTES;
-    static constexpr int NBARS = 2 * STAGES + 4 + 4;
+    // epilogue block pool: [tile parity 2][lane quarter 4][NBLK] swizzled 32x32 fp16 blocks.  A block first receives
+    // the residual (TMA load, prefetched), is updated in place with the result, and is stored from there (TMA store).
+    static constexpr int POOL_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+    static constexpr int BAR_OFF = POOL_OFF + 2 * 4 * NBLK * EPI_BLK_BYTES;
+    static constexpr int NBARS = 2 * STAGES + 4 + V2_EPI_WARPS;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
     static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-template <int BN, int STAGES>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(192, 1)
+// NBLK = output 32-column blocks per tile the pool is sized for: BN/32, or BN/64 for a GEGLU-only instance
+template <int BN, int STAGES, int NBLK>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD,
                 const __grid_constant__ CUtensorMap tmR, const GemmArgs a, const int m_pairs, const int n_tiles,
                 const int splits) {
-    using L = SmemLayout2<BN, STAGES>;
+    using L = SmemLayout2<BN, STAGES, NBLK>;
     constexpr int TCOLS = TmemCols<2 * BN>::value;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
     extern __shared__ uint8_t smem_raw[];
@@ -412,8 +429,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
-    uint64_t* res_bar = tmem_empty_bar + 2;            // [4], one per epilogue warp (residual tile landed)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + 4);
+    uint64_t* res_bar = tmem_empty_bar + 2;            // [8], one per epilogue warp (its residual blocks landed)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + V2_EPI_WARPS);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -434,9 +451,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
-            mbar_init(&tmem_empty_bar[b], 8);
+            mbar_init(&tmem_empty_bar[b], 2 * V2_EPI_WARPS);
         }
-        for (int w = 0; w < 4; ++w) mbar_init(&res_bar[w], 1);
+        for (int w = 0; w < V2_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
         if (a.tma_epi) {
             tma_prefetch_desc(&tmD);
             if (a.residual) tma_prefetch_desc(&tmR);
@@ -530,13 +547,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         }
         __syncwarp();
     } else {
-        // ---------------------------------- epilogue (both CTAs) ----------------------------------
+        // ---------------------------------- epilogue (both CTAs, 8 warps) ----------------------------------
+        // Warp w may only touch TMEM lanes [32*(w%4), +32).  Two warps share each lane quarter and split the tile's
+        // 32-column output blocks between them (even / odd), which doubles the issue slots and the latency hiding of
+        // this otherwise single-warp-per-scheduler phase.
         const int q = warp & 3;
+        const int hh = (warp - 2) >> 2;                         // 0: even blocks, 1: odd blocks
         const int r = q * 32 + lane;
-        uint8_t* dstage = smem + L::DST_OFF + q * 2 * EPI_BLK_BYTES;
-        uint8_t* rstage = smem + L::RES_OFF + q * L::NBLK * EPI_BLK_BYTES;
-        uint64_t* rbar = &res_bar[q];
-        uint32_t res_phase = 0, dbuf = 0;
+        uint64_t* rbar = &res_bar[warp - 2];
+        uint32_t res_phase = 0;
         const bool geglu = a.act == VMV_ACT_GEGLU;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
         const int swz = (lane >> 1) & 3;                        // SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
@@ -550,6 +569,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const uint32_t aph = (acc_it >> 1) & 1;
             const long long grow = tile_row_to_global(a, mt, r);
             const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
+            uint8_t* pool = smem + L::POOL_OFF + ((buf * 4 + q) * L::NBLK) * EPI_BLK_BYTES;
             int cb = 0, nvalid = 0;
             long long row0 = 0;
             const int col0 = nt * out_bn;
@@ -557,28 +577,39 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 row0 = tile_row0(a, mt, q * 32, &cb);
                 nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
                 if (nvalid < 0) nvalid = 0;
-                if (a.residual && lane == 0 && nvalid > 0) {
-                    // prefetch this warp's 32 x out_bn residual slab; it lands while the MMAs of this tile run
-                    mbar_arrive_expect_tx(rbar, (uint32_t)nvalid * EPI_BLK_BYTES);
-                    for (int blk = 0; blk < nvalid; ++blk) {
-                        if (a.d3d) tma_load_3d(rstage + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0, cb);
-                        else tma_load_2d(rstage + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0);
+                if (lane == 0) {
+                    // this pool half was last used two tiles ago: all but the newest store group must have been read
+                    bulk_wait_group_read<1>();
+                    if (a.residual) {
+                        // prefetch this warp's residual blocks; they land while the MMAs of this tile run
+                        const int mine = (nvalid - hh + 1) / 2;
+                        if (mine > 0) {
+                            mbar_arrive_expect_tx(rbar, (uint32_t)mine * EPI_BLK_BYTES);
+                            for (int blk = hh; blk < nvalid; blk += 2) {
+                                if (a.d3d) tma_load_3d(pool + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0, cb);
+                                else tma_load_2d(pool + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0);
+                            }
+                        }
                     }
                 }
+                __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
             tc_fence_after();
             if (!a.tma_epi) {
-                epilogue_store<BN>(a, nt, split, grow, grow >= 0, trow);
+                if (hh == 0) epilogue_store<BN>(a, nt, split, grow, grow >= 0, trow);     // split-K partials: one warp per quarter
             } else {
                 const bool valid = grow >= 0;
-                if (a.residual && nvalid > 0) {
+                if (a.residual && hh < nvalid) {
                     mbar_wait(rbar, res_phase);
                     res_phase ^= 1;
                 }
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
+                float2 ms = make_float2(0.f, 1.f);
+                const bool ln = a.ln_stats != nullptr && valid;
+                if (ln) ms = a.ln_stats[grow];
 #pragma unroll 1
-                for (int blk = 0; blk < nvalid; ++blk) {
+                for (int blk = hh; blk < nvalid; blk += 2) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
                     float x[32];
                     if (geglu) {
@@ -587,11 +618,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         for (int h = 0; h < 2; ++h) {
                             tmem_ld_32x32b_x16(trow + c + 16 * h, v);
                             tmem_ld_32x32b_x16(trow + BN / 2 + c + 16 * h, g);
-                            tmem_ld_wait();
+                            const int nv = nt * BN + c + 16 * h, ng = nv + BN / 2;     // GEMM columns of value / gate
                             float bv[16], bg[16];
                             if (a.bias) {
-                                const float4* pv = reinterpret_cast<const float4*>(a.bias + nt * BN + c + 16 * h);
-                                const float4* pg = reinterpret_cast<const float4*>(a.bias + nt * BN + BN / 2 + c + 16 * h);
+                                const float4* pv = reinterpret_cast<const float4*>(a.bias + nv);
+                                const float4* pg = reinterpret_cast<const float4*>(a.bias + ng);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     const float4 x4 = __ldg(pv + j), y4 = __ldg(pg + j);
@@ -602,25 +633,44 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) { bv[j] = 0.f; bg[j] = 0.f; }
                             }
+                            float sv[16], sg[16];
+                            if (ln) {
+                                const float4* pv = reinterpret_cast<const float4*>(a.ln_colsum + nv);
+                                const float4* pg = reinterpret_cast<const float4*>(a.ln_colsum + ng);
 #pragma unroll
-                            for (int j = 0; j < 16; ++j)
-                                x[16 * h + j] = (__uint_as_float(v[j]) + bv[j]) * gelu_erf_f(__uint_as_float(g[j]) + bg[j]);
+                                for (int j = 0; j < 4; ++j) {
+                                    const float4 x4 = __ldg(pv + j), y4 = __ldg(pg + j);
+                                    sv[4 * j] = x4.x; sv[4 * j + 1] = x4.y; sv[4 * j + 2] = x4.z; sv[4 * j + 3] = x4.w;
+                                    sg[4 * j] = y4.x; sg[4 * j + 1] = y4.y; sg[4 * j + 2] = y4.z; sg[4 * j + 3] = y4.w;
+                                }
+                            }
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) {
+                                float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
+                                if (ln) {
+                                    val = ms.y * (val - ms.x * sv[j]);
+                                    gate = ms.y * (gate - ms.x * sg[j]);
+                                }
+                                x[16 * h + j] = (val + bv[j]) * gelu_erf_f(gate + bg[j]);
+                            }
                         }
                     } else {
                         uint32_t v[32];
                         tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
                         tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                        tmem_ld_wait();
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]);
                         const int n = col0 + c;
+                        float bb[32];
                         if (a.bias) {
                             const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float4 b4 = __ldg(bp + j);
-                                x[4 * j] += b4.x; x[4 * j + 1] += b4.y; x[4 * j + 2] += b4.z; x[4 * j + 3] += b4.w;
+                                const float4 b4 = __ldg(bp + j);
+                                bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
                             }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) bb[j] = 0.f;
                         }
                         if (rb) {
                             const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
@@ -631,48 +681,57 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     float2 f = unpack_half2(w[j]);
-                                    x[8 * h + 2 * j] += f.x;
-                                    x[8 * h + 2 * j + 1] += f.y;
+                                    bb[8 * h + 2 * j] += f.x;
+                                    bb[8 * h + 2 * j + 1] += f.y;
                                 }
                             }
+                        }
+                        tmem_ld_wait();
+                        if (ln) {
+                            const float4* sp = reinterpret_cast<const float4*>(a.ln_colsum + n);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 c4 = __ldg(sp + j);
+                                x[4 * j] = ms.y * (__uint_as_float(v[4 * j]) - ms.x * c4.x) + bb[4 * j];
+                                x[4 * j + 1] = ms.y * (__uint_as_float(v[4 * j + 1]) - ms.x * c4.y) + bb[4 * j + 1];
+                                x[4 * j + 2] = ms.y * (__uint_as_float(v[4 * j + 2]) - ms.x * c4.z) + bb[4 * j + 2];
+                                x[4 * j + 3] = ms.y * (__uint_as_float(v[4 * j + 3]) - ms.x * c4.w) + bb[4 * j + 3];
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bb[j];
                         }
                         if (a.act == VMV_ACT_SILU) {
 #pragma unroll
                             for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
                         }
                     }
-                    if (a.residual) {
-                        const uint8_t* rrow = rstage + blk * EPI_BLK_BYTES + lane * 64;
+                    // the block's pool slot holds the residual (if any): update in place, then hand it to the TMA engine
+                    uint8_t* prow = pool + blk * EPI_BLK_BYTES + lane * 64;
 #pragma unroll
-                        for (int h = 0; h < 4; ++h) {
-                            uint4 u = *reinterpret_cast<const uint4*>(rrow + ((h ^ swz) << 4));
-                            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+                    for (int h = 0; h < 4; ++h) {
+                        uint4* pc = reinterpret_cast<uint4*>(prow + ((h ^ swz) << 4));
+                        if (a.residual) {
+                            const uint4 u = *pc;
+                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                float2 f = unpack_half2(w[j]);
+                                const float2 f = unpack_half2(w[j]);
                                 x[8 * h + 2 * j] += f.x;
                                 x[8 * h + 2 * j + 1] += f.y;
                             }
                         }
+                        *pc = make_uint4(pack_half2(x[8 * h], x[8 * h + 1]), pack_half2(x[8 * h + 2], x[8 * h + 3]),
+                                         pack_half2(x[8 * h + 4], x[8 * h + 5]), pack_half2(x[8 * h + 6], x[8 * h + 7]));
                     }
-                    // stage the 32 x 32 fp16 block (swizzled) and hand it to the TMA engine
-                    uint8_t* dptr = dstage + (dbuf & 1) * EPI_BLK_BYTES;
-                    if (lane == 0) bulk_wait_group_read<1>();        // the store that last read this buffer is done
-                    __syncwarp();
-#pragma unroll
-                    for (int h = 0; h < 4; ++h)
-                        *reinterpret_cast<uint4*>(dptr + lane * 64 + ((h ^ swz) << 4)) =
-                            make_uint4(pack_half2(x[8 * h], x[8 * h + 1]), pack_half2(x[8 * h + 2], x[8 * h + 3]),
-                                       pack_half2(x[8 * h + 4], x[8 * h + 5]), pack_half2(x[8 * h + 6], x[8 * h + 7]));
                     fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        if (a.d3d) tma_store_3d(&tmD, dptr, col0 + c, (int)row0, cb);
-                        else tma_store_2d(&tmD, dptr, col0 + c, (int)row0);
-                        bulk_commit_group();
+                        if (a.d3d) tma_store_3d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0, cb);
+                        else tma_store_2d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0);
                     }
-                    ++dbuf;
                 }
+                if (lane == 0) bulk_commit_group();              // one store group per tile (see wait at the top)
             }
             tc_fence_before();
             __syncwarp();
@@ -704,6 +763,11 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
         float4 u = p[0], w = p[1];
         x[0] += u.x; x[1] += u.y; x[2] += u.z; x[3] += u.w;
         x[4] += w.x; x[5] += w.y; x[6] += w.z; x[7] += w.w;
+    }
+    if (a.ln_stats) {
+        const float2 ms = a.ln_stats[row];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = ms.y * (x[j] - ms.x * a.ln_colsum[n + j]);
     }
     if (a.bias) {
 #pragma unroll
@@ -793,14 +857,14 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
     return VMV_OK;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int NBLK>
 static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const CUtensorMap& tD,
                             const CUtensorMap& tR, const GemmArgs& a, int m_pairs, int n_tiles, int splits,
                             cudaStream_t st) {
-    using L = SmemLayout2<BN, STAGES>;
+    using L = SmemLayout2<BN, STAGES, NBLK>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::DYN_BYTES);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(v2 smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(e));
@@ -818,7 +882,7 @@ static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, cons
     const long long total = (long long)m_pairs * n_tiles * splits;
     int clusters = num_sms / 2;
     if (total < clusters) clusters = (int)total;
-    gemm_tc2_kernel<BN, STAGES><<<dim3(2 * clusters), 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, tD, tR, a, m_pairs, n_tiles,
+    gemm_tc2_kernel<BN, STAGES, NBLK><<<dim3(2 * clusters), V2_THREADS, L::DYN_BYTES, st>>>(tA1, tA2, tW, tD, tR, a, m_pairs, n_tiles,
                                                                                splits);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
@@ -831,8 +895,7 @@ static int pick_block_n(const vmv_gemm_params* p, int variant) {
     if (variant == 2) {
         if (p->act == VMV_ACT_GEGLU) return (N % 256 == 0) ? 256 : 128;   // BN/2 must be a multiple of 32
         if (N % 160 == 0) return 160;
-        if (N % 256 == 0) return 256;
-        return 128;
+        return 128;                        // 256-wide tiles are reserved for GEGLU (their output is 128 wide)
     }
     if (p->act == VMV_ACT_GEGLU) return (N % 160 == 0) ? 160 : 128;
     if (N % 160 == 0) return 160;
@@ -877,6 +940,9 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1;
     a.residual = static_cast<const __half*>(p->residual);
     a.ldr = p->ldr;
+    a.ln_stats = static_cast<const float2*>(p->ln_stats);
+    a.ln_colsum = p->ln_colsum;
+    VMV_CHECK_ARG((p->ln_stats == nullptr) == (p->ln_colsum == nullptr), "vmv_gemm: ln_stats and ln_colsum go together");
     if (p->rowbias) VMV_CHECK_ARG(p->ld_rowbias % 8 == 0, "vmv_gemm: ld_rowbias must be a multiple of 8");
     if (p->residual) VMV_CHECK_ARG(p->ldr % 8 == 0, "vmv_gemm: ldr must be a multiple of 8");
 
@@ -1027,9 +1093,10 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
             if ((rc = epi_map(&tD, p->D, p->ldd)) != VMV_OK) return rc;
             if (p->residual && (rc = epi_map(&tR, p->residual, p->ldr)) != VMV_OK) return rc;
         }
-        if (BN == 128) rc = launch_instance2<128, 6>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 6>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else rc = launch_instance2<256, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        if (BN == 128) rc = launch_instance2<128, 6, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (BN == 160) rc = launch_instance2<160, 5, 5>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (p->act == VMV_ACT_GEGLU) rc = launch_instance2<256, 5, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else rc = launch_instance2<256, 3, 8>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
         // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one

@@ -221,9 +221,60 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, long long M, int C
     }
 }
 
+// mean / rstd of each row (exact two-pass in registers), no normalised output: the consumer GEMM folds the affine part.
+__global__ void __launch_bounds__(256)
+layernorm_stats_kernel(const __half* __restrict__ x, long long ldx, long long M, int C, float eps, float2* __restrict__ stats) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const int nvec = C / 8;
+    float v[LN_MAX_VEC][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < nvec) {
+            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vec * 8));
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(w[j]);
+                v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
+                sum += f.x + f.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_MAX_VEC; ++i) {
+        const int vec = lane + i * 32;
+        if (vec < nvec) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { float d = v[i][j] - mean; sq += d * d; }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(sq / (float)C + eps));
+}
+
 }  // namespace vmv
 
 using namespace vmv;
+
+extern "C" int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float eps, void* stats, void* stream) {
+    VMV_CHECK_ARG(x && stats, "vmv_layernorm_stats: null pointer");
+    VMV_CHECK_ARG(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 32 * 8 && ldx % 8 == 0 && M > 0, "vmv_layernorm_stats: bad C/ld/M");
+    const int wpb = 8;
+    layernorm_stats_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), ldx, M, C, eps, static_cast<float2*>(stats));
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_layernorm_stats");
+    return VMV_OK;
+}
 
 static int gn_check(const char* who, const void* x1, int64_t ldx1, int C1, const void* x2, int64_t ldx2, int C2,
                     int64_t rows_per_batch, int nbatch) {

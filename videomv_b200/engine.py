@@ -24,11 +24,11 @@ SM_COUNT = 148
 
 
 class _W:
-    """Packed fp16 weight [N,K] + fp32 bias."""
-    __slots__ = ("w", "b", "bn")
+    """Packed fp16 weight [N,K] + fp32 bias (+ column sums when a LayerNorm is folded in)."""
+    __slots__ = ("w", "b", "bn", "colsum")
 
-    def __init__(self, w, b=None, bn=0):
-        self.w, self.b, self.bn = w, b, bn
+    def __init__(self, w, b=None, bn=0, colsum=None):
+        self.w, self.b, self.bn, self.colsum = w, b, bn, colsum
 
 
 def _f32(p):
@@ -57,23 +57,29 @@ class UNetEngine:
     def _lin(self, layer, bias=True) -> _W:
         return _W(packing.pack_linear(layer.weight.detach()), _f32(layer.bias) if bias and layer.bias is not None else None)
 
+    def _folded(self, ws, bias, norm, geglu=False) -> _W:
+        """Linear(s) `ws` (row-concatenated) consuming LayerNorm `norm`: fold gamma/beta into the weights/bias."""
+        w = torch.cat([z.detach().reshape(z.shape[0], -1) for z in ws], 0)
+        wg, bf = packing.fold_layernorm(w, bias, norm.weight, norm.bias)
+        if geglu:
+            wp, bp, bn = packing.pack_geglu(wg, bf)
+        else:
+            wp, bp, bn = wg.to(torch.float16).contiguous(), bf, 0
+        return _W(wp, bp, bn, wp.float().sum(1).contiguous())
+
     def _pack_tblock(self, tb, cross: bool):
         d = {}
         a1, a2 = tb.attn1, tb.attn2
-        d["qkv1"] = _W(packing.pack_cat(a1.to_q.weight.detach(), a1.to_k.weight.detach(), a1.to_v.weight.detach()))
+        d["qkv1"] = self._folded([a1.to_q.weight, a1.to_k.weight, a1.to_v.weight], None, tb.norm1)
         d["o1"] = self._lin(a1.to_out[0])
         if cross:
-            d["q2"] = _W(packing.pack_linear(a2.to_q.weight.detach()))
+            d["q2"] = self._folded([a2.to_q.weight], None, tb.norm2)
             d["kv2_w"] = packing.pack_cat(a2.to_k.weight.detach(), a2.to_v.weight.detach())   # gathered into kv_all
         else:
-            d["qkv2"] = _W(packing.pack_cat(a2.to_q.weight.detach(), a2.to_k.weight.detach(), a2.to_v.weight.detach()))
+            d["qkv2"] = self._folded([a2.to_q.weight, a2.to_k.weight, a2.to_v.weight], None, tb.norm2)
         d["o2"] = self._lin(a2.to_out[0])
-        w, b, bn = packing.pack_geglu(tb.ff.net[0].proj.weight.detach(), tb.ff.net[0].proj.bias.detach())
-        d["ff1"] = _W(w, b, bn)
+        d["ff1"] = self._folded([tb.ff.net[0].proj.weight], tb.ff.net[0].proj.bias, tb.norm3, geglu=True)
         d["ff2"] = self._lin(tb.ff.net[2])
-        for i in (1, 2, 3):
-            n = getattr(tb, f"norm{i}")
-            d[f"ln{i}"] = (_f32(n.weight), _f32(n.bias))
         return d
 
     def _pack_block(self, mod):
@@ -158,20 +164,27 @@ class UNetEngine:
         M = a.shape[0]
         N = w.w.shape[0]
         bn = w.bn or (160 if N % 160 == 0 else 128)
-        # the persistent kernel runs 74 CTA pairs, each on 256 x bn tiles; split K when there are too few tiles
+        # The persistent kernel runs one CTA pair per 2 SMs (74 pairs) on 256 x bn tiles.  When the tile count is a
+        # poor fit for 74 (few tiles at the 8x8 / 4x4 levels) split K so the last wave is not mostly idle.
         tiles = ((M + 255) // 256) * ((N + bn - 1) // bn)
         nkb = w.w.shape[1] // 64
+        pairs = SM_COUNT // 2
         split = 0
-        if kw.get("act", 0) != ops.ACT_GEGLU and tiles * 2 <= SM_COUNT // 2 and nkb >= 16:
-            split = min(nkb // 8, max(1, (SM_COUNT // 2) // tiles))
-            if split >= 2:
+        if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs:
+            def util(s_):
+                t_ = tiles * s_
+                return t_ / (-(-t_ // pairs) * pairs)
+            best, best_u = 1, util(1)
+            for s_ in range(2, min(nkb // 8, 8) + 1):
+                if util(s_) > best_u + 0.08:
+                    best, best_u = s_, util(s_)
+            if best >= 2:
+                split = best
                 need = split * M * N * 4
                 if self._ws is None or self._ws.numel() < need:
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 kw["workspace"] = self._ws
-            else:
-                split = 0
-        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, **kw)
+        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, ln_colsum=w.colsum if "ln_stats" in kw else None, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
     # blocks
@@ -238,21 +251,19 @@ class UNetEngine:
                               q_strides=st, k_strides=st, v_strides=st, o_strides=(HW * C, 0, C))
             return o
 
-        n = ops.layernorm(h, *tb["ln1"])
-        h = self._gemm(self_attn(self._gemm(n, tb["qkv1"])), tb["o1"], residual=h)
-        n = ops.layernorm(h, *tb["ln2"])
+        # the three LayerNorms are folded into the GEMMs that consume them: only per-row {mean, rstd} is computed
+        h = self._gemm(self_attn(self._gemm(h, tb["qkv1"], ln_stats=ops.layernorm_stats(h))), tb["o1"], residual=h)
         if temporal:
-            h = self._gemm(self_attn(self._gemm(n, tb["qkv2"])), tb["o2"], residual=h)
+            h = self._gemm(self_attn(self._gemm(h, tb["qkv2"], ln_stats=ops.layernorm_stats(h))), tb["o2"], residual=h)
         else:
-            q = self._gemm(n, tb["q2"])
+            q = self._gemm(h, tb["q2"], ln_stats=ops.layernorm_stats(h))
             kview, vview, L, ldkv = kv
             o = torch.empty((M, C), dtype=torch.float16, device=h.device)
             ops.attention(q, kview, vview, o, outer=B * Fr, inner=1, heads=heads, nq=HW, nk=L,
                           q_strides=(HW * C, 0, C), k_strides=(L * ldkv, 0, ldkv), v_strides=(L * ldkv, 0, ldkv),
                           o_strides=(HW * C, 0, C), kv_group=Fr)
             h = self._gemm(o, tb["o2"], residual=h)
-        n = ops.layernorm(h, *tb["ln3"])
-        g = self._gemm(n, tb["ff1"], act=ops.ACT_GEGLU)
+        g = self._gemm(h, tb["ff1"], act=ops.ACT_GEGLU, ln_stats=ops.layernorm_stats(h))
         return self._gemm(g, tb["ff2"], residual=h)
 
     def _spatial(self, d, x, S):

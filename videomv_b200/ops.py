@@ -54,7 +54,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          bias: Optional[torch.Tensor] = None, rowbias: Optional[torch.Tensor] = None, rows_per_group: int = 0,
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
-         workspace: Optional[torch.Tensor] = None, variant: int = 0) -> torch.Tensor:
+         workspace: Optional[torch.Tensor] = None, variant: int = 0, ln_stats: Optional[torch.Tensor] = None,
+         ln_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -88,6 +89,10 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     if residual is not None:
         _rows(residual, "gemm residual")
         p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
+    if ln_stats is not None:
+        if ln_stats.dtype != torch.float32 or ln_stats.numel() != 2 * M or ln_colsum is None or ln_colsum.numel() != N:
+            raise ValueError("gemm ln_stats must be fp32 [M,2] and ln_colsum fp32 [N]")
+        p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
     p.act, p.block_n, p.stages, p.split_k, p.variant = act, block_n, stages, split_k, variant
     if split_k > 1:
         need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
@@ -138,6 +143,17 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
                                 rows_per_batch, nbatch, stats.data_ptr(), stat_rows, gamma.data_ptr(), beta.data_ptr(),
                                 float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
     _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))     # stats read + apply read + write
+    return out
+
+
+def layernorm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """Per-row {mean, rstd} fp32 [M,2] for a LayerNorm folded into the consuming GEMM (see `gemm(ln_stats=...)`)."""
+    _rows(x, "layernorm_stats x")
+    out = torch.empty((x.shape[0], 2), dtype=torch.float32, device=x.device)
+    e0 = _prof_begin()
+    check(_lib.lib().vmv_layernorm_stats(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(eps), out.data_ptr(),
+                                         _stream()), "vmv_layernorm_stats")
+    _prof_end(e0, "layernorm", 0.0, 2.0 * x.shape[0] * x.shape[1])
     return out
 
 

@@ -54,3 +54,14 @@ def pack_geglu(w: torch.Tensor, b: torch.Tensor):
 def pack_cat(*ws: torch.Tensor) -> torch.Tensor:
     """Row-concatenate several [Ni,K] projections (fused QKV / KV)."""
     return torch.cat([pack_linear(w) for w in ws], dim=0).contiguous()
+
+
+def fold_layernorm(w: torch.Tensor, b, gamma: torch.Tensor, beta: torch.Tensor):
+    """LayerNorm(gamma, beta) followed by Linear(w, b)  ==  rstd*(x @ (w*gamma)^T - mean*colsum) + (b + w @ beta).
+    Returns (w*gamma fp32 [N,K], fp32 bias b + w@beta). The caller packs the weight and takes colsum of the PACKED fp16
+    values (so the mean correction cancels exactly what the tensor cores accumulated)."""
+    w32 = w.detach().reshape(w.shape[0], -1).float()
+    bias = w32 @ beta.detach().float()
+    if b is not None:
+        bias = bias + b.detach().float()
+    return w32 * gamma.detach().float()[None, :], bias.contiguous()
