@@ -142,8 +142,11 @@ def test_folded_layernorm(M, C, N, geglu, variant):
     if geglu:
         val, gate = ref.chunk(2, dim=-1)
         ref = val * F.gelu(gate)
-    # the folded form rounds W*gamma (not LN(h)) to fp16: same error budget as the unfused pair, different roundings
-    assert_close(f"folded LN M{M} C{C} N{N} geglu{int(geglu)}", out, ref, rtol=2e-3, atol=2e-3)
+    # The reference here is fp32 end to end, so unlike the other tests the bound must also cover the fp16 rounding of
+    # the weights (W*gamma here, W and LN(h) in the unfused pair): ~2x fp16 eps on each GEMM output, and GEGLU multiplies
+    # two such outputs (value * gelu(gate)), hence the doubled bound for it.
+    tol = 4e-3 if geglu else 2e-3
+    assert_close(f"folded LN M{M} C{C} N{N} geglu{int(geglu)}", out, ref, rtol=tol, atol=tol)
 
 
 def test_bad_args_raise():

@@ -52,6 +52,7 @@ struct GemmArgs {
     float* partial;   // split-K: fp32 [splits, M, N]
     const float2* ln_stats;   // folded LayerNorm: per-row {mean, rstd}
     const float* ln_colsum;   // folded LayerNorm: per-column sum of the gamma-scaled weights
+    int dbg;          // profiling experiments (VMV_GEMM_DEBUG): 1 = skip the TMA stores, 2 = skip the whole epilogue body
     int tma_epi;      // v2: epilogue stores (and residual loads) go through TMA + swizzled smem staging
     int d3d;          // TMA epilogue maps are (n, F*HW, B) (temporal conv: tiles never straddle samples)
 };
@@ -598,6 +599,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             tc_fence_after();
             if (!a.tma_epi) {
                 if (hh == 0) epilogue_store<BN>(a, nt, split, grow, grow >= 0, trow);     // split-K partials: one warp per quarter
+            } else if (a.dbg & 2) {
+                if (a.residual && hh < nvalid) { mbar_wait(rbar, res_phase); res_phase ^= 1; }
             } else {
                 const bool valid = grow >= 0;
                 if (a.residual && hh < nvalid) {
@@ -726,7 +729,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     }
                     fence_proxy_async();
                     __syncwarp();
-                    if (lane == 0) {
+                    if (lane == 0 && !(a.dbg & 1)) {
                         if (a.d3d) tma_store_3d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0, cb);
                         else tma_store_2d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0);
                     }
@@ -940,6 +943,11 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1;
     a.residual = static_cast<const __half*>(p->residual);
     a.ldr = p->ldr;
+    {
+        static int dbg = -1;
+        if (dbg < 0) { const char* e = getenv("VMV_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
+        a.dbg = dbg;
+    }
     a.ln_stats = static_cast<const float2*>(p->ln_stats);
     a.ln_colsum = p->ln_colsum;
     VMV_CHECK_ARG((p->ln_stats == nullptr) == (p->ln_colsum == nullptr), "vmv_gemm: ln_stats and ln_colsum go together");

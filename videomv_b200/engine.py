@@ -171,14 +171,16 @@ class UNetEngine:
         pairs = SM_COUNT // 2
         split = 0
         if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs:
-            def util(s_):
+            # time(s) ~ T_full / utilisation(s) + cost of the fp32 partials (write + read back + extra launch)
+            t_full = 2.0 * M * N * nkb * 64 / 0.9e15
+
+            def est(s_):
                 t_ = tiles * s_
-                return t_ / (-(-t_ // pairs) * pairs)
-            best, best_u = 1, util(1)
-            for s_ in range(2, min(nkb // 8, 8) + 1):
-                if util(s_) > best_u + 0.08:
-                    best, best_u = s_, util(s_)
-            if best >= 2:
+                u = t_ / (-(-t_ // pairs) * pairs)
+                extra = 0.0 if s_ == 1 else (2.0 * s_ * M * N * 4 + M * N * 2) / 5e12 + 5e-6
+                return t_full / u + extra
+            best = min(range(1, min(nkb // 8, 8) + 1), key=est)
+            if best >= 2 and est(best) < 0.9 * est(1):
                 split = best
                 need = split * M * N * 4
                 if self._ws is None or self._ws.numel() < need:
