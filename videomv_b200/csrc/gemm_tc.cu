@@ -53,8 +53,7 @@ struct GemmArgs {
     const float2* ln_stats;   // folded LayerNorm: per-row {mean, rstd}
     const float* ln_colsum;   // folded LayerNorm: per-column sum of the gamma-scaled weights
     int dbg;          // profiling experiments (VMV_GEMM_DEBUG): 1 = skip the TMA stores, 2 = skip the whole epilogue body
-    int tma_epi;      // v2: epilogue stores (and residual loads) go through TMA + swizzled smem staging
-    int d3d;          // TMA epilogue maps are (n, F*HW, B) (temporal conv: tiles never straddle samples)
+    int fast_epi;     // v2: register epilogue with 256-bit global accesses (needs 32 B aligned D / residual / rowbias rows)
 };
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
@@ -401,25 +400,25 @@ constexpr int V2_EPI_WARPS = 8;
 template <int BN, int STAGES, int NBLK_>
 struct SmemLayout2 {
     static constexpr int B_STAGE_BYTES = (BN / 2) * BK * 2;
-    static constexpr int NBLK = NBLK_;                                        // max output blocks per tile
+    static constexpr int NBLK = NBLK_;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    // epilogue block pool: [tile parity 2][lane quarter 4][NBLK] swizzled 32x32 fp16 blocks.  A block first receives
-    // the residual (TMA load, prefetched), is updated in place with the result, and is stored from there (TMA store).
-    static constexpr int POOL_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int BAR_OFF = POOL_OFF + 2 * 4 * NBLK * EPI_BLK_BYTES;
-    static constexpr int NBARS = 2 * STAGES + 4 + V2_EPI_WARPS;
+    // per-epilogue-warp scratch: 128 bias floats + 128 LayerNorm column sums for the columns the warp owns in the
+    // current tile (fetched before the accumulator is ready, read back with LDS on the critical path)
+    static constexpr int SCR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
+    static constexpr int SCR_BYTES_PER_WARP = 2 * 128 * 4;
+    static constexpr int BAR_OFF = SCR_OFF + V2_EPI_WARPS * SCR_BYTES_PER_WARP;
+    static constexpr int NBARS = 2 * STAGES + 4;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
     static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
 };
 
-// NBLK = output 32-column blocks per tile the pool is sized for: BN/32, or BN/64 for a GEGLU-only instance
+// NBLK is unused by the register epilogue (kept so instantiations stay distinct per use)
 template <int BN, int STAGES, int NBLK>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
-                const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmD,
-                const __grid_constant__ CUtensorMap tmR, const GemmArgs a, const int m_pairs, const int n_tiles,
+                const __grid_constant__ CUtensorMap tmW, const GemmArgs a, const int m_pairs, const int n_tiles,
                 const int splits) {
     using L = SmemLayout2<BN, STAGES, NBLK>;
     constexpr int TCOLS = TmemCols<2 * BN>::value;
@@ -430,8 +429,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tmem_full_bar = empty_bar + STAGES;      // [2]
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;      // [2], used in the leader only
-    uint64_t* res_bar = tmem_empty_bar + 2;            // [8], one per epilogue warp (its residual blocks landed)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(res_bar + V2_EPI_WARPS);
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -453,11 +451,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         for (int b = 0; b < 2; ++b) {
             mbar_init(&tmem_full_bar[b], 1);
             mbar_init(&tmem_empty_bar[b], 2 * V2_EPI_WARPS);
-        }
-        for (int w = 0; w < V2_EPI_WARPS; ++w) mbar_init(&res_bar[w], 1);
-        if (a.tma_epi) {
-            tma_prefetch_desc(&tmD);
-            if (a.residual) tma_prefetch_desc(&tmR);
         }
         fence_barrier_init();
     }
@@ -549,17 +542,19 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         __syncwarp();
     } else {
         // ---------------------------------- epilogue (both CTAs, 8 warps) ----------------------------------
-        // Warp w may only touch TMEM lanes [32*(w%4), +32).  Two warps share each lane quarter and split the tile's
-        // 32-column output blocks between them (even / odd), which doubles the issue slots and the latency hiding of
-        // this otherwise single-warp-per-scheduler phase.
+        // Warp w may only touch TMEM lanes [32*(w%4), +32): two warps share each lane quarter and split the tile's
+        // 32-column output blocks (even / odd) -- twice the issue slots and latency hiding of a 4-warp epilogue.
+        // Each lane owns one output row: per block it drains 32 fp32 accumulators (2 x tcgen05.ld.x16), applies the
+        // fused epilogue and writes 64 contiguous bytes with two 256-bit stores (full 32 B sectors, no staging).
+        // Global-latency loads are taken off the accumulator critical path: bias / LayerNorm column sums are staged in
+        // smem before the tile's MMAs finish, and the residual of block i+1 is requested before block i is processed.
         const int q = warp & 3;
         const int hh = (warp - 2) >> 2;                         // 0: even blocks, 1: odd blocks
         const int r = q * 32 + lane;
-        uint64_t* rbar = &res_bar[warp - 2];
-        uint32_t res_phase = 0;
+        float* sbias = reinterpret_cast<float*>(smem + L::SCR_OFF + (warp - 2) * L::SCR_BYTES_PER_WARP);
+        float* scol = sbias + 128;
         const bool geglu = a.act == VMV_ACT_GEGLU;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
-        const int swz = (lane >> 1) & 3;                        // SWIZZLE_64B: 16B-chunk index ^= (row >> 1) & 3
         int acc_it = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
             const int split = t / tiles_mn;
@@ -569,172 +564,122 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int buf = acc_it & 1;
             const uint32_t aph = (acc_it >> 1) & 1;
             const long long grow = tile_row_to_global(a, mt, r);
+            const bool valid = grow >= 0;
             const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-            uint8_t* pool = smem + L::POOL_OFF + ((buf * 4 + q) * L::NBLK) * EPI_BLK_BYTES;
-            int cb = 0, nvalid = 0;
-            long long row0 = 0;
             const int col0 = nt * out_bn;
-            if (a.tma_epi) {
-                row0 = tile_row0(a, mt, q * 32, &cb);
-                nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
-                if (nvalid < 0) nvalid = 0;
-                if (lane == 0) {
-                    // this pool half was last used two tiles ago: all but the newest store group must have been read
-                    bulk_wait_group_read<1>();
-                    if (a.residual) {
-                        // prefetch this warp's residual blocks; they land while the MMAs of this tile run
-                        const int mine = (nvalid - hh + 1) / 2;
-                        if (mine > 0) {
-                            mbar_arrive_expect_tx(rbar, (uint32_t)mine * EPI_BLK_BYTES);
-                            for (int blk = hh; blk < nvalid; blk += 2) {
-                                if (a.d3d) tma_load_3d(pool + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0, cb);
-                                else tma_load_2d(pool + blk * EPI_BLK_BYTES, &tmR, rbar, col0 + blk * EPI_BLK_COLS, (int)row0);
-                            }
-                        }
+            int nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
+            if (nvalid < 0) nvalid = 0;
+            const __half* resrow = (a.residual && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
+            uint32_t rcur[16];
+            if (a.fast_epi) {
+                // (1) stage this warp's bias / column-sum slices.  Slot j*32+i holds column (hh+2j)*32+i of the tile;
+                //     GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
+                __syncwarp();                                   // previous tile's readers are done with the scratch
+                const int nmine = (nvalid - hh + 1) / 2;
+                if (a.bias || a.ln_colsum) {
+                    const int per = geglu ? 64 : 32;
+                    for (int i = lane; i < nmine * per; i += 32) {
+                        const int j = i / per, w = i - j * per;
+                        const int blk = hh + 2 * j;
+                        const int n = geglu ? nt * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0 + blk * 32 + w;
+                        sbias[i] = a.bias ? __ldg(a.bias + n) : 0.f;
+                        if (a.ln_colsum) scol[i] = __ldg(a.ln_colsum + n);
                     }
+                }
+                // (2) request the residual of my first block
+                if (resrow && hh < nvalid) {
+                    ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
+                    ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                 }
                 __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
             tc_fence_after();
-            if (!a.tma_epi) {
-                if (hh == 0) epilogue_store<BN>(a, nt, split, grow, grow >= 0, trow);     // split-K partials: one warp per quarter
-            } else if (a.dbg & 2) {
-                if (a.residual && hh < nvalid) { mbar_wait(rbar, res_phase); res_phase ^= 1; }
-            } else {
-                const bool valid = grow >= 0;
-                if (a.residual && hh < nvalid) {
-                    mbar_wait(rbar, res_phase);
-                    res_phase ^= 1;
-                }
+            if (!a.fast_epi) {
+                if (hh == 0) epilogue_store<BN>(a, nt, split, grow, valid, trow);     // split-K partials / unaligned outputs
+            } else if (!(a.dbg & 2)) {
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
                 float2 ms = make_float2(0.f, 1.f);
                 const bool ln = a.ln_stats != nullptr && valid;
                 if (ln) ms = a.ln_stats[grow];
+                const bool has_b = a.bias != nullptr;
+                int j = 0;
 #pragma unroll 1
-                for (int blk = hh; blk < nvalid; blk += 2) {
+                for (int blk = hh; blk < nvalid; blk += 2, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
                     float x[32];
+                    uint32_t v[32];
                     if (geglu) {
-                        uint32_t v[16], g[16];
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            tmem_ld_32x32b_x16(trow + c + 16 * h, v);
-                            tmem_ld_32x32b_x16(trow + BN / 2 + c + 16 * h, g);
-                            const int nv = nt * BN + c + 16 * h, ng = nv + BN / 2;     // GEMM columns of value / gate
-                            float bv[16], bg[16];
-                            if (a.bias) {
-                                const float4* pv = reinterpret_cast<const float4*>(a.bias + nv);
-                                const float4* pg = reinterpret_cast<const float4*>(a.bias + ng);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 x4 = __ldg(pv + j), y4 = __ldg(pg + j);
-                                    bv[4 * j] = x4.x; bv[4 * j + 1] = x4.y; bv[4 * j + 2] = x4.z; bv[4 * j + 3] = x4.w;
-                                    bg[4 * j] = y4.x; bg[4 * j + 1] = y4.y; bg[4 * j + 2] = y4.z; bg[4 * j + 3] = y4.w;
-                                }
-                            } else {
-#pragma unroll
-                                for (int j = 0; j < 16; ++j) { bv[j] = 0.f; bg[j] = 0.f; }
-                            }
-                            float sv[16], sg[16];
-                            if (ln) {
-                                const float4* pv = reinterpret_cast<const float4*>(a.ln_colsum + nv);
-                                const float4* pg = reinterpret_cast<const float4*>(a.ln_colsum + ng);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    const float4 x4 = __ldg(pv + j), y4 = __ldg(pg + j);
-                                    sv[4 * j] = x4.x; sv[4 * j + 1] = x4.y; sv[4 * j + 2] = x4.z; sv[4 * j + 3] = x4.w;
-                                    sg[4 * j] = y4.x; sg[4 * j + 1] = y4.y; sg[4 * j + 2] = y4.z; sg[4 * j + 3] = y4.w;
-                                }
-                            }
-                            tmem_ld_wait();
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
-                                if (ln) {
-                                    val = ms.y * (val - ms.x * sv[j]);
-                                    gate = ms.y * (gate - ms.x * sg[j]);
-                                }
-                                x[16 * h + j] = (val + bv[j]) * gelu_erf_f(gate + bg[j]);
-                            }
-                        }
-                    } else {
-                        uint32_t v[32];
+                        uint32_t g[32];
                         tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
                         tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                        const int n = col0 + c;
-                        float bb[32];
-                        if (a.bias) {
-                            const float4* bp = reinterpret_cast<const float4*>(a.bias + n);
+                        tmem_ld_32x32b_x16(trow + BN / 2 + c, *reinterpret_cast<uint32_t(*)[16]>(&g[0]));
+                        tmem_ld_32x32b_x16(trow + BN / 2 + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&g[16]));
+                        tmem_ld_wait();
+                        const float* bv = sbias + j * 64;
+                        const float* cv = scol + j * 64;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 b4 = __ldg(bp + j);
-                                bb[4 * j] = b4.x; bb[4 * j + 1] = b4.y; bb[4 * j + 2] = b4.z; bb[4 * j + 3] = b4.w;
+                        for (int i = 0; i < 32; ++i) {
+                            float val = __uint_as_float(v[i]), gate = __uint_as_float(g[i]);
+                            if (ln) {
+                                val = ms.y * (val - ms.x * cv[i]);
+                                gate = ms.y * (gate - ms.x * cv[32 + i]);
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) bb[j] = 0.f;
+                            if (has_b) { val += bv[i]; gate += bv[32 + i]; }
+                            x[i] = val * gelu_erf_f(gate);
                         }
+                    } else {
+                        tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                        tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                        uint32_t rbv[16];
                         if (rb) {
-                            const uint4* rp = reinterpret_cast<const uint4*>(rb + n);
-#pragma unroll
-                            for (int h = 0; h < 4; ++h) {
-                                uint4 u = __ldg(rp + h);
-                                uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                                for (int j = 0; j < 4; ++j) {
-                                    float2 f = unpack_half2(w[j]);
-                                    bb[8 * h + 2 * j] += f.x;
-                                    bb[8 * h + 2 * j + 1] += f.y;
-                                }
-                            }
+                            ldg256(rb + col0 + c, *reinterpret_cast<uint32_t(*)[8]>(&rbv[0]));
+                            ldg256(rb + col0 + c + 16, *reinterpret_cast<uint32_t(*)[8]>(&rbv[8]));
                         }
                         tmem_ld_wait();
-                        if (ln) {
-                            const float4* sp = reinterpret_cast<const float4*>(a.ln_colsum + n);
+                        const float* bv = sbias + j * 32;
+                        const float* cv = scol + j * 32;
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const float4 c4 = __ldg(sp + j);
-                                x[4 * j] = ms.y * (__uint_as_float(v[4 * j]) - ms.x * c4.x) + bb[4 * j];
-                                x[4 * j + 1] = ms.y * (__uint_as_float(v[4 * j + 1]) - ms.x * c4.y) + bb[4 * j + 1];
-                                x[4 * j + 2] = ms.y * (__uint_as_float(v[4 * j + 2]) - ms.x * c4.z) + bb[4 * j + 2];
-                                x[4 * j + 3] = ms.y * (__uint_as_float(v[4 * j + 3]) - ms.x * c4.w) + bb[4 * j + 3];
+                        for (int i = 0; i < 32; ++i) {
+                            float val = __uint_as_float(v[i]);
+                            if (ln) val = ms.y * (val - ms.x * cv[i]);
+                            if (has_b) val += bv[i];
+                            x[i] = val;
+                        }
+                        if (rb) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) {
+                                const float2 f = unpack_half2(rbv[i]);
+                                x[2 * i] += f.x;
+                                x[2 * i + 1] += f.y;
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + bb[j];
                         }
                         if (a.act == VMV_ACT_SILU) {
 #pragma unroll
-                            for (int j = 0; j < 32; ++j) x[j] = silu_f(x[j]);
+                            for (int i = 0; i < 32; ++i) x[i] = silu_f(x[i]);
                         }
                     }
-                    // the block's pool slot holds the residual (if any): update in place, then hand it to the TMA engine
-                    uint8_t* prow = pool + blk * EPI_BLK_BYTES + lane * 64;
+                    if (resrow) {
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        uint4* pc = reinterpret_cast<uint4*>(prow + ((h ^ swz) << 4));
-                        if (a.residual) {
-                            const uint4 u = *pc;
-                            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const float2 f = unpack_half2(w[j]);
-                                x[8 * h + 2 * j] += f.x;
-                                x[8 * h + 2 * j + 1] += f.y;
-                            }
+                        for (int i = 0; i < 16; ++i) {
+                            const float2 f = unpack_half2(rcur[i]);
+                            x[2 * i] += f.x;
+                            x[2 * i + 1] += f.y;
                         }
-                        *pc = make_uint4(pack_half2(x[8 * h], x[8 * h + 1]), pack_half2(x[8 * h + 2], x[8 * h + 3]),
-                                         pack_half2(x[8 * h + 4], x[8 * h + 5]), pack_half2(x[8 * h + 6], x[8 * h + 7]));
+                        if (blk + 2 < nvalid) {                 // request the next block's residual now
+                            ldg256(resrow + (blk + 2) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
+                            ldg256(resrow + (blk + 2) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
+                        }
                     }
-                    fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0 && !(a.dbg & 1)) {
-                        if (a.d3d) tma_store_3d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0, cb);
-                        else tma_store_2d(&tmD, pool + blk * EPI_BLK_BYTES, col0 + c, (int)row0);
+                    if (valid && !(a.dbg & 1)) {
+                        uint32_t o[16];
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
+                        __half* dst = a.D + grow * a.ldd + col0 + c;
+                        stg256(dst, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
+                        stg256(dst + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
                     }
                 }
-                if (lane == 0) bulk_commit_group();              // one store group per tile (see wait at the top)
             }
             tc_fence_before();
             __syncwarp();
@@ -743,7 +688,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
             }
         }
-        if (lane == 0) bulk_wait_group<0>();                         // all TMA stores of this warp have completed
     }
 
     tc_fence_before();
@@ -861,9 +805,8 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
 }
 
 template <int BN, int STAGES, int NBLK>
-static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const CUtensorMap& tD,
-                            const CUtensorMap& tR, const GemmArgs& a, int m_pairs, int n_tiles, int splits,
-                            cudaStream_t st) {
+static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
+                            int m_pairs, int n_tiles, int splits, cudaStream_t st) {
     using L = SmemLayout2<BN, STAGES, NBLK>;
     static bool attr_set = false;
     if (!attr_set) {
@@ -885,8 +828,7 @@ static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, cons
     const long long total = (long long)m_pairs * n_tiles * splits;
     int clusters = num_sms / 2;
     if (total < clusters) clusters = (int)total;
-    gemm_tc2_kernel<BN, STAGES, NBLK><<<dim3(2 * clusters), V2_THREADS, L::DYN_BYTES, st>>>(tA1, tA2, tW, tD, tR, a, m_pairs, n_tiles,
-                                                                               splits);
+    gemm_tc2_kernel<BN, STAGES, NBLK><<<dim3(2 * clusters), V2_THREADS, L::DYN_BYTES, st>>>(tA1, tA2, tW, a, m_pairs, n_tiles, splits);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
     return VMV_OK;
@@ -1080,31 +1022,14 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
 
     if (pl.variant == 2) {
         const int m_pairs = (pl.m_tiles + 1) / 2;
-        CUtensorMap tD = tW, tR = tW;
         if (pl.splits <= 1) {
-            // epilogue through TMA: 32-column x 32-row fp16 boxes, 64B swizzle (see epilogue in gemm_tc2_kernel)
             VMV_CHECK_ARG(!(p->act == VMV_ACT_GEGLU && p->residual), "vmv_gemm: GEGLU with residual is not supported");
-            a.tma_epi = 1;
-            a.d3d = p->mode == VMV_GEMM_TCONV3;
-            cuuint32_t box[3] = {EPI_BLK_COLS, 32, 1};
-            auto epi_map = [&](CUtensorMap* m, const void* base, long long ld) -> int {
-                if (a.d3d) {
-                    const cuuint64_t rows = (cuuint64_t)a.F * a.HW;
-                    cuuint64_t dims[3] = {(cuuint64_t)a.n_out, rows, (cuuint64_t)p->B};
-                    cuuint64_t strides[2] = {(cuuint64_t)ld * 2, (cuuint64_t)ld * 2 * rows};
-                    return make_map(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
-                }
-                cuuint64_t dims[2] = {(cuuint64_t)a.n_out, (cuuint64_t)p->M};
-                cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-                return make_map(m, base, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
-            };
-            if ((rc = epi_map(&tD, p->D, p->ldd)) != VMV_OK) return rc;
-            if (p->residual && (rc = epi_map(&tR, p->residual, p->ldr)) != VMV_OK) return rc;
+            auto al32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };
+            a.fast_epi = al32(p->D, p->ldd) && al32(p->residual, p->ldr) && al32(p->rowbias, p->ld_rowbias) ? 1 : 0;
         }
-        if (BN == 128) rc = launch_instance2<128, 6, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 5, 5>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (p->act == VMV_ACT_GEGLU) rc = launch_instance2<256, 5, 4>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else rc = launch_instance2<256, 3, 8>(tA1, tA2, tW, tD, tR, a, m_pairs, pl.n_tiles, pl.splits, st);
+        if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
         // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one

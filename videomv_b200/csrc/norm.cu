@@ -222,43 +222,54 @@ layernorm_kernel(const __half* __restrict__ x, long long ldx, long long M, int C
 }
 
 // mean / rstd of each row (exact two-pass in registers), no normalised output: the consumer GEMM folds the affine part.
+// A warp handles ROWS rows at once and issues all of their 16 B loads before reducing (memory-level parallelism:
+// this kernel is a pure read stream); NV = vectors per lane per row.
+template <int NV, int ROWS>
 __global__ void __launch_bounds__(256)
 layernorm_stats_kernel(const __half* __restrict__ x, long long ldx, long long M, int C, float eps, float2* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= M) return;
+    const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
+    if (row0 >= M) return;
     const int nvec = C / 8;
-    float v[LN_MAX_VEC][8];
-    float sum = 0.f;
+    uint4 u[ROWS][NV];
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        const int vec = lane + i * 32;
-        if (vec < nvec) {
-            uint4 u = __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vec * 8));
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (int rr = 0; rr < ROWS; ++rr) {
+        const long long row = row0 + rr < M ? row0 + rr : M - 1;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const int vec = lane + i * 32;
+            u[rr][i] = vec < nvec ? __ldg(reinterpret_cast<const uint4*>(x + row * ldx + vec * 8)) : make_uint4(0, 0, 0, 0);
+        }
+    }
+#pragma unroll
+    for (int rr = 0; rr < ROWS; ++rr) {
+        float v[NV][8];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            const uint32_t w[4] = {u[rr][i].x, u[rr][i].y, u[rr][i].z, u[rr][i].w};
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(w[j]);
+                const float2 f = unpack_half2(w[j]);
                 v[i][2 * j] = f.x; v[i][2 * j + 1] = f.y;
-                sum += f.x + f.y;
+                sum += f.x + f.y;                       // zero padding beyond nvec adds nothing
             }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / (float)C;
-    float sq = 0.f;
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)C;
+        float sq = 0.f;
 #pragma unroll
-    for (int i = 0; i < LN_MAX_VEC; ++i) {
-        const int vec = lane + i * 32;
-        if (vec < nvec) {
+        for (int i = 0; i < NV; ++i) {
+            if (lane + i * 32 < nvec) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { float d = v[i][j] - mean; sq += d * d; }
+                for (int j = 0; j < 8; ++j) { const float d = v[i][j] - mean; sq += d * d; }
+            }
         }
-    }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
-    if (lane == 0) stats[row] = make_float2(mean, rsqrtf(sq / (float)C + eps));
+        for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        if (lane == 0 && row0 + rr < M) stats[row0 + rr] = make_float2(mean, rsqrtf(sq / (float)C + eps));
+    }
 }
 
 }  // namespace vmv
@@ -269,8 +280,17 @@ extern "C" int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_
     VMV_CHECK_ARG(x && stats, "vmv_layernorm_stats: null pointer");
     VMV_CHECK_ARG(C > 0 && C % 8 == 0 && C <= LN_MAX_VEC * 32 * 8 && ldx % 8 == 0 && M > 0, "vmv_layernorm_stats: bad C/ld/M");
     const int wpb = 8;
-    layernorm_stats_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const __half*>(x), ldx, M, C, eps, static_cast<float2*>(stats));
+    const int nv = (C / 8 + 31) / 32;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const __half* xp = static_cast<const __half*>(x);
+    float2* sp = static_cast<float2*>(stats);
+#define VMV_LNS(NV_, R_) layernorm_stats_kernel<NV_, R_><<<(unsigned)((M + wpb * R_ - 1) / (wpb * R_)), wpb * 32, 0, st>>>(xp, ldx, M, C, eps, sp)
+    if (nv <= 1) VMV_LNS(1, 4);
+    else if (nv == 2) VMV_LNS(2, 4);
+    else if (nv == 3) VMV_LNS(3, 2);
+    else if (nv <= 5) VMV_LNS(5, 2);
+    else VMV_LNS(8, 1);
+#undef VMV_LNS
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_layernorm_stats");
     return VMV_OK;
