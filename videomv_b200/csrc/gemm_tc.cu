@@ -1025,7 +1025,9 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
         if (pl.splits <= 1) {
             VMV_CHECK_ARG(!(p->act == VMV_ACT_GEGLU && p->residual), "vmv_gemm: GEGLU with residual is not supported");
             auto al32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };
-            a.fast_epi = al32(p->D, p->ldd) && al32(p->residual, p->ldr) && al32(p->rowbias, p->ld_rowbias) ? 1 : 0;
+            a.fast_epi = (a.n_out % EPI_BLK_COLS == 0) && al32(p->D, p->ldd) && al32(p->residual, p->ldr) &&
+                                 al32(p->rowbias, p->ld_rowbias)
+                             ? 1 : 0;
         }
         if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
         else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
