@@ -144,6 +144,10 @@ int vmv_conv3x3_in(const float* x1, int32_t C1, const float* x2, int32_t C2, int
  * -> out fp32 NCFHW [B,Cout,F,H,W] */
 int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, int32_t W, int32_t C, const float* w,
                     const float* bias, int32_t Cout, float* out, void* stream);
+/* channels-last fp16 rows [B*F*H*W, ldx] (first Cout columns) -> fp32 NCFHW [B,Cout,F,H,W]: the final rearrange of
+ * unet_t2v.py:368 when the head conv runs on the tensor cores (vmv_gemm CONV3X3 with Cout zero-padded to 16 columns) */
+int vmv_rows_to_ncfhw(const void* x, int64_t ldx, int32_t B, int32_t F, int32_t H, int32_t W, int32_t Cout, float* out,
+                      void* stream);
 /* sinusoidal_embedding util.py:177-189: t int64 [B] -> out fp16 [B, dim] = [cos | sin] */
 int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out, void* stream);
 /* e[b*F+f, :] = silu( t_emb[b,:] (+ t_emb2[b,:]) (+ cam_emb[b*F+f,:]) )   (unet_t2v.py:326-335 + the nn.SiLU

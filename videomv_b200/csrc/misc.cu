@@ -170,6 +170,19 @@ conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int
     }
 }
 
+// [M, ld] fp16 rows (first Cout columns valid) -> fp32 NCFHW [B,Cout,F,H,W]   (head conv output, unet_t2v.py:368)
+__global__ void rows_to_ncfhw_kernel(const __half* __restrict__ x, long long ld, int B, int F, long long HW, int Cout,
+                                     float* __restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over B*Cout*F*HW outputs
+    const long long total = (long long)B * Cout * F * HW;
+    if (i >= total) return;
+    const long long p = i % HW;
+    const int f = (int)((i / HW) % F);
+    const int co = (int)((i / (HW * F)) % Cout);
+    const long long b = i / (HW * F * Cout);
+    out[i] = __half2float(x[((b * F + f) * HW + p) * ld + co]);
+}
+
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, int B, int dim, __half* __restrict__ out) {
     const int half_dim = dim / 2;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -276,6 +289,17 @@ extern "C" int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, i
         static_cast<const __half*>(x), B, F, H, W, C, w, bias, out);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_out");
+    return VMV_OK;
+}
+
+extern "C" int vmv_rows_to_ncfhw(const void* x, int64_t ldx, int32_t B, int32_t F, int32_t H, int32_t W, int32_t Cout,
+                                 float* out, void* stream) {
+    VMV_CHECK_ARG(x && out && B > 0 && F > 0 && H > 0 && W > 0 && Cout > 0 && ldx >= Cout, "vmv_rows_to_ncfhw: bad args");
+    const long long total = (long long)B * Cout * F * H * W;
+    rows_to_ncfhw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(x), ldx, B, F, (long long)H * W, Cout, out);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_rows_to_ncfhw");
     return VMV_OK;
 }
 

@@ -152,6 +152,14 @@ class UNetEngine:
         self.dec = [self._pack_block(b) for b in m.output_blocks]
         self.head_gn = (_f32(m.out[0].weight), _f32(m.out[0].bias))
         self.head_w, self.head_b = _f32(m.out[2].weight), _f32(m.out[2].bias)
+        # head conv on the tensor cores: Cout (4) zero-padded to 16 GEMM columns
+        hw = m.out[2].weight.detach()
+        self.head_cout = hw.shape[0]
+        hpad = torch.zeros((16, hw.shape[1], 3, 3), dtype=hw.dtype, device=hw.device)
+        hpad[: hw.shape[0]] = hw
+        bpad = torch.zeros(16, dtype=torch.float32, device=hw.device)
+        bpad[: hw.shape[0]] = m.out[2].bias.detach().float()
+        self.head_gemm = _W(packing.pack_conv3x3(hpad), bpad, 128) if hw.shape[0] <= 16 and hw.shape[1] % 64 == 0 else None
         # one GEMM produces every ResBlock's emb projection / every cross-attention's K,V
         self.emb_all = _W(torch.cat(self._emb_w, 0).contiguous(), torch.cat(self._emb_b, 0).contiguous())
         self.kv_all = _W(torch.cat(self._kv_w, 0).contiguous())
@@ -417,7 +425,11 @@ class UNetEngine:
         for blk in self.dec:
             h = self._run_block(blk, h, skips.pop(), S)
         a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True)
-        out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
+        if self.head_gemm is not None:
+            o16 = self._gemm(a, self.head_gemm, mode=ops.CONV3X3, geom=(1, B * Fr, S["H"], S["W"]))
+            out = ops.rows_to_ncfhw(o16, B, Fr, S["H"], S["W"], self.head_cout)
+        else:
+            out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
         return out if sh is None else parallel.gather_frames(out, sh)
 
     # ------------------------------------------------------------------------------------------------------------

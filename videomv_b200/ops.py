@@ -235,6 +235,15 @@ def conv3x3_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, B: int, F:
     return out
 
 
+def rows_to_ncfhw(x: torch.Tensor, B: int, F: int, H: int, W: int, cout: int) -> torch.Tensor:
+    """fp16 rows [B*F*H*W, >=cout] -> fp32 [B,cout,F,H,W]."""
+    _rows(x, "rows_to_ncfhw x")
+    out = torch.empty((B, cout, F, H, W), dtype=torch.float32, device=x.device)
+    check(_lib.lib().vmv_rows_to_ncfhw(x.data_ptr(), x.stride(0), B, F, H, W, cout, out.data_ptr(), _stream()),
+          "vmv_rows_to_ncfhw")
+    return out
+
+
 def sinusoidal_embedding(t: torch.Tensor, dim: int) -> torch.Tensor:
     assert t.dtype == torch.int64 and t.is_cuda and t.is_contiguous()
     out = torch.empty((t.shape[0], dim), dtype=torch.float16, device=t.device)
