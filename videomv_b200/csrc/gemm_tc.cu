@@ -406,7 +406,7 @@ struct SmemLayout2 {
     // per-epilogue-warp scratch: 128 bias floats + 128 LayerNorm column sums for the columns the warp owns in the
     // current tile (fetched before the accumulator is ready, read back with LDS on the critical path)
     static constexpr int SCR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int SCR_BYTES_PER_WARP = 2 * 2 * 128 * 4;           // double-buffered over tiles
+    static constexpr int SCR_BYTES_PER_WARP = 2 * 128 * 4;
     static constexpr int BAR_OFF = SCR_OFF + V2_EPI_WARPS * SCR_BYTES_PER_WARP;
     static constexpr int NBARS = 2 * STAGES + 4;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
@@ -551,99 +551,61 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int q = warp & 3;
         const int hh = (warp - 2) >> 2;                         // 0: even blocks, 1: odd blocks
         const int r = q * 32 + lane;
-        float* scratch = reinterpret_cast<float*>(smem + L::SCR_OFF + (warp - 2) * L::SCR_BYTES_PER_WARP);
+        float* sbias = reinterpret_cast<float*>(smem + L::SCR_OFF + (warp - 2) * L::SCR_BYTES_PER_WARP);
+        float* scol = sbias + 128;
         const bool geglu = a.act == VMV_ACT_GEGLU;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
-        const int per = geglu ? 64 : 32;                        // scratch slots per owned block
-        const bool has_vec = a.fast_epi && (a.bias != nullptr || a.ln_colsum != nullptr);
-
-        struct EpiTile { int nt, mt, split, col0, nvalid; long long grow; };
-        auto decode = [&](int t) {
-            EpiTile e;
-            e.split = t / tiles_mn;
-            const int rem = t - e.split * tiles_mn;
-            const int mp = rem / n_tiles;
-            e.nt = rem - mp * n_tiles;
-            e.mt = 2 * mp + (int)rank;
-            e.col0 = e.nt * out_bn;
-            e.nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - e.col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
-            if (e.nvalid < 0) e.nvalid = 0;
-            e.grow = tile_row_to_global(a, e.mt, r);
-            return e;
-        };
-        // per-column vectors of the blocks this warp owns in tile e: slot j*per+w <-> block hh+2j (GEGLU: w>=32 = gate)
-        auto vec_load = [&](const EpiTile& e, float (&nb)[4], float (&nc)[4]) {
-            const int nslots = ((e.nvalid - hh + 1) / 2) * per;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = lane + 32 * k;
-                nb[k] = 0.f; nc[k] = 0.f;
-                if (i < nslots) {
-                    const int j = i / per, w = i - j * per, blk = hh + 2 * j;
-                    const int n = geglu ? e.nt * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : e.col0 + blk * 32 + w;
-                    if (a.bias) nb[k] = __ldg(a.bias + n);
-                    if (a.ln_colsum) nc[k] = __ldg(a.ln_colsum + n);
-                }
-            }
-        };
-        auto res_ptr = [&](const EpiTile& e) -> const __half* {
-            return (a.residual && e.grow >= 0) ? a.residual + e.grow * a.ldr + e.col0 : nullptr;
-        };
-
-        // software pipeline over tiles: everything tile i+1 needs from global memory before its accumulator is ready
-        // (bias / column-sum slices, first residual block) is requested while tile i is being drained.
-        EpiTile cur = decode(cluster_id < total_tiles ? cluster_id : 0);
-        uint32_t rcur[16], rnext[16];
-        float nb[4], nc[4];
-        if (a.fast_epi && cluster_id < total_tiles) {
-            if (has_vec) {
-                vec_load(cur, nb, nc);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) { scratch[lane + 32 * k] = nb[k]; scratch[128 + lane + 32 * k] = nc[k]; }
-            }
-            const __half* rp0 = res_ptr(cur);
-            if (rp0 && hh < cur.nvalid) {
-                ldg256(rp0 + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
-                ldg256(rp0 + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
-            }
-            __syncwarp();
-        }
         int acc_it = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
+            const int split = t / tiles_mn;
+            const int rem = t - split * tiles_mn;
+            const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
+            const int mt = 2 * mp + (int)rank;
             const int buf = acc_it & 1;
             const uint32_t aph = (acc_it >> 1) & 1;
-            const bool valid = cur.grow >= 0;
+            const long long grow = tile_row_to_global(a, mt, r);
+            const bool valid = grow >= 0;
             const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
-            const float* sbias = scratch + buf * 256;
-            const float* scol = sbias + 128;
-            const __half* resrow = res_ptr(cur);
-            // requests for the next tile (consumed after this tile is drained)
-            const int tn = t + num_clusters;
-            const bool has_next = a.fast_epi && tn < total_tiles;
-            EpiTile nxt = cur;
-            if (has_next) {
-                nxt = decode(tn);
-                if (has_vec) vec_load(nxt, nb, nc);
-                const __half* rpn = res_ptr(nxt);
-                if (rpn && hh < nxt.nvalid) {
-                    ldg256(rpn + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rnext[0]));
-                    ldg256(rpn + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rnext[8]));
+            const int col0 = nt * out_bn;
+            int nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
+            if (nvalid < 0) nvalid = 0;
+            const __half* resrow = (a.residual && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
+            uint32_t rcur[16];
+            if (a.fast_epi) {
+                // (1) stage this warp's bias / column-sum slices.  Slot j*32+i holds column (hh+2j)*32+i of the tile;
+                //     GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
+                __syncwarp();                                   // previous tile's readers are done with the scratch
+                const int nmine = (nvalid - hh + 1) / 2;
+                if (a.bias || a.ln_colsum) {
+                    const int per = geglu ? 64 : 32;
+                    for (int i = lane; i < nmine * per; i += 32) {
+                        const int j = i / per, w = i - j * per;
+                        const int blk = hh + 2 * j;
+                        const int n = geglu ? nt * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0 + blk * 32 + w;
+                        sbias[i] = a.bias ? __ldg(a.bias + n) : 0.f;
+                        if (a.ln_colsum) scol[i] = __ldg(a.ln_colsum + n);
+                    }
                 }
+                // (2) request the residual of my first block
+                if (resrow && hh < nvalid) {
+                    ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
+                    ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
+                }
+                __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
             tc_fence_after();
             if (!a.fast_epi) {
-                if (hh == 0) epilogue_store<BN>(a, cur.nt, cur.split, cur.grow, valid, trow);   // split-K partials / unaligned
+                if (hh == 0) epilogue_store<BN>(a, nt, split, grow, valid, trow);     // split-K partials / unaligned outputs
             } else if (!(a.dbg & 2)) {
-                const __half* rb = (a.rowbias && valid) ? a.rowbias + (cur.grow / a.rows_per_group) * a.ld_rowbias : nullptr;
+                const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
                 float2 ms = make_float2(0.f, 1.f);
                 const bool ln = a.ln_stats != nullptr && valid;
-                if (ln) ms = a.ln_stats[cur.grow];
+                if (ln) ms = a.ln_stats[grow];
                 const bool has_b = a.bias != nullptr;
-                const int col0 = cur.col0;
                 int j = 0;
 #pragma unroll 1
-                for (int blk = hh; blk < cur.nvalid; blk += 2, ++j) {
+                for (int blk = hh; blk < nvalid; blk += 2, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
                     float x[32];
                     uint32_t v[32];
@@ -704,7 +666,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             x[2 * i] += f.x;
                             x[2 * i + 1] += f.y;
                         }
-                        if (blk + 2 < cur.nvalid) {             // request this tile's next block now
+                        if (blk + 2 < nvalid) {                 // request the next block's residual now
                             ldg256(resrow + (blk + 2) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
                             ldg256(resrow + (blk + 2) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                         }
@@ -713,7 +675,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
-                        __half* dst = a.D + cur.grow * a.ldd + col0 + c;
+                        __half* dst = a.D + grow * a.ldd + col0 + c;
                         stg256(dst, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
                         stg256(dst + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
                     }
@@ -725,18 +687,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 if (rank == 0) mbar_arrive(&tmem_empty_bar[buf]);
                 else mbar_arrive_remote(&tmem_empty_bar[buf], 0);
             }
-            // hand the prefetched state over to the next iteration
-            if (has_next) {
-                if (has_vec) {
-                    float* sn = scratch + ((acc_it + 1) & 1) * 256;
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) { sn[lane + 32 * k] = nb[k]; sn[128 + lane + 32 * k] = nc[k]; }
-                }
-#pragma unroll
-                for (int i = 0; i < 16; ++i) rcur[i] = rnext[i];
-                __syncwarp();
-            }
-            cur = nxt;
         }
     }
 
@@ -1080,7 +1030,7 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                              ? 1 : 0;
         }
         if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);   // 8 x 26 KB
+        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
         else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
