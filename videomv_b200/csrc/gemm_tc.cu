@@ -490,6 +490,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    if (a.dbg & 4) {                       // experiment: no operand traffic, barrier protocol only
+                        if (rank == 0) mbar_arrive(&full_bar[s]);
+                        else mbar_arrive_remote(&full_bar[s], 0);
+                        continue;
+                    }
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
                     else mbar_arrive_remote(&full_bar[s], 0);
                     void* sa = smem + L::A_OFF + s * A_STAGE_BYTES;
@@ -531,9 +536,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
                     const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + L::B_OFF + s * L::B_STAGE_BYTES));
+                    if (!(a.dbg & 8)) {
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_f16_ss_2sm(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_f16_ss_2sm(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
+                    }
                     umma_commit_2sm(&empty_bar[s]);
                 }
                 umma_commit_2sm(&tmem_full_bar[buf]);
