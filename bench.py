@@ -102,6 +102,8 @@ def pick_cpu_threads(run_once) -> int:
         dt = time.time() - t0
         if best_t is None or dt < best_t:
             best_n, best_t = n, dt
+        elif dt > 1.5 * best_t:
+            break                                   # getting worse with more threads: stop probing
     torch.set_num_threads(best_n)
     return best_n
 

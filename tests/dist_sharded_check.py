@@ -1,7 +1,11 @@
 """torchrun worker: frame-sharded forward (P ranks, NCCL) must equal the single-GPU forward.
 Launched by tests/test_sharded_gpu.py (needs >= 2 GPUs)."""
+import datetime
 import os
 import sys
+
+os.environ.setdefault("TORCH_NCCL_BLOCKING_WAIT", "1")       # a stuck collective raises after the timeout instead of hanging
+os.environ.setdefault("NCCL_DEBUG", "WARN")
 
 import torch
 import torch.distributed as dist
@@ -14,7 +18,28 @@ from tests.test_unet_gpu import build  # noqa: E402
 def main():
     rank, local = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local), timeout=datetime.timedelta(seconds=90))
+
+    def say(msg):
+        print(f"[sharded] rank {rank}: {msg}", flush=True)
+
+    # which NCCL primitives work on this box (diagnostic; the engine uses all_gather + all_reduce by default)
+    z = torch.ones(1024, device="cuda") * (rank + 1)
+    dist.all_reduce(z)
+    torch.cuda.synchronize()
+    say(f"all_reduce ok ({z[0].item()})")
+    g = torch.empty(dist.get_world_size() * 1024, device="cuda")
+    dist.all_gather_into_tensor(g, z)
+    torch.cuda.synchronize()
+    say("all_gather_into_tensor ok")
+    if os.environ.get("VMV_TRY_A2A", "0") == "1":
+        try:
+            r = torch.empty_like(g)
+            dist.all_to_all_single(r, g)
+            torch.cuda.synchronize()
+            say("all_to_all_single ok")
+        except Exception as e:  # noqa: BLE001
+            say(f"all_to_all_single FAILED: {e!r}")
     meta, d, _ = load_case("t2v_small_t981_cam")                  # 24 frames, 8x8 latent -> 1x1 at the deepest level
     world = dist.get_world_size()
     # deepest level must have >= world pixels: use a 16x16 latent (-> 2x2) for 2..4 ranks
@@ -23,8 +48,11 @@ def main():
     model, _ = build(meta, meta["seed_w"])
     kw = dict(y=d["y"].cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
     ref = model(x, d["t"].cuda(), **kw)
+    torch.cuda.synchronize()
+    say("single-GPU reference forward done")
     model.set_frame_sharding()
     out = model(x, d["t"].cuda(), **kw)
+    torch.cuda.synchronize()
     rel = ((out - ref).norm() / ref.norm()).item()
     ncoll = model._engine().shard.collectives
     print(f"[sharded] rank {rank}/{world}: rel_l2 vs single-GPU {rel:.3e}, {ncoll} collectives per forward", flush=True)

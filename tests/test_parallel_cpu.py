@@ -16,8 +16,8 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, B, F, HW, C, ret):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+def _worker(rank, world, port, B, F, HW, C, ret, exchange="gather"):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), VMV_SHARD_EXCHANGE=exchange)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         from videomv_b200 import parallel
@@ -45,9 +45,10 @@ def _worker(rank, world, port, B, F, HW, C, ret):
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["gather", "a2a"])
 @pytest.mark.parametrize("B,F,HW,C", [(1, 24, 16, 8), (2, 4, 64, 16)])
-def test_layout_transposition_world2(B, F, HW, C):
+def test_layout_transposition_world2(B, F, HW, C, exchange):
     world = 2
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world, _free_port(), B, F, HW, C, ret), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, _free_port(), B, F, HW, C, ret, exchange), nprocs=world, join=True)
     assert all(ret.get(r) for r in range(world)), dict(ret)

@@ -15,6 +15,6 @@ def test_frame_sharded_equals_single_gpu():
     n = 2
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr", "127.0.0.1",
            "--master-port", "29541", os.path.join(ROOT, "tests", "dist_sharded_check.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=400, cwd=ROOT)
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0

@@ -19,10 +19,17 @@ one all-reduce of 2*32*B doubles between the statistics and apply kernels.  Coll
 """
 from __future__ import annotations
 
+import os
 from typing import Optional
 
 import torch
 import torch.distributed as dist
+
+# How layouts are exchanged.  "a2a": one all_to_all_single (minimal traffic, NCCL send/recv channels).  "gather": one
+# all_gather_into_tensor + local slicing (P x the traffic, but only the collective transports that all_reduce uses; the
+# payloads here are <= 31 MB so the exchange is latency- not bandwidth-bound either way).  Default "gather": on the
+# sandboxed 2-GPU box of round 1 the first NCCL send/recv never completed (profiles/r1_multi_gpu.md).
+EXCHANGE = os.environ.get("VMV_SHARD_EXCHANGE", "gather")
 
 
 class ShardCtx:
@@ -41,11 +48,23 @@ class ShardCtx:
             raise ValueError(f"frame sharding needs every level's H*W (min {hw_min}) divisible by {self.world}")
 
 
+def _gather(x: torch.Tensor, ctx: ShardCtx) -> torch.Tensor:
+    x = x.contiguous()
+    flat = torch.empty((ctx.world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+    dist.all_gather_into_tensor(flat, x, group=ctx.group)      # concatenation along dim 0 (accepted by NCCL and gloo)
+    ctx.collectives += 1
+    return flat.view((ctx.world,) + tuple(x.shape))
+
+
 def frames_to_pixels(x: torch.Tensor, B: int, Fl: int, HW: int, ctx: ShardCtx) -> torch.Tensor:
     """layout A [B*Fl*HW, C] -> layout B [B*F*HWl, C]   (F = Fl*P, HWl = HW/P)."""
     P = ctx.world
     C = x.shape[1]
     HWl = HW // P
+    if EXCHANGE == "gather":
+        g = _gather(x.reshape(B, Fl, HW, C), ctx)                              # [P(src frames), B, Fl, HW, C]
+        mine = g[:, :, :, ctx.rank * HWl:(ctx.rank + 1) * HWl]                 # my pixel chunk of every frame
+        return mine.permute(1, 0, 2, 3, 4).reshape(B * P * Fl * HWl, C)
     # [B, Fl, P, HWl, C] -> [P(dest), B, Fl, HWl, C]
     send = x.reshape(B, Fl, P, HWl, C).permute(2, 0, 1, 3, 4).contiguous()
     recv = torch.empty_like(send)
@@ -60,6 +79,10 @@ def pixels_to_frames(x: torch.Tensor, B: int, Fl: int, HW: int, ctx: ShardCtx) -
     P = ctx.world
     C = x.shape[1]
     HWl = HW // P
+    if EXCHANGE == "gather":
+        g = _gather(x.reshape(B, P * Fl, HWl, C), ctx)                         # [P(src pixels), B, F, HWl, C]
+        mine = g[:, :, ctx.rank * Fl:(ctx.rank + 1) * Fl]                      # my frames of every pixel chunk
+        return mine.permute(1, 2, 0, 3, 4).reshape(B * Fl * P * HWl, C)
     # [B, P(dest frames), Fl, HWl, C] -> [P(dest), B, Fl, HWl, C]
     send = x.reshape(B, P, Fl, HWl, C).permute(1, 0, 2, 3, 4).contiguous()
     recv = torch.empty_like(send)
@@ -77,7 +100,5 @@ def allreduce_stats(stats: torch.Tensor, ctx: ShardCtx) -> None:
 
 def gather_frames(out: torch.Tensor, ctx: ShardCtx) -> torch.Tensor:
     """[B, C, Fl, h, w] per rank -> [B, C, F, h, w] on every rank (final output only)."""
-    parts = [torch.empty_like(out) for _ in range(ctx.world)]
-    dist.all_gather(parts, out.contiguous(), group=ctx.group)
-    ctx.collectives += 1
-    return torch.cat(parts, dim=2)
+    g = _gather(out, ctx)                                                      # [P, B, C, Fl, h, w]
+    return g.permute(1, 2, 0, 3, 4, 5).reshape(out.shape[0], out.shape[1], -1, out.shape[3], out.shape[4]).contiguous()
