@@ -32,14 +32,6 @@ def main():
     dist.all_gather_into_tensor(g, z)
     torch.cuda.synchronize()
     say("all_gather_into_tensor ok")
-    if os.environ.get("VMV_TRY_A2A", "0") == "1":
-        try:
-            r = torch.empty_like(g)
-            dist.all_to_all_single(r, g)
-            torch.cuda.synchronize()
-            say("all_to_all_single ok")
-        except Exception as e:  # noqa: BLE001
-            say(f"all_to_all_single FAILED: {e!r}")
     meta, d, _ = load_case("t2v_small_t981_cam")                  # 24 frames, 8x8 latent -> 1x1 at the deepest level
     world = dist.get_world_size()
     # deepest level must have >= world pixels: use a 16x16 latent (-> 2x2) for 2..4 ranks
@@ -70,6 +62,16 @@ def main():
         ok *= 0
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.barrier()
+    if os.environ.get("VMV_TRY_A2A", "0") == "1":      # diagnostic, last: a timeout here may poison the communicator
+        try:
+            snd = torch.ones(2 * 1024, device="cuda")
+            rcv = torch.empty_like(snd)
+            dist.all_to_all_single(rcv, snd)
+            torch.cuda.synchronize()
+            say("all_to_all_single ok")
+        except Exception as e:  # noqa: BLE001
+            say(f"all_to_all_single FAILED: {e!r}")
+            os._exit(0 if int(ok.item()) == 1 else 1)
     dist.destroy_process_group()
     sys.exit(0 if int(ok.item()) == 1 else 1)
 
