@@ -294,6 +294,8 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         # ---- roofline leg: one instrumented (eager, per-launch CUDA events) CFG-batched forward
         pk = _peaks()
         model.enable_cuda_graphs(False)
+        if sharded:
+            model.set_frame_sharding(enable=False)   # the instrumented forward below runs on rank 0 alone
         xt = dev_noise
         t = torch.full((1,), 981, dtype=torch.long, device=dev)
         for _ in range(2):
@@ -337,6 +339,11 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
+        model._engine()._graphs.clear()              # graphs that captured NCCL kernels go before the communicator
+        torch.cuda.synchronize()
+        if sharded:
+            sys.stdout.flush()
+            os._exit(0)                              # NCCL teardown after captured collectives hung on the sandboxed box
         dist.destroy_process_group()
 
 

@@ -62,6 +62,11 @@ def main():
         ok *= 0
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.barrier()
+    code = 0 if int(ok.item()) == 1 else 1
+    # CUDA graphs that captured NCCL kernels must die before the communicator does
+    model.enable_cuda_graphs(False)
+    model._engine()._graphs.clear()
+    torch.cuda.synchronize()
     if os.environ.get("VMV_TRY_A2A", "0") == "1":      # diagnostic, last: a timeout here may poison the communicator
         try:
             snd = torch.ones(2 * 1024, device="cuda")
@@ -71,7 +76,8 @@ def main():
             say("all_to_all_single ok")
         except Exception as e:  # noqa: BLE001
             say(f"all_to_all_single FAILED: {e!r}")
-            os._exit(0 if int(ok.item()) == 1 else 1)
+    sys.stdout.flush()
+    os._exit(code)          # skip NCCL teardown: destroy_process_group hung here on the sandboxed box
     dist.destroy_process_group()
     sys.exit(0 if int(ok.item()) == 1 else 1)
 
