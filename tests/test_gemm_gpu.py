@@ -25,6 +25,7 @@ def _r(*shape, scale=1.0, seed=0):
     (300, 64, 128, 64, 0), (512, 256, 2560, 256, 0), (6144, 640, 640, 128, 6),
     (49152, 320, 320, 0, 0), (49152, 2560, 320, 0, 0), (385, 480, 1280, 0, 0), (129, 160, 4096, 0, 0),
     (777, 48, 192, 0, 0), (2048, 80, 64, 0, 0), (1536, 1280, 640, 128, 0),
+    (12288, 640, 640, 0, 0), (12288, 1920, 640, 0, 0), (49152, 960, 320, 0, 0), (3072, 3840, 1280, 0, 0), (600, 672, 128, 0, 0),
 ])
 def test_linear(M, N, K, bn, stages, variant):
     from videomv_b200 import ops

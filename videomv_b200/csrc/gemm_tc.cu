@@ -470,7 +470,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const int rem = t - split * tiles_mn;
                 const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
                 const int mt = 2 * mp + (int)rank;
-                const int nrow = nt * BN + (int)rank * (BN / 2);
+                // the pair splits the tile's W rows; a ragged last tile (N % BN != 0) is nt_cols wide and each CTA
+                // contributes nt_cols/2 rows (its box still loads BN/2 rows; the surplus is never read by the MMA)
+                const int nt_cols = min(BN, a.N - nt * BN);
+                const int nrow = nt * BN + (int)rank * (nt_cols / 2);
                 int c1 = 0, c2 = 0, c3 = 0;
                 if (a.mode == VMV_GEMM_LINEAR) {
                     c1 = mt * BM;
@@ -518,10 +521,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     } else if (warp == 1) {
         if (lane == 0 && rank == 0) {
             // ------------------------------ MMA issuer (leader CTA only) ------------------------------
-            constexpr uint32_t idesc = umma_idesc_f16_f32(2 * BM, BN);
             int it = 0, acc_it = 0;
             for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
                 const int split = t / tiles_mn;
+                const int nt_mma = (t - split * tiles_mn) % n_tiles;
+                const uint32_t idesc = umma_idesc_f16_f32(2 * BM, min(BN, a.N - nt_mma * BN));   // ragged last N tile
                 const int kb_begin = split * a.kb_per_split;
                 const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
                 const int buf = acc_it & 1;
@@ -846,8 +850,12 @@ static int pick_block_n(const vmv_gemm_params* p, int variant) {
     const int N = p->N;
     if (variant == 2) {
         if (p->act == VMV_ACT_GEGLU) return (N % 256 == 0) ? 256 : 128;   // BN/2 must be a multiple of 32
+        // tcgen05.mma in SS mode is operand-bandwidth bound: wider N amortises the A reads (measured 759 / 874 / 1254
+        // TFLOP/s MMA-only for N = 128 / 160 / 256, profiles/r1_mainloop_isolation.log), and fewer N tiles re-read A
+        // less often.  256-wide tiles with a ragged last tile for everything wider than 320 columns.
+        if (N > 320) return 256;
         if (N % 160 == 0) return 160;
-        return 128;                        // 256-wide tiles are reserved for GEGLU (their output is 128 wide)
+        return 128;
     }
     if (p->act == VMV_ACT_GEGLU) return (N % 160 == 0) ? 160 : 128;
     if (N % 160 == 0) return 160;
@@ -953,6 +961,7 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
         VMV_CHECK_ARG(p->N % pl->bn == 0 && (pl->bn / 2) % (pl->variant == 2 ? 32 : 16) == 0,
                       "vmv_gemm: GEGLU needs N %% block_n == 0 and block_n in {128, 256} for the CTA-pair kernel");
     pl->n_tiles = (p->N + pl->bn - 1) / pl->bn;
+    // (a ragged last tile of the CTA-pair kernel is (N % bn) wide: a multiple of 16, so each CTA's half is 8-row aligned)
     pl->splits = p->split_k > 1 ? p->split_k : 1;
     if (pl->splits > a.nkb) pl->splits = a.nkb;
     if (p->act == VMV_ACT_GEGLU) pl->splits = 1;

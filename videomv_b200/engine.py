@@ -171,7 +171,7 @@ class UNetEngine:
     def _gemm(self, a, w: _W, **kw):
         M = a.shape[0]
         N = w.w.shape[0]
-        bn = w.bn or (160 if N % 160 == 0 else 128)
+        bn = w.bn or (256 if N > 320 else (160 if N % 160 == 0 else 128))      # mirrors pick_block_n in gemm_tc.cu
         # The persistent kernel runs one CTA pair per 2 SMs (74 pairs) on 256 x bn tiles.  When the tile count is a
         # poor fit for 74 (few tiles at the 8x8 / 4x4 levels) split K so the last wave is not mostly idle.
         tiles = ((M + 255) // 256) * ((N + bn - 1) // bn)
