@@ -313,12 +313,20 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
             f = fam.setdefault(name, [0, 0.0, 0.0, 0.0])
             f[0] += 1; f[1] += fl; f[2] += by; f[3] += a.elapsed_time(b)
         g = fam.get("gemm_tc", [0, 0.0, 0.0, 1e-9])
-        achieved = g[1] / (g[3] * 1e-3) / 1e12
-        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc_kernel<BN,STAGES> (tcgen05 GEMM / implicit conv family)",
+        # device time of every GEMM launch of that forward: each distinct shape replayed from a CUDA graph (the eager
+        # event pairs above include host launch gaps, which exceed the kernel for the many small launches)
+        from videomv_b200.profiling import gemm_shape_times
+        rows = gemm_shape_times(prof)
+        dev_ms = sum(n * us for _, n, _, us in rows) / 1e3
+        achieved = g[1] / (dev_ms * 1e-3) / 1e12
+        line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,STAGES,.> (tcgen05 CTA-pair GEMM / implicit conv family)",
                             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
                             "traffic": None, "peak_source": pk["src"] + " bf16_tflops_sustained",
-                            "launches_per_forward": g[0], "algorithmic_tflop_per_forward_b2": g[1] / 1e12,
-                            "kernel_ms_per_forward_b2": g[3]}
+                            "launches_per_forward": g[0], "distinct_shapes": len(rows),
+                            "algorithmic_tflop_per_forward_b2": g[1] / 1e12, "kernel_ms_per_forward_b2": dev_ms,
+                            "how": "algorithmic FLOPs of the 422 launches of one CFG-batched forward / their device time "
+                                   "(CUDA events around graph replays of each distinct shape, L2-warm)",
+                            "eager_event_ms_per_forward_b2": g[3]}
         line["breakdown_ms_per_forward_b2"] = {k: round(v[3], 3) for k, v in fam.items()}
         line["breakdown_ms_per_forward_b2"]["eager_wall_total"] = round(ev0.elapsed_time(ev1), 3)
         hb = {k: v for k, v in fam.items() if k in ("groupnorm", "layernorm")}

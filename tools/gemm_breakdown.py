@@ -34,33 +34,11 @@ def main():
     for name, fl, by, a, b, desc, replay in prof:
         ms = a.elapsed_time(b)
         f = fam.setdefault(name, [0, 0.0, 0.0]); f[0] += 1; f[1] += fl; f[2] += ms
-        if name == "gemm_tc":
-            g = shapes.setdefault(desc, [0, fl, replay]); g[0] += 1
     print("family totals, eager event-to-event (ms; small kernels are CPU-launch bound here):",
           {k: (v[0], round(v[2], 3)) for k, v in fam.items()})
     # true device time per shape: 8 back-to-back launches captured in a CUDA graph, replayed 3x, L2-warm
-    rows = []
-    for desc, (n, fl, replay) in shapes.items():
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            replay()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for _ in range(8):
-                replay()
-        g.replay()
-        torch.cuda.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(3):
-            g.replay()
-        e1.record()
-        torch.cuda.synchronize()
-        us = e0.elapsed_time(e1) * 1e3 / 24
-        rows.append((desc, n, fl, us))
+    from videomv_b200.profiling import gemm_shape_times
+    rows = gemm_shape_times(prof)
     tot = sum(n * us for _, n, _, us in rows)
     print("| shape | n | us each | total ms | share | TFLOP/s |\n|---|---:|---:|---:|---:|---:|")
     for desc, n, fl, us in sorted(rows, key=lambda r: -r[1] * r[3]):
