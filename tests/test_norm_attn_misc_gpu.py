@@ -52,7 +52,8 @@ def _attn_ref(q, k, v, scale):
     return torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, -1), v.float())
 
 
-@pytest.mark.parametrize("NF,HW,heads", [(24, 1024, 5), (24, 256, 10), (24, 64, 20), (24, 16, 20), (2, 4096, 5), (3, 100, 2)])
+@pytest.mark.parametrize("NF,HW,heads", [(24, 1024, 5), (24, 256, 10), (24, 64, 20), (24, 16, 20), (2, 4096, 5), (3, 100, 2),
+                                         (3, 300, 2), (5, 128, 1), (2, 1000, 3)])
 def test_attention_spatial_fused_qkv(NF, HW, heads):
     from videomv_b200 import ops
     C = heads * 64
@@ -67,7 +68,8 @@ def test_attention_spatial_fused_qkv(NF, HW, heads):
     assert_close(f"attn spatial NF{NF} HW{HW} h{heads}", out, ref, rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("B,Fr,HW,heads,L", [(1, 24, 1024, 5, 77), (2, 24, 64, 20, 77), (1, 4, 256, 10, 145)])
+@pytest.mark.parametrize("B,Fr,HW,heads,L", [(1, 24, 1024, 5, 77), (2, 24, 64, 20, 77), (1, 4, 256, 10, 145), (2, 3, 256, 10, 77),
+                                              (2, 2, 4096, 5, 145)])
 def test_attention_cross(B, Fr, HW, heads, L):
     from videomv_b200 import ops
     C = heads * 64

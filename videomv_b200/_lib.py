@@ -15,7 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 LIBPATH = os.path.join(LIBDIR, "libvideomv_b200.so")
-SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "misc.cu"]
+SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

@@ -14,6 +14,8 @@
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
+#include <stdlib.h>
+
 namespace vmv {
 
 void count_launch(int n = 1);
@@ -214,6 +216,8 @@ attention_kernel(const vmv_attn_params p) {
     }
 }
 
+int attention_tc_try(const vmv_attn_params* p, cudaStream_t st);   // attention_tc.cu
+
 }  // namespace vmv
 
 using namespace vmv;
@@ -228,6 +232,15 @@ extern "C" int vmv_attention(const vmv_attn_params* p, void* stream) {
     const long long nb = (long long)p->outer * p->inner;
     VMV_CHECK_ARG(nb <= 65535 * 1LL && p->heads <= 65535, "vmv_attention: batch %lld too large for one launch", nb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    {
+        // long contiguous sequences (spatial self-attention, text cross-attention) -> tcgen05 kernel
+        static int use_tc = -1;
+        if (use_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
+        if (use_tc) {
+            const int rc = attention_tc_try(p, st);
+            if (rc != VMV_ERR_UNSUPPORTED) return rc;
+        }
+    }
     if (p->nq <= 32 && p->nk <= 32) {
         dim3 grid((p->nq + 31) / 32, p->heads, (unsigned)nb);
         attention_kernel<2, 32><<<grid, 64, 0, st>>>(*p);

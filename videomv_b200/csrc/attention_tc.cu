@@ -1,0 +1,283 @@
+// tcgen05 flash attention for the long-sequence cases (spatial self-attention 256..4096 tokens, text cross-attention):
+//   O = softmax(Q K^T * scale) V,  head_dim 64, fp16 in/out, fp32 softmax, batches contiguous in memory.
+//
+// One CTA = 128 query rows of one (batch, head); K/V streamed in 128-key chunks through a 2-stage TMA ring.
+//   warp 0      TMA producer (Q once, then K/V chunks; 128B-swizzled boxes straight out of the fused QKV GEMM output)
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
+//                 S_j = Q K_j^T      M128 x N128 x K64   (both operands K-major)            -> TMEM cols [0,128)
+//                 O_j = P_j V_j      M128 x N64  x K128  (P K-major from smem, V MN-major)  -> TMEM cols [128,192)
+//   warps 2..5  softmax, one query row per thread: row max / exp2 / row sum in registers (two TMEM passes over S so
+//               only 32 scores are live at a time), P written to smem in the UMMA K-major 128B-swizzle layout, running
+//               output kept in registers and corrected per chunk (O_j is read back from TMEM, never accumulated there)
+// Issue order S_{j+1} before P_j V_j lets the tensor core compute the next scores while the softmax warps work; two CTAs
+// fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
+#include "common.cuh"
+#include "../../include/videomv_b200.h"
+
+#include <mutex>
+
+namespace vmv {
+
+void count_launch(int n = 1);
+int make_map_generic(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes);
+
+constexpr int AT_BM = 128, AT_BN = 128, AT_D = 64;
+constexpr int AT_TILE = 128 * 64 * 2;                     // 16 KiB: one [128][64] fp16 tile
+constexpr int AT_OFF_Q = 0;
+constexpr int AT_OFF_K = AT_TILE;                         // 2 stages
+constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_TILE;          // 2 stages
+constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_TILE;          // [128][128] fp16 = two K atoms of 64 keys
+constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_TILE;
+constexpr int AT_SMEM = AT_OFF_BAR + 10 * 8 + 16;      // 2 CTAs/SM: 2 x (112.1 KB + 1 KB reserved) < 228 KB
+constexpr int AT_TMEM_COLS = 256;                         // S: [0,128)  O: [128,192)
+
+struct AttTcArgs {
+    int nq, nk, kv_group;
+    float scale_log2;                                     // scale * log2(e)
+    __half* o;
+    long long o_bs, o_rs;                                 // elements
+};
+
+// MN-major (N contiguous) 128B-swizzled B operand: V chunk [128 keys][64 d].  One 64-wide MN atom; 8-key groups 1024 B
+// apart (SBO); a K step of 16 keys advances the start address by 2048 B.  (cute::UMMA::SmemDescriptor, DeepGEMM
+// make_umma_desc<Major::MN>: SBO = 8 * 64 * 2, LBO = BLOCK_K * 64 * 2.)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, uint32_t block_k) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((block_k * 128u) >> 4) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
+__global__ void __launch_bounds__(192, 2)
+attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                    const __grid_constant__ CUtensorMap tmV, const AttTcArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];     // 128B-swizzled tiles need 1024 B alignment (checked below)
+    if ((smem_u32(smem) & 1023u) != 0) __trap();
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
+    uint64_t* q_full = bars;            // [1]
+    uint64_t* kv_full = bars + 1;       // [2]
+    uint64_t* kv_empty = bars + 3;      // [2]
+    uint64_t* s_full = bars + 5;        // [1]  scores of chunk j are in TMEM
+    uint64_t* p_full = bars + 6;        // [1]  P_j is in smem, S is free (4 warp arrivals)
+    uint64_t* o_full = bars + 7;        // [1]  P_j V_j is in TMEM, the P buffer is free
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int qt = blockIdx.x, h = blockIdx.y, bo = blockIdx.z;
+    const int kbo = bo / a.kv_group;
+    const int q0 = qt * AT_BM;
+    const int nchunks = (a.nk + AT_BN - 1) / AT_BN;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmQ);
+        tma_prefetch_desc(&tmK);
+        tma_prefetch_desc(&tmV);
+        mbar_init(q_full, 1);
+        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(s_full, 1);
+        mbar_init(p_full, 4);
+        mbar_init(o_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_ptr_smem);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_arrive_expect_tx(q_full, AT_TILE);
+            tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + q0);
+            for (int j = 0; j < nchunks; ++j) {
+                const int st = j & 1;
+                const uint32_t ph = (j >> 1) & 1;
+                mbar_wait(&kv_empty[st], ph ^ 1);
+                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
+                tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc_s = umma_idesc_f16_f32(AT_BM, AT_BN);                  // K-major A and B
+            constexpr uint32_t idesc_o = umma_idesc_f16_f32(AT_BM, AT_D) | (1u << 16);     // B (= V) is MN-major
+            const uint64_t qdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_Q));
+            const uint64_t pdesc0 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P));
+            const uint64_t pdesc1 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P + AT_TILE));
+            auto issue_s = [&](int j) {
+                const int st = j & 1;
+                mbar_wait(&kv_full[st], (j >> 1) & 1);
+                tc_fence_after();
+                const uint64_t kdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_K + st * AT_TILE));
+#pragma unroll
+                for (int k = 0; k < AT_D / 16; ++k) umma_f16_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(s_full);
+            };
+            mbar_wait(q_full, 0);
+            issue_s(0);
+            for (int j = 0; j < nchunks; ++j) {
+                const int st = j & 1;
+                mbar_wait(p_full, j & 1);                     // P_j in smem; the softmax warps are done with S_j
+                tc_fence_after();
+                if (j + 1 < nchunks) issue_s(j + 1);          // next scores first: they overlap softmax_{j+1} with P_j V_j
+                const uint64_t vdesc = umma_desc_sw128_mnmajor(smem_u32(smem + AT_OFF_V + st * AT_TILE), AT_BN);
+#pragma unroll
+                for (int k = 0; k < AT_BN / 16; ++k) {
+                    const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+                    umma_f16_ss(tmem_base + AT_BN, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : 0u);
+                }
+                umma_commit(o_full);
+                umma_commit(&kv_empty[st]);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ------------------------------- softmax / output: one query row per thread -------------------------------
+        const int q = warp & 3;
+        const int r = q * 32 + lane;
+        const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+        const int swz = r & 7;
+        uint8_t* prow = smem + AT_OFF_P + r * 128;
+        float m_run = -INFINITY, l_run = 0.f;
+        float o[AT_D];
+#pragma unroll
+        for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+        const float sl2 = a.scale_log2;
+
+        auto add_o = [&]() {                                  // o += O_j from TMEM
+#pragma unroll
+            for (int c = 0; c < AT_D; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(trow + AT_BN + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld_32x32b_x16(trow + AT_BN + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
+            }
+        };
+
+        for (int j = 0; j < nchunks; ++j) {
+            const int kbase = j * AT_BN;
+            mbar_wait(s_full, j & 1);
+            tc_fence_after();
+            // pass 1: row max of this chunk (keys beyond nk are masked)
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < AT_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (kbase + c + i < a.nk) mx = fmaxf(mx, __uint_as_float(v[i]));
+            }
+            const float m_new = fmaxf(m_run, mx);             // finite: chunk 0 always holds key 0
+            const float corr = exp2f((m_run - m_new) * sl2);
+            if (j > 0) {
+                mbar_wait(o_full, (j - 1) & 1);               // P_{j-1} V_{j-1} landed; the P buffer is free again
+                tc_fence_after();
+                add_o();
+            }
+#pragma unroll
+            for (int i = 0; i < AT_D; ++i) o[i] *= corr;
+            l_run *= corr;
+            m_run = m_new;
+            const float msc = m_new * sl2;
+            // pass 2: probabilities -> smem (K-major, 128B swizzle: 16B chunk index ^= row & 7 inside each 64-key atom)
+#pragma unroll
+            for (int c = 0; c < AT_BN; c += 32) {
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
+                float p[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    p[i] = (kbase + c + i < a.nk) ? exp2f(__uint_as_float(v[i]) * sl2 - msc) : 0.f;
+                    l_run += p[i];
+                }
+                uint8_t* atom = prow + (c >> 6) * AT_TILE;    // 64 keys per atom
+                const int chunk0 = (c & 63) >> 3;             // first 16B chunk of this batch inside the atom row
+#pragma unroll
+                for (int h4 = 0; h4 < 4; ++h4)
+                    *reinterpret_cast<uint4*>(atom + (((chunk0 + h4) ^ swz) << 4)) =
+                        make_uint4(pack_half2(p[8 * h4], p[8 * h4 + 1]), pack_half2(p[8 * h4 + 2], p[8 * h4 + 3]),
+                                   pack_half2(p[8 * h4 + 4], p[8 * h4 + 5]), pack_half2(p[8 * h4 + 6], p[8 * h4 + 7]));
+            }
+            fence_proxy_async();                              // generic-proxy smem writes -> visible to the MMA
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_full);
+        }
+        mbar_wait(o_full, (nchunks - 1) & 1);
+        tc_fence_after();
+        add_o();
+        const int qrow = q0 + r;
+        if (qrow < a.nq) {
+            const float inv = 1.f / l_run;
+            __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D;
+#pragma unroll
+            for (int c = 0; c < AT_D; c += 16) {
+                uint32_t w[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) w[i] = pack_half2(o[c + 2 * i] * inv, o[c + 2 * i + 1] * inv);
+                stg256(dst + c, w);
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<AT_TMEM_COLS>(tmem_base);
+}
+
+static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31) == 0; }
+
+// Returns VMV_OK if launched, VMV_ERR_UNSUPPORTED if the problem does not fit this kernel (caller falls back to the
+// generic strided kernel), another code on error.
+int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
+    if (p->inner != 1 || p->nq < 128) return VMV_ERR_UNSUPPORTED;
+    if (p->q_bs_outer != (int64_t)p->nq * p->q_rs || p->k_bs_outer != (int64_t)p->nk * p->k_rs ||
+        p->v_bs_outer != (int64_t)p->nk * p->v_rs)
+        return VMV_ERR_UNSUPPORTED;                               // batches must be contiguous row blocks
+    if (p->outer % p->kv_group != 0) return VMV_ERR_UNSUPPORTED;
+    if (!aligned32(p->o) || p->o_rs % 16 != 0 || p->o_bs_outer % 16 != 0) return VMV_ERR_UNSUPPORTED;
+    if ((reinterpret_cast<uintptr_t>(p->q) | reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v)) & 15)
+        return VMV_ERR_UNSUPPORTED;
+    CUtensorMap tq, tk, tv;
+    const unsigned box[2] = {AT_D, 128};
+    auto mk = [&](CUtensorMap* m, const void* base, long long rows, long long rs) {
+        const unsigned long long dims[2] = {(unsigned long long)p->heads * AT_D, (unsigned long long)rows};
+        const unsigned long long strides[1] = {(unsigned long long)rs * 2};
+        return make_map_generic(m, base, 2, dims, strides, box, 128);
+    };
+    int rc;
+    if ((rc = mk(&tq, p->q, (long long)p->outer * p->nq, p->q_rs)) != VMV_OK) return rc;
+    if ((rc = mk(&tk, p->k, (long long)(p->outer / p->kv_group) * p->nk, p->k_rs)) != VMV_OK) return rc;
+    if ((rc = mk(&tv, p->v, (long long)(p->outer / p->kv_group) * p->nk, p->v_rs)) != VMV_OK) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
+        if (e != cudaSuccess) { set_error("attention_tc: smem attribute: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+        attr_set = true;
+    }
+    AttTcArgs a;
+    a.nq = p->nq; a.nk = p->nk; a.kv_group = p->kv_group;
+    a.scale_log2 = p->scale * 1.4426950408889634f;
+    a.o = static_cast<__half*>(p->o);
+    a.o_bs = p->o_bs_outer; a.o_rs = p->o_rs;
+    dim3 grid((p->nq + AT_BM - 1) / AT_BM, p->heads, p->outer);
+    attention_tc_kernel<<<grid, 192, AT_SMEM, st>>>(tq, tk, tv, a);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_attention (tcgen05)");
+    return VMV_OK;
+}
+
+}  // namespace vmv

@@ -795,6 +795,16 @@ static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t
     return VMV_OK;
 }
 
+// exported to the other translation units (attention_tc.cu): fp16 tiled tensor map, inner box = 64 elements
+int make_map_generic(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+                     const unsigned long long* strides_bytes, const unsigned* box, int swizzle_bytes) {
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+    return make_map(m, base, rank, d, st, b, swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
+}
+
 template <int BN, int STAGES>
 static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
                            dim3 grid, cudaStream_t st) {
