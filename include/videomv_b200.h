@@ -126,6 +126,9 @@ typedef struct vmv_attn_params {
     int64_t o_bs_outer, o_bs_inner, o_rs;
     int32_t kv_group;          /* kv outer index = bo / kv_group */
     float scale;               /* head_dim^-0.5 */
+    int32_t impl;              /* 0 auto | 1 strided mma.sync kernel (any layout) | 2 tcgen05/TMEM kernel (contiguous
+                                  batches, nq >= 128; VMV_ERR_UNSUPPORTED otherwise).  Auto currently picks 1: the
+                                  tcgen05 kernel is validated but not yet faster. */
 } vmv_attn_params;
 int vmv_attention(const vmv_attn_params* p, void* stream);
 

@@ -54,15 +54,18 @@ def _attn_ref(q, k, v, scale):
 
 @pytest.mark.parametrize("NF,HW,heads", [(24, 1024, 5), (24, 256, 10), (24, 64, 20), (24, 16, 20), (2, 4096, 5), (3, 100, 2),
                                          (3, 300, 2), (5, 128, 1), (2, 1000, 3)])
-def test_attention_spatial_fused_qkv(NF, HW, heads):
+@pytest.mark.parametrize("impl", [1, 2], ids=["mma.sync", "tcgen05"])
+def test_attention_spatial_fused_qkv(NF, HW, heads, impl):
     from videomv_b200 import ops
+    if impl == 2 and HW < 128:
+        pytest.skip("tcgen05 attention needs nq >= 128")
     C = heads * 64
     qkv = _r(NF * HW, 3 * C, seed=1)
     out = torch.empty(NF * HW, C, dtype=torch.float16, device="cuda")
     ld = 3 * C
     ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], out, outer=NF, inner=1, heads=heads, nq=HW, nk=HW,
                   q_strides=(HW * ld, 0, ld), k_strides=(HW * ld, 0, ld), v_strides=(HW * ld, 0, ld),
-                  o_strides=(HW * C, 0, C))
+                  o_strides=(HW * C, 0, C), impl=impl)
     t = qkv.reshape(NF, HW, 3, heads, 64).permute(2, 0, 3, 1, 4)
     ref = _attn_ref(t[0], t[1], t[2], 0.125).permute(0, 2, 1, 3).reshape(NF * HW, C)
     assert_close(f"attn spatial NF{NF} HW{HW} h{heads}", out, ref, rtol=2e-3, atol=2e-3)
@@ -70,15 +73,18 @@ def test_attention_spatial_fused_qkv(NF, HW, heads):
 
 @pytest.mark.parametrize("B,Fr,HW,heads,L", [(1, 24, 1024, 5, 77), (2, 24, 64, 20, 77), (1, 4, 256, 10, 145), (2, 3, 256, 10, 77),
                                               (2, 2, 4096, 5, 145)])
-def test_attention_cross(B, Fr, HW, heads, L):
+@pytest.mark.parametrize("impl", [1, 2], ids=["mma.sync", "tcgen05"])
+def test_attention_cross(B, Fr, HW, heads, L, impl):
     from videomv_b200 import ops
+    if impl == 2 and HW < 128:
+        pytest.skip("tcgen05 attention needs nq >= 128")
     C = heads * 64
     q = _r(B * Fr * HW, C, seed=1)
     kv = _r(B * L, 2 * C, seed=2)
     out = torch.empty_like(q)
     ops.attention(q, kv, kv[:, C:], out, outer=B * Fr, inner=1, heads=heads, nq=HW, nk=L,
                   q_strides=(HW * C, 0, C), k_strides=(L * 2 * C, 0, 2 * C), v_strides=(L * 2 * C, 0, 2 * C),
-                  o_strides=(HW * C, 0, C), kv_group=Fr)
+                  o_strides=(HW * C, 0, C), kv_group=Fr, impl=impl)
     qh = q.reshape(B * Fr, HW, heads, 64).permute(0, 2, 1, 3)
     kvh = kv.reshape(B, L, 2, heads, 64).permute(2, 0, 3, 1, 4).repeat_interleave(Fr, dim=1)
     ref = _attn_ref(qh, kvh[0], kvh[1], 0.125).permute(0, 2, 1, 3).reshape(B * Fr * HW, C)

@@ -89,7 +89,7 @@ class AttnParams(ctypes.Structure):
         ("k_bs_outer", c_i64), ("k_bs_inner", c_i64), ("k_rs", c_i64),
         ("v_bs_outer", c_i64), ("v_bs_inner", c_i64), ("v_rs", c_i64),
         ("o_bs_outer", c_i64), ("o_bs_inner", c_i64), ("o_rs", c_i64),
-        ("kv_group", c_i32), ("scale", c_f32),
+        ("kv_group", c_i32), ("scale", c_f32), ("impl", c_i32),
     ]
 
 
@@ -135,7 +135,7 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if L.vmv_abi_version() != 1:
+    if L.vmv_abi_version() != 2:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
     if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
             L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams)):

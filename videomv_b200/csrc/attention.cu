@@ -233,12 +233,18 @@ extern "C" int vmv_attention(const vmv_attn_params* p, void* stream) {
     VMV_CHECK_ARG(nb <= 65535 * 1LL && p->heads <= 65535, "vmv_attention: batch %lld too large for one launch", nb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
-        // long contiguous sequences (spatial self-attention, text cross-attention) -> tcgen05 kernel
-        static int use_tc = -1;
-        if (use_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); use_tc = (e && e[0] == '0') ? 0 : 1; }
-        if (use_tc) {
+        // tcgen05 kernel for long contiguous sequences (spatial self-attention, text cross-attention): explicit
+        // (impl == 2) or, when VMV_ATTN_TC=1, whenever the layout allows.
+        static int auto_tc = -1;
+        if (auto_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); auto_tc = (e && e[0] == '1') ? 1 : 0; }
+        if (p->impl == 2 || (p->impl == 0 && auto_tc)) {
             const int rc = attention_tc_try(p, st);
             if (rc != VMV_ERR_UNSUPPORTED) return rc;
+            if (p->impl == 2) {
+                set_error("vmv_attention: impl=2 (tcgen05) needs contiguous batches (inner == 1, batch stride == n * row "
+                          "stride), nq >= 128 and 32 B aligned output rows");
+                return VMV_ERR_UNSUPPORTED;
+            }
         }
     }
     if (p->nq <= 32 && p->nk <= 32) {

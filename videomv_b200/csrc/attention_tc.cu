@@ -6,11 +6,14 @@
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
 //                 S_j = Q K_j^T      M128 x N128 x K64   (both operands K-major)            -> TMEM cols [0,128)
 //                 O_j = P_j V_j      M128 x N64  x K128  (P K-major from smem, V MN-major)  -> TMEM cols [128,192)
-//   warps 2..5  softmax, one query row per thread: row max / exp2 / row sum in registers (two TMEM passes over S so
-//               only 32 scores are live at a time), P written to smem in the UMMA K-major 128B-swizzle layout, running
-//               output kept in registers and corrected per chunk (O_j is read back from TMEM, never accumulated there)
-// Issue order S_{j+1} before P_j V_j lets the tensor core compute the next scores while the softmax warps work; two CTAs
-// fit per SM (112 KB smem, 256 TMEM columns each) so one CTA's exponentials overlap the other's MMAs.
+//   warps 2..9  softmax: two warps per TMEM lane quarter; a query row is shared by one thread of each, which takes 64 of
+//               the chunk's 128 keys (single TMEM pass, scores stay in registers) and 32 of the 64 output columns.  The
+//               pair exchanges its partial row max through smem (named barrier per quarter); P is written to smem in the
+//               UMMA K-major 128B-swizzle layout (one 64-key atom per warp); the running output lives in registers and is
+//               corrected per chunk (O_j is read back from TMEM, never accumulated there).
+// Issue order S_{j+1} before P_j V_j lets the tensor core compute the next scores while the softmax warps work.  The
+// kernel is exponent-bound (16 MUFU/clk/SM: 1024 cycles per 128x128 chunk vs 512 cycles of MMA), hence two warps per
+// scheduler on the softmax side to hide the TMEM / barrier latencies.
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
@@ -28,8 +31,10 @@ constexpr int AT_OFF_Q = 0;
 constexpr int AT_OFF_K = AT_TILE;                         // 2 stages
 constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_TILE;          // 2 stages
 constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_TILE;          // [128][128] fp16 = two K atoms of 64 keys
-constexpr int AT_OFF_BAR = AT_OFF_P + 2 * AT_TILE;
-constexpr int AT_SMEM = AT_OFF_BAR + 10 * 8 + 16;      // 2 CTAs/SM: 2 x (112.1 KB + 1 KB reserved) < 228 KB
+constexpr int AT_OFF_X = AT_OFF_P + 2 * AT_TILE;          // float [2 parity][2 halves][128 rows] max exchange + [2][128] sums
+constexpr int AT_OFF_BAR = AT_OFF_X + 6 * 128 * 4;
+constexpr int AT_SMEM = AT_OFF_BAR + 10 * 8 + 16;
+constexpr int AT_THREADS = 320;
 constexpr int AT_TMEM_COLS = 256;                         // S: [0,128)  O: [128,192)
 
 struct AttTcArgs {
@@ -52,7 +57,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_mnmajor(uint32_t smem_addr, 
     return d;
 }
 
-__global__ void __launch_bounds__(192, 2)
+__global__ void __launch_bounds__(AT_THREADS, 1)
 attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                     const __grid_constant__ CUtensorMap tmV, const AttTcArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];     // 128B-swizzled tiles need 1024 B alignment (checked below)
@@ -79,7 +84,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_init(q_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         mbar_init(s_full, 1);
-        mbar_init(p_full, 4);
+        mbar_init(p_full, 8);
         mbar_init(o_full, 1);
         fence_barrier_init();
     }
@@ -138,47 +143,46 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
         __syncwarp();
     } else {
-        // ------------------------------- softmax / output: one query row per thread -------------------------------
+        // ---------------- softmax / output: a query row = one thread of each of the two warps of its lane quarter ----------------
         const int q = warp & 3;
+        const int hh = (warp - 2) >> 2;                       // key half [64 hh, +64) and output columns [32 hh, +32)
         const int r = q * 32 + lane;
         const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
         const int swz = r & 7;
-        uint8_t* prow = smem + AT_OFF_P + r * 128;
+        uint8_t* prow = smem + AT_OFF_P + hh * AT_TILE + r * 128;      // my 64-key atom, my row
+        float* xmax = reinterpret_cast<float*>(smem + AT_OFF_X);       // [2][2][128]
+        float* xsum = xmax + 4 * 128;                                  // [2][128]
         float m_run = -INFINITY, l_run = 0.f;
-        float o[AT_D];
+        float o[32];
 #pragma unroll
-        for (int i = 0; i < AT_D; ++i) o[i] = 0.f;
+        for (int i = 0; i < 32; ++i) o[i] = 0.f;
         const float sl2 = a.scale_log2;
-
-        auto add_o = [&]() {                                  // o += O_j from TMEM
+        auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
+        auto add_o = [&]() {                                  // o += my 32 columns of O_j from TMEM
+            uint32_t v[32];
+            tmem_ld_32x32b_x16(trow + AT_BN + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld_32x32b_x16(trow + AT_BN + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < AT_D; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x16(trow + AT_BN + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld_32x32b_x16(trow + AT_BN + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i) o[c + i] += __uint_as_float(v[i]);
-            }
+            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
         };
 
         for (int j = 0; j < nchunks; ++j) {
-            const int kbase = j * AT_BN;
+            const int kbase = j * AT_BN + hh * 64;
             mbar_wait(s_full, j & 1);
             tc_fence_after();
-            // pass 1: row max of this chunk (keys beyond nk are masked)
+            uint32_t sv[64];
+#pragma unroll
+            for (int c = 0; c < 64; c += 16) tmem_ld_32x32b_x16(trow + hh * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&sv[c]));
+            tmem_ld_wait();
             float mx = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < AT_BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-#pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (kbase + c + i < a.nk) mx = fmaxf(mx, __uint_as_float(v[i]));
-            }
-            const float m_new = fmaxf(m_run, mx);             // finite: chunk 0 always holds key 0
+            for (int i = 0; i < 64; ++i)
+                if (kbase + i < a.nk) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            float* xm = xmax + (j & 1) * 256;
+            xm[hh * 128 + r] = mx;
+            pair_sync();
+            const float m_new = fmaxf(m_run, fmaxf(mx, xm[(hh ^ 1) * 128 + r]));   // finite: chunk 0 holds key 0
             const float corr = exp2f((m_run - m_new) * sl2);
             if (j > 0) {
                 mbar_wait(o_full, (j - 1) & 1);               // P_{j-1} V_{j-1} landed; the P buffer is free again
@@ -186,30 +190,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 add_o();
             }
 #pragma unroll
-            for (int i = 0; i < AT_D; ++i) o[i] *= corr;
+            for (int i = 0; i < 32; ++i) o[i] *= corr;
             l_run *= corr;
             m_run = m_new;
             const float msc = m_new * sl2;
-            // pass 2: probabilities -> smem (K-major, 128B swizzle: 16B chunk index ^= row & 7 inside each 64-key atom)
 #pragma unroll
-            for (int c = 0; c < AT_BN; c += 32) {
-                uint32_t v[32];
-                tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-                tmem_ld_wait();
-                float p[32];
+            for (int c8 = 0; c8 < 8; ++c8) {                  // 8 x 16-byte chunks = my 64 keys
+                float p[8];
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    p[i] = (kbase + c + i < a.nk) ? exp2f(__uint_as_float(v[i]) * sl2 - msc) : 0.f;
+                for (int i = 0; i < 8; ++i) {
+                    p[i] = (kbase + c8 * 8 + i < a.nk) ? exp2f(__uint_as_float(sv[c8 * 8 + i]) * sl2 - msc) : 0.f;
                     l_run += p[i];
                 }
-                uint8_t* atom = prow + (c >> 6) * AT_TILE;    // 64 keys per atom
-                const int chunk0 = (c & 63) >> 3;             // first 16B chunk of this batch inside the atom row
-#pragma unroll
-                for (int h4 = 0; h4 < 4; ++h4)
-                    *reinterpret_cast<uint4*>(atom + (((chunk0 + h4) ^ swz) << 4)) =
-                        make_uint4(pack_half2(p[8 * h4], p[8 * h4 + 1]), pack_half2(p[8 * h4 + 2], p[8 * h4 + 3]),
-                                   pack_half2(p[8 * h4 + 4], p[8 * h4 + 5]), pack_half2(p[8 * h4 + 6], p[8 * h4 + 7]));
+                *reinterpret_cast<uint4*>(prow + ((c8 ^ swz) << 4)) =
+                    make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
             }
             fence_proxy_async();                              // generic-proxy smem writes -> visible to the MMA
             tc_fence_before();
@@ -219,12 +213,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         mbar_wait(o_full, (nchunks - 1) & 1);
         tc_fence_after();
         add_o();
+        xsum[hh * 128 + r] = l_run;
+        pair_sync();
+        const float inv = 1.f / (l_run + xsum[(hh ^ 1) * 128 + r]);
         const int qrow = q0 + r;
         if (qrow < a.nq) {
-            const float inv = 1.f / l_run;
-            __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D;
+            __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D + hh * 32;
 #pragma unroll
-            for (int c = 0; c < AT_D; c += 16) {
+            for (int c = 0; c < 32; c += 16) {
                 uint32_t w[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) w[i] = pack_half2(o[c + 2 * i] * inv, o[c + 2 * i + 1] * inv);
@@ -274,7 +270,7 @@ int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
     a.o = static_cast<__half*>(p->o);
     a.o_bs = p->o_bs_outer; a.o_rs = p->o_rs;
     dim3 grid((p->nq + AT_BM - 1) / AT_BM, p->heads, p->outer);
-    attention_tc_kernel<<<grid, 192, AT_SMEM, st>>>(tq, tk, tv, a);
+    attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, a);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_attention (tcgen05)");
     return VMV_OK;

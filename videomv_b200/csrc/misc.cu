@@ -227,7 +227,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
 using namespace vmv;
 
 extern "C" const char* vmv_last_error(void) { return g_err; }
-extern "C" int vmv_abi_version(void) { return 1; }
+extern "C" int vmv_abi_version(void) { return 2; }
 extern "C" long long vmv_launch_count(void) { return g_launches.load(); }
 extern "C" int vmv_sizeof_gemm_params(void) { return (int)sizeof(vmv_gemm_params); }
 extern "C" int vmv_sizeof_attn_params(void) { return (int)sizeof(vmv_attn_params); }

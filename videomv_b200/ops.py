@@ -172,7 +172,7 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: flo
 
 def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tensor, *, outer: int, inner: int,
               heads: int, nq: int, nk: int, q_strides, k_strides, v_strides, o_strides, kv_group: int = 1,
-              scale: float = 0.125) -> torch.Tensor:
+              scale: float = 0.125, impl: int = 0) -> torch.Tensor:
     """softmax(q k^T scale) v with explicit (outer, inner, row) element strides; q/k/v/out are any fp16 CUDA
     tensors whose data_ptr is the first element of head 0."""
     p = AttnParams()
@@ -182,7 +182,7 @@ def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, out: torch.Tens
     p.k_bs_outer, p.k_bs_inner, p.k_rs = k_strides
     p.v_bs_outer, p.v_bs_inner, p.v_rs = v_strides
     p.o_bs_outer, p.o_bs_inner, p.o_rs = o_strides
-    p.kv_group, p.scale = kv_group, scale
+    p.kv_group, p.scale, p.impl = kv_group, scale, impl
     e0 = _prof_begin()
     check(_lib.lib().vmv_attention(ctypes.byref(p), _stream()), "vmv_attention")
     nb = outer * inner * heads
