@@ -27,15 +27,17 @@ int make_map_generic(CUtensorMap* m, const void* base, int rank, const unsigned 
 
 constexpr int AT_BM = 128, AT_BN = 128, AT_D = 64;
 constexpr int AT_TILE = 128 * 64 * 2;                     // 16 KiB: one [128][64] fp16 tile
+constexpr int AT_KV = 3;                                  // K/V ring depth (chunk j+2 loads while chunk j is consumed)
 constexpr int AT_OFF_Q = 0;
-constexpr int AT_OFF_K = AT_TILE;                         // 2 stages
-constexpr int AT_OFF_V = AT_OFF_K + 2 * AT_TILE;          // 2 stages
-constexpr int AT_OFF_P = AT_OFF_V + 2 * AT_TILE;          // [128][128] fp16 = two K atoms of 64 keys
+constexpr int AT_OFF_K = AT_TILE;
+constexpr int AT_OFF_V = AT_OFF_K + AT_KV * AT_TILE;
+constexpr int AT_OFF_P = AT_OFF_V + AT_KV * AT_TILE;      // [128][128] fp16 = two K atoms of 64 keys
 constexpr int AT_OFF_X = AT_OFF_P + 2 * AT_TILE;          // float [2 parity][2 halves][128 rows] max exchange + [2][128] sums
 constexpr int AT_OFF_BAR = AT_OFF_X + 6 * 128 * 4;
-constexpr int AT_SMEM = AT_OFF_BAR + 10 * 8 + 16;
+constexpr int AT_SMEM = AT_OFF_BAR + 16 * 8 + 16;
 constexpr int AT_THREADS = 320;
-constexpr int AT_TMEM_COLS = 256;                         // S: [0,128)  O: [128,192)
+constexpr int AT_TMEM_COLS = 512;                         // S0: [0,128)  S1: [128,256)  O: [256,320)
+constexpr int AT_OCOL = 256;
 
 struct AttTcArgs {
     int nq, nk, kv_group;
@@ -64,12 +66,12 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if ((smem_u32(smem) & 1023u) != 0) __trap();
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
     uint64_t* q_full = bars;            // [1]
-    uint64_t* kv_full = bars + 1;       // [2]
-    uint64_t* kv_empty = bars + 3;      // [2]
-    uint64_t* s_full = bars + 5;        // [1]  scores of chunk j are in TMEM
-    uint64_t* p_full = bars + 6;        // [1]  P_j is in smem, S is free (4 warp arrivals)
-    uint64_t* o_full = bars + 7;        // [1]  P_j V_j is in TMEM, the P buffer is free
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 8);
+    uint64_t* kv_full = bars + 1;       // [AT_KV]
+    uint64_t* kv_empty = bars + 4;      // [AT_KV]
+    uint64_t* s_full = bars + 7;        // [2]  scores of chunk j are in TMEM buffer j&1
+    uint64_t* p_full = bars + 9;        // [1]  P_j is in smem and S buffer j&1 is free (8 warp arrivals)
+    uint64_t* o_full = bars + 10;       // [1]  P_j V_j is in TMEM, the P buffer is free
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int qt = blockIdx.x, h = blockIdx.y, bo = blockIdx.z;
@@ -82,8 +84,9 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
-        for (int s = 0; s < 2; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-        mbar_init(s_full, 1);
+        for (int s = 0; s < AT_KV; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
         mbar_init(p_full, 8);
         mbar_init(o_full, 1);
         fence_barrier_init();
@@ -99,8 +102,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             mbar_arrive_expect_tx(q_full, AT_TILE);
             tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + q0);
             for (int j = 0; j < nchunks; ++j) {
-                const int st = j & 1;
-                const uint32_t ph = (j >> 1) & 1;
+                const int st = j % AT_KV;
+                const uint32_t ph = (j / AT_KV) & 1;
                 mbar_wait(&kv_empty[st], ph ^ 1);
                 mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
                 tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
@@ -115,30 +118,32 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint64_t qdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_Q));
             const uint64_t pdesc0 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P));
             const uint64_t pdesc1 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P + AT_TILE));
-            auto issue_s = [&](int j) {
-                const int st = j & 1;
-                mbar_wait(&kv_full[st], (j >> 1) & 1);
+            auto issue_s = [&](int j) {                       // S_j -> TMEM buffer j&1
+                const int st = j % AT_KV;
+                mbar_wait(&kv_full[st], (j / AT_KV) & 1);
                 tc_fence_after();
                 const uint64_t kdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_K + st * AT_TILE));
 #pragma unroll
-                for (int k = 0; k < AT_D / 16; ++k) umma_f16_ss(tmem_base, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(s_full);
+                for (int k = 0; k < AT_D / 16; ++k)
+                    umma_f16_ss(tmem_base + (j & 1) * AT_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[j & 1]);
             };
             mbar_wait(q_full, 0);
             issue_s(0);
+            if (nchunks > 1) issue_s(1);                      // two score buffers: S_{j+1} is computed during softmax_j
             for (int j = 0; j < nchunks; ++j) {
-                const int st = j & 1;
-                mbar_wait(p_full, j & 1);                     // P_j in smem; the softmax warps are done with S_j
+                const int st = j % AT_KV;
+                mbar_wait(p_full, j & 1);                     // P_j in smem; the softmax warps are done with S buffer j&1
                 tc_fence_after();
-                if (j + 1 < nchunks) issue_s(j + 1);          // next scores first: they overlap softmax_{j+1} with P_j V_j
                 const uint64_t vdesc = umma_desc_sw128_mnmajor(smem_u32(smem + AT_OFF_V + st * AT_TILE), AT_BN);
 #pragma unroll
                 for (int k = 0; k < AT_BN / 16; ++k) {
                     const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-                    umma_f16_ss(tmem_base + AT_BN, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : 0u);
+                    umma_f16_ss(tmem_base + AT_OCOL, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : 0u);
                 }
                 umma_commit(o_full);
                 umma_commit(&kv_empty[st]);
+                if (j + 2 < nchunks) issue_s(j + 2);          // refill the score buffer softmax_j just released
             }
         }
         __syncwarp();
@@ -160,8 +165,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
         auto add_o = [&]() {                                  // o += my 32 columns of O_j from TMEM
             uint32_t v[32];
-            tmem_ld_32x32b_x16(trow + AT_BN + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-            tmem_ld_32x32b_x16(trow + AT_BN + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+            tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+            tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
             tmem_ld_wait();
 #pragma unroll
             for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
@@ -169,16 +174,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
         for (int j = 0; j < nchunks; ++j) {
             const int kbase = j * AT_BN + hh * 64;
-            mbar_wait(s_full, j & 1);
+            const bool full = kbase + 64 <= a.nk;             // warp-uniform: only the last chunk can be ragged
+            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
             tc_fence_after();
             uint32_t sv[64];
 #pragma unroll
-            for (int c = 0; c < 64; c += 16) tmem_ld_32x32b_x16(trow + hh * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&sv[c]));
+            for (int c = 0; c < 64; c += 16)
+                tmem_ld_32x32b_x16(trow + (j & 1) * AT_BN + hh * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&sv[c]));
             tmem_ld_wait();
             float mx = -INFINITY;
+            if (full) {
 #pragma unroll
-            for (int i = 0; i < 64; ++i)
-                if (kbase + i < a.nk) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+            } else {
+#pragma unroll
+                for (int i = 0; i < 64; ++i) {
+                    if (kbase + i >= a.nk) sv[i] = 0xff800000u;                 // -inf: exp2 gives exactly 0
+                    mx = fmaxf(mx, __uint_as_float(sv[i]));
+                }
+            }
             float* xm = xmax + (j & 1) * 256;
             xm[hh * 128 + r] = mx;
             pair_sync();
@@ -199,7 +213,7 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 float p[8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    p[i] = (kbase + c8 * 8 + i < a.nk) ? exp2f(__uint_as_float(sv[c8 * 8 + i]) * sl2 - msc) : 0.f;
+                    p[i] = exp2f(fmaf(__uint_as_float(sv[c8 * 8 + i]), sl2, -msc));
                     l_run += p[i];
                 }
                 *reinterpret_cast<uint4*>(prow + ((c8 ^ swz) << 4)) =
