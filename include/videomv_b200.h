@@ -100,6 +100,14 @@ int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2
                         int64_t rows_per_batch, int32_t nbatch, const double* stats, int64_t stat_rows,
                         const float* gamma, const float* beta, float eps, int32_t silu,
                         void* out, int64_t ldo, void* stream);
+/* Single-launch form of the two calls above (single-GPU path: no reduction between statistics and apply): statistics,
+ * an in-kernel arrival barrier per chunk, then apply with x re-read from L2.  `scratch` holds
+ * vmv_groupnorm_fused_scratch_bytes(nbatch) bytes that must be ZERO on entry (one region per call; the engine zeroes a
+ * per-forward arena once).  Returns VMV_ERR_UNSUPPORTED when the grid cannot be made co-resident (never spins then). */
+int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch);
+int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                        int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
+                        float eps, int32_t silu, void* out, int64_t ldo, void* stream);
 
 /* Per-row LayerNorm statistics only: stats[m] = {mean, 1/sqrt(var+eps)} fp32 (for the folded form in vmv_gemm). */
 int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float eps, void* stats, void* stream);
@@ -127,8 +135,8 @@ typedef struct vmv_attn_params {
     int32_t kv_group;          /* kv outer index = bo / kv_group */
     float scale;               /* head_dim^-0.5 */
     int32_t impl;              /* 0 auto | 1 strided mma.sync kernel (any layout) | 2 tcgen05/TMEM kernel (contiguous
-                                  batches, nq >= 128; VMV_ERR_UNSUPPORTED otherwise).  Auto currently picks 1: the
-                                  tcgen05 kernel is validated but not yet faster. */
+                                  batches, nq >= 128; VMV_ERR_UNSUPPORTED otherwise).  Auto picks 2 whenever the
+                                  layout allows (spatial self-attention, text cross-attention), else 1. */
 } vmv_attn_params;
 int vmv_attention(const vmv_attn_params* p, void* stream);
 

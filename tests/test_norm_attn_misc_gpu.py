@@ -20,14 +20,16 @@ def _r(*shape, scale=1.0, seed=0, shift=0.0):
     (2, 24 * 16, 1280, 0, 1e-5, True), (24, 16, 1280, 1280, 1e-5, True), (4, 256, 64, 0, 1e-5, True),
     (24, 64, 1280, 640, 1e-5, True), (4, 64, 128, 64, 1e-6, False), (48, 1024, 640, 320, 1e-5, True),
 ])
-def test_groupnorm(nb, rows, C1, C2, eps, silu):
+@pytest.mark.parametrize("fused", [False, True], ids=["split", "fused"])
+def test_groupnorm(nb, rows, C1, C2, eps, silu, fused):
     from videomv_b200 import ops
     x1 = _r(nb * rows, C1, seed=1, shift=0.5, scale=2.0)
     x2 = _r(nb * rows, C2, seed=2, shift=-0.3) if C2 else None
     C = C1 + C2
     gamma = 1 + 0.1 * torch.randn(C, device="cuda")
     beta = 0.1 * torch.randn(C, device="cuda")
-    out = ops.groupnorm(x1, gamma, beta, rows_per_batch=rows, eps=eps, silu=silu, x2=x2)
+    arena = ops.GnArena("cuda", 1 << 20) if fused else None       # single-launch kernel (stats + barrier + apply)
+    out = ops.groupnorm(x1, gamma, beta, rows_per_batch=rows, eps=eps, silu=silu, x2=x2, scratch=arena)
     x = x1.float() if x2 is None else torch.cat([x1, x2], 1).float()
     xi = x.reshape(nb, rows, C).permute(0, 2, 1)
     ref = F.group_norm(xi, 32, gamma, beta, eps)
@@ -35,6 +37,10 @@ def test_groupnorm(nb, rows, C1, C2, eps, silu):
         ref = F.silu(ref)
     ref = ref.permute(0, 2, 1).reshape(nb * rows, C)
     assert_close(f"groupnorm nb{nb} rows{rows} C{C1}+{C2}", out, ref)
+    if fused:                                                     # second call on a fresh region, in place over x1
+        if C2 == 0:
+            out2 = ops.groupnorm(x1, gamma, beta, rows_per_batch=rows, eps=eps, silu=silu, out=x1, scratch=arena)
+            assert_close(f"groupnorm in-place nb{nb} rows{rows} C{C1}", out2, ref)
 
 
 @pytest.mark.parametrize("M,C", [(24576, 320), (6144, 640), (1536, 1280), (100, 512), (7, 64), (33, 2048)])

@@ -105,6 +105,9 @@ SYMBOLS = {
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
     "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
+    "vmv_groupnorm_fused_scratch_bytes": (c_i64, [c_i32]),
+    "vmv_groupnorm_fused": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+                                           c_f32, c_i32, c_vp, c_i64, c_vp]),
     "vmv_layernorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
     "vmv_attention": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),

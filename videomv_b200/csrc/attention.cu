@@ -8,9 +8,9 @@
 // frames of a sample) and temporal attention (rows = frames of a pixel) -- no head split / merge or
 // NCHW<->token transposes (reference util.py:237-244,262-267,1054-1083).
 //
-// NOTE (roadmap): this is the legacy-MMA (HMMA) implementation that made the path correct end to end;
-// attention is 3% of the FLOPs at 256^2.  The tcgen05/TMEM version for the 1024/4096-token spatial case
-// is tracked in DESIGN.md.
+// This mma.sync kernel serves the strided / short-row cases (temporal attention over 24 frames, < 128 query rows);
+// spatial self-attention and text cross-attention are dispatched to the persistent tcgen05/TMEM kernel in
+// attention_tc.cu (profiles/r1_attention_tc_vs_mma.log).
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
@@ -153,7 +153,7 @@ attention_kernel(const vmv_attn_params p) {
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float m_new = fmaxf(m_run[i], mx[i]);       // finite: chunk 0 always holds key 0
-            corr[i] = exp2f((m_run[i] - m_new) * sl2);
+            corr[i] = ex2_approx_f((m_run[i] - m_new) * sl2);
             m_run[i] = m_new;
             msc[i] = m_new * sl2;
             l_run[i] *= corr[i];
@@ -166,10 +166,10 @@ attention_kernel(const vmv_attn_params p) {
         uint32_t pf[BC / 16][4];
 #pragma unroll
         for (int j = 0; j < BC / 8; ++j) {
-            const float p0 = exp2f(s[j][0] * sl2 - msc[0]);
-            const float p1 = exp2f(s[j][1] * sl2 - msc[0]);
-            const float p2 = exp2f(s[j][2] * sl2 - msc[1]);
-            const float p3 = exp2f(s[j][3] * sl2 - msc[1]);
+            const float p0 = ex2_approx_f(s[j][0] * sl2 - msc[0]);
+            const float p1 = ex2_approx_f(s[j][1] * sl2 - msc[0]);
+            const float p2 = ex2_approx_f(s[j][2] * sl2 - msc[1]);
+            const float p3 = ex2_approx_f(s[j][3] * sl2 - msc[1]);
             l_run[0] += p0 + p1;
             l_run[1] += p2 + p3;
             pf[j >> 1][(j & 1) * 2] = pack_half2(p0, p1);
@@ -233,10 +233,10 @@ extern "C" int vmv_attention(const vmv_attn_params* p, void* stream) {
     VMV_CHECK_ARG(nb <= 65535 * 1LL && p->heads <= 65535, "vmv_attention: batch %lld too large for one launch", nb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
-        // tcgen05 kernel for long contiguous sequences (spatial self-attention, text cross-attention): explicit
-        // (impl == 2) or, when VMV_ATTN_TC=1, whenever the layout allows.
+        // tcgen05 kernel whenever the layout allows (contiguous batches of >= 128 query rows: spatial self-attention
+        // and text cross-attention), or explicitly with impl == 2.  VMV_ATTN_TC=0 keeps auto on the mma.sync kernel.
         static int auto_tc = -1;
-        if (auto_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); auto_tc = (e && e[0] == '1') ? 1 : 0; }
+        if (auto_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); auto_tc = (e && e[0] == '0') ? 0 : 1; }
         if (p->impl == 2 || (p->impl == 0 && auto_tc)) {
             const int rc = attention_tc_try(p, st);
             if (rc != VMV_ERR_UNSUPPORTED) return rc;

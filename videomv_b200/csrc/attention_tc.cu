@@ -1,19 +1,21 @@
 // tcgen05 flash attention for the long-sequence cases (spatial self-attention 256..4096 tokens, text cross-attention):
 //   O = softmax(Q K^T * scale) V,  head_dim 64, fp16 in/out, fp32 softmax, batches contiguous in memory.
 //
-// One CTA = 128 query rows of one (batch, head); K/V streamed in 128-key chunks through a 2-stage TMA ring.
-//   warp 0      TMA producer (Q once, then K/V chunks; 128B-swizzled boxes straight out of the fused QKV GEMM output)
+// Persistent: one CTA per SM walks tiles of 128 query rows of one (batch, head); K/V are streamed in 128-key chunks
+// through a 4-stage TMA ring.  All pipeline counters run across tiles, so the next tile's Q / first K/V chunks are
+// loaded and its first two score tiles computed while the softmax warps finish and store the current tile.
+//   warp 0      TMA producer (Q per tile, then K/V chunks; 128B-swizzled boxes straight out of the fused QKV GEMM output)
 //   warp 1      TMEM allocator + single-thread tcgen05.mma issuer
-//                 S_j = Q K_j^T      M128 x N128 x K64   (both operands K-major)            -> TMEM cols [0,128)
-//                 O_j = P_j V_j      M128 x N64  x K128  (P K-major from smem, V MN-major)  -> TMEM cols [128,192)
+//                 S_g = Q K_g^T      M128 x N128 x K64   (both operands K-major)            -> TMEM cols [128 (g&1), +128)
+//                 O_g = P_g V_g      M128 x N64  x K128  (P K-major from smem, V MN-major)  -> TMEM cols [256,320)
 //   warps 2..9  softmax: two warps per TMEM lane quarter; a query row is shared by one thread of each, which takes 64 of
 //               the chunk's 128 keys (single TMEM pass, scores stay in registers) and 32 of the 64 output columns.  The
 //               pair exchanges its partial row max through smem (named barrier per quarter); P is written to smem in the
 //               UMMA K-major 128B-swizzle layout (one 64-key atom per warp); the running output lives in registers and is
 //               corrected per chunk (O_j is read back from TMEM, never accumulated there).
-// Issue order S_{j+1} before P_j V_j lets the tensor core compute the next scores while the softmax warps work.  The
-// kernel is exponent-bound (16 MUFU/clk/SM: 1024 cycles per 128x128 chunk vs 512 cycles of MMA), hence two warps per
-// scheduler on the softmax side to hide the TMEM / barrier latencies.
+// Two score buffers: S_{g+1} (and S_{g+2} as soon as softmax_g releases its buffer) are computed while the softmax warps
+// work on chunk g.  The kernel is exponent-bound (16 MUFU/clk/SM: 1024 cycles per 128x128 chunk vs 512 cycles of MMA),
+// hence two warps per scheduler on the softmax side to hide the TMEM / barrier latencies.
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
@@ -27,7 +29,7 @@ int make_map_generic(CUtensorMap* m, const void* base, int rank, const unsigned 
 
 constexpr int AT_BM = 128, AT_BN = 128, AT_D = 64;
 constexpr int AT_TILE = 128 * 64 * 2;                     // 16 KiB: one [128][64] fp16 tile
-constexpr int AT_KV = 3;                                  // K/V ring depth (chunk j+2 loads while chunk j is consumed)
+constexpr int AT_KV = 4;                                  // K/V ring depth (a 32 KiB chunk is ~1 chunk period of TMA latency)
 constexpr int AT_OFF_Q = 0;
 constexpr int AT_OFF_K = AT_TILE;
 constexpr int AT_OFF_V = AT_OFF_K + AT_KV * AT_TILE;
@@ -41,6 +43,7 @@ constexpr int AT_OCOL = 256;
 
 struct AttTcArgs {
     int nq, nk, kv_group;
+    int nqt, heads, ntiles;                               // tile = (batch, head, 128-row block), q block fastest
     float scale_log2;                                     // scale * log2(e)
     __half* o;
     long long o_bs, o_rs;                                 // elements
@@ -67,23 +70,23 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + AT_OFF_BAR);
     uint64_t* q_full = bars;            // [1]
     uint64_t* kv_full = bars + 1;       // [AT_KV]
-    uint64_t* kv_empty = bars + 4;      // [AT_KV]
-    uint64_t* s_full = bars + 7;        // [2]  scores of chunk j are in TMEM buffer j&1
-    uint64_t* p_full = bars + 9;        // [1]  P_j is in smem and S buffer j&1 is free (8 warp arrivals)
-    uint64_t* o_full = bars + 10;       // [1]  P_j V_j is in TMEM, the P buffer is free
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* kv_empty = bars + 5;      // [AT_KV]
+    uint64_t* s_full = bars + 9;        // [2]  scores of chunk g are in TMEM buffer g&1
+    uint64_t* p_full = bars + 11;       // [1]  P_g is in smem and S buffer g&1 is free (8 warp arrivals)
+    uint64_t* o_full = bars + 12;       // [1]  P_g V_g is in TMEM, the P buffer is free
+    uint64_t* q_empty = bars + 13;      // [1]  every S MMA of the tile has read Q
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int qt = blockIdx.x, h = blockIdx.y, bo = blockIdx.z;
-    const int kbo = bo / a.kv_group;
-    const int q0 = qt * AT_BM;
     const int nchunks = (a.nk + AT_BN - 1) / AT_BN;
+    const int tstep = gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmQ);
         tma_prefetch_desc(&tmK);
         tma_prefetch_desc(&tmV);
         mbar_init(q_full, 1);
+        mbar_init(q_empty, 1);
         for (int s = 0; s < AT_KV; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
         mbar_init(&s_full[0], 1);
         mbar_init(&s_full[1], 1);
@@ -99,15 +102,20 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 
     if (warp == 0) {
         if (lane == 0) {
-            mbar_arrive_expect_tx(q_full, AT_TILE);
-            tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + q0);
-            for (int j = 0; j < nchunks; ++j) {
-                const int st = j % AT_KV;
-                const uint32_t ph = (j / AT_KV) & 1;
-                mbar_wait(&kv_empty[st], ph ^ 1);
-                mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
-                tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
-                tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+            int g = 0, tc = 0;                                // chunk / tile counters of this CTA
+            for (int T = blockIdx.x; T < a.ntiles; T += tstep, ++tc) {
+                const int qt = T % a.nqt, h = (T / a.nqt) % a.heads, bo = T / (a.nqt * a.heads);
+                const int kbo = bo / a.kv_group;
+                mbar_wait(q_empty, (tc & 1) ^ 1);
+                mbar_arrive_expect_tx(q_full, AT_TILE);
+                tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + qt * AT_BM);
+                for (int j = 0; j < nchunks; ++j, ++g) {
+                    const int st = g % AT_KV;
+                    mbar_wait(&kv_empty[st], ((g / AT_KV) & 1) ^ 1);
+                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
+                    tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                    tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                }
             }
         }
         __syncwarp();
@@ -118,32 +126,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             const uint64_t qdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_Q));
             const uint64_t pdesc0 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P));
             const uint64_t pdesc1 = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_P + AT_TILE));
-            auto issue_s = [&](int j) {                       // S_j -> TMEM buffer j&1
-                const int st = j % AT_KV;
-                mbar_wait(&kv_full[st], (j / AT_KV) & 1);
+            // score cursor: runs up to two chunks ahead of the P V cursor, across tile boundaries
+            int sT = blockIdx.x, sj = 0, sg = 0, stc = 0;
+            auto issue_next_s = [&]() {                       // S_sg -> TMEM buffer sg&1
+                if (sT >= a.ntiles) return;
+                if (sj == 0) mbar_wait(q_full, stc & 1);
+                const int st = sg % AT_KV;
+                mbar_wait(&kv_full[st], (sg / AT_KV) & 1);
                 tc_fence_after();
                 const uint64_t kdesc = umma_desc_sw128_kmajor(smem_u32(smem + AT_OFF_K + st * AT_TILE));
 #pragma unroll
                 for (int k = 0; k < AT_D / 16; ++k)
-                    umma_f16_ss(tmem_base + (j & 1) * AT_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
-                umma_commit(&s_full[j & 1]);
+                    umma_f16_ss(tmem_base + (sg & 1) * AT_BN, qdesc + 2 * k, kdesc + 2 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&s_full[sg & 1]);
+                ++sg;
+                if (++sj == nchunks) { umma_commit(q_empty); sj = 0; sT += tstep; ++stc; }
             };
-            mbar_wait(q_full, 0);
-            issue_s(0);
-            if (nchunks > 1) issue_s(1);                      // two score buffers: S_{j+1} is computed during softmax_j
-            for (int j = 0; j < nchunks; ++j) {
-                const int st = j % AT_KV;
-                mbar_wait(p_full, j & 1);                     // P_j in smem; the softmax warps are done with S buffer j&1
-                tc_fence_after();
-                const uint64_t vdesc = umma_desc_sw128_mnmajor(smem_u32(smem + AT_OFF_V + st * AT_TILE), AT_BN);
+            issue_next_s();
+            issue_next_s();
+            int g = 0;
+            for (int T = blockIdx.x; T < a.ntiles; T += tstep) {
+                for (int j = 0; j < nchunks; ++j, ++g) {
+                    const int st = g % AT_KV;
+                    mbar_wait(p_full, g & 1);                 // P_g in smem; the softmax warps are done with S buffer g&1
+                    tc_fence_after();
+                    const uint64_t vdesc = umma_desc_sw128_mnmajor(smem_u32(smem + AT_OFF_V + st * AT_TILE), AT_BN);
 #pragma unroll
-                for (int k = 0; k < AT_BN / 16; ++k) {
-                    const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
-                    umma_f16_ss(tmem_base + AT_OCOL, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < AT_BN / 16; ++k) {
+                        const uint64_t pd = (k < 4 ? pdesc0 : pdesc1) + 2 * (k & 3);
+                        umma_f16_ss(tmem_base + AT_OCOL, pd, vdesc + (2048 >> 4) * k, idesc_o, k > 0 ? 1u : 0u);
+                    }
+                    umma_commit(o_full);
+                    umma_commit(&kv_empty[st]);
+                    issue_next_s();                           // refill the score buffer softmax_g just released
                 }
-                umma_commit(o_full);
-                umma_commit(&kv_empty[st]);
-                if (j + 2 < nchunks) issue_s(j + 2);          // refill the score buffer softmax_j just released
             }
         }
         __syncwarp();
@@ -157,89 +173,100 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         uint8_t* prow = smem + AT_OFF_P + hh * AT_TILE + r * 128;      // my 64-key atom, my row
         float* xmax = reinterpret_cast<float*>(smem + AT_OFF_X);       // [2][2][128]
         float* xsum = xmax + 4 * 128;                                  // [2][128]
-        float m_run = -INFINITY, l_run = 0.f;
-        float o[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) o[i] = 0.f;
         const float sl2 = a.scale_log2;
         auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + q) : "memory"); };
-        auto add_o = [&]() {                                  // o += my 32 columns of O_j from TMEM
-            uint32_t v[32];
-            tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-            tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
-            tmem_ld_wait();
+        int g = 0;
+        for (int T = blockIdx.x; T < a.ntiles; T += tstep) {
+            const int qt = T % a.nqt, h = (T / a.nqt) % a.heads, bo = T / (a.nqt * a.heads);
+            float m_run = -INFINITY, l_run = 0.f;
+            float o[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
-        };
-
-        for (int j = 0; j < nchunks; ++j) {
-            const int kbase = j * AT_BN + hh * 64;
-            const bool full = kbase + 64 <= a.nk;             // warp-uniform: only the last chunk can be ragged
-            mbar_wait(&s_full[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            uint32_t sv[64];
+            for (int i = 0; i < 32; ++i) o[i] = 0.f;
+            auto add_o = [&]() {                              // o += my 32 columns of O_g from TMEM
+                uint32_t v[32];
+                tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                tmem_ld_32x32b_x16(trow + AT_OCOL + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                tmem_ld_wait();
 #pragma unroll
-            for (int c = 0; c < 64; c += 16)
-                tmem_ld_32x32b_x16(trow + (j & 1) * AT_BN + hh * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&sv[c]));
-            tmem_ld_wait();
-            float mx = -INFINITY;
-            if (full) {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
-            } else {
-#pragma unroll
-                for (int i = 0; i < 64; ++i) {
-                    if (kbase + i >= a.nk) sv[i] = 0xff800000u;                 // -inf: exp2 gives exactly 0
-                    mx = fmaxf(mx, __uint_as_float(sv[i]));
-                }
-            }
-            float* xm = xmax + (j & 1) * 256;
-            xm[hh * 128 + r] = mx;
-            pair_sync();
-            const float m_new = fmaxf(m_run, fmaxf(mx, xm[(hh ^ 1) * 128 + r]));   // finite: chunk 0 holds key 0
-            const float corr = exp2f((m_run - m_new) * sl2);
-            if (j > 0) {
-                mbar_wait(o_full, (j - 1) & 1);               // P_{j-1} V_{j-1} landed; the P buffer is free again
+                for (int i = 0; i < 32; ++i) o[i] += __uint_as_float(v[i]);
+            };
+            for (int j = 0; j < nchunks; ++j, ++g) {
+                const int kbase = j * AT_BN + hh * 64;
+                const bool full = kbase + 64 <= a.nk;         // warp-uniform: only the last chunk can be ragged
+                mbar_wait(&s_full[g & 1], (g >> 1) & 1);
                 tc_fence_after();
-                add_o();
-            }
+                uint32_t sv[64];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) o[i] *= corr;
-            l_run *= corr;
-            m_run = m_new;
-            const float msc = m_new * sl2;
+                for (int c = 0; c < 64; c += 16)
+                    tmem_ld_32x32b_x16(trow + (g & 1) * AT_BN + hh * 64 + c, *reinterpret_cast<uint32_t(*)[16]>(&sv[c]));
+                tmem_ld_wait();
+                float mx = -INFINITY;
+                if (full) {
 #pragma unroll
-            for (int c8 = 0; c8 < 8; ++c8) {                  // 8 x 16-byte chunks = my 64 keys
-                float p[8];
+                    for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                } else {
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    p[i] = exp2f(fmaf(__uint_as_float(sv[c8 * 8 + i]), sl2, -msc));
-                    l_run += p[i];
+                    for (int i = 0; i < 64; ++i) {
+                        if (kbase + i >= a.nk) sv[i] = 0xff800000u;             // -inf: exp2 gives exactly 0
+                        mx = fmaxf(mx, __uint_as_float(sv[i]));
+                    }
                 }
-                *reinterpret_cast<uint4*>(prow + ((c8 ^ swz) << 4)) =
-                    make_uint4(pack_half2(p[0], p[1]), pack_half2(p[2], p[3]), pack_half2(p[4], p[5]), pack_half2(p[6], p[7]));
-            }
-            fence_proxy_async();                              // generic-proxy smem writes -> visible to the MMA
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(p_full);
-        }
-        mbar_wait(o_full, (nchunks - 1) & 1);
-        tc_fence_after();
-        add_o();
-        xsum[hh * 128 + r] = l_run;
-        pair_sync();
-        const float inv = 1.f / (l_run + xsum[(hh ^ 1) * 128 + r]);
-        const int qrow = q0 + r;
-        if (qrow < a.nq) {
-            __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D + hh * 32;
+                float* xm = xmax + (g & 1) * 256;
+                xm[hh * 128 + r] = mx;
+                pair_sync();
+                const float m_new = fmaxf(m_run, fmaxf(mx, xm[(hh ^ 1) * 128 + r]));   // finite: chunk 0 holds key 0
+                const float corr = ex2_approx_f((m_run - m_new) * sl2);
+                m_run = m_new;
+                const float msc = m_new * sl2;
+                // Exponentials first, into registers: the MUFU phase overlaps P_{g-1} V_{g-1} on the tensor core.  Only
+                // then wait for that MMA (it frees the P buffer and holds the O tile to fold into the running output).
+                uint32_t pk[32];
+                float lsum = 0.f;
 #pragma unroll
-            for (int c = 0; c < 32; c += 16) {
-                uint32_t w[8];
+                for (int c8 = 0; c8 < 8; ++c8) {              // 8 x 16-byte chunks = my 64 keys
+                    float p[8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) w[i] = pack_half2(o[c + 2 * i] * inv, o[c + 2 * i + 1] * inv);
-                stg256(dst + c, w);
+                    for (int i = 0; i < 8; ++i)
+                        p[i] = ex2_approx_f(fmaf(__uint_as_float(sv[c8 * 8 + i]), sl2, -msc));
+                    lsum += ((p[0] + p[1]) + (p[2] + p[3])) + ((p[4] + p[5]) + (p[6] + p[7]));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pk[c8 * 4 + i] = pack_half2(p[2 * i], p[2 * i + 1]);
+                }
+                l_run = fmaf(l_run, corr, lsum);
+                if (j > 0) {
+                    mbar_wait(o_full, (g - 1) & 1);           // P_{g-1} V_{g-1} landed; the P buffer is free again
+                    tc_fence_after();
+                    add_o();
+                }
+#pragma unroll
+                for (int c8 = 0; c8 < 8; ++c8)
+                    *reinterpret_cast<uint4*>(prow + ((c8 ^ swz) << 4)) =
+                        make_uint4(pk[c8 * 4], pk[c8 * 4 + 1], pk[c8 * 4 + 2], pk[c8 * 4 + 3]);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) o[i] *= corr;
+                fence_proxy_async();                          // generic-proxy smem writes -> visible to the MMA
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(p_full);
             }
+            mbar_wait(o_full, (g - 1) & 1);
+            tc_fence_after();
+            add_o();
+            xsum[hh * 128 + r] = l_run;
+            pair_sync();
+            const float inv = 1.f / (l_run + xsum[(hh ^ 1) * 128 + r]);
+            const int qrow = qt * AT_BM + r;
+            if (qrow < a.nq) {
+                __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D + hh * 32;
+#pragma unroll
+                for (int c = 0; c < 32; c += 16) {
+                    uint32_t w[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) w[i] = pack_half2(o[c + 2 * i] * inv, o[c + 2 * i + 1] * inv);
+                    stg256(dst + c, w);
+                }
+            }
+            pair_sync();                                      // xsum is reused by the next tile
         }
     }
 
@@ -283,7 +310,18 @@ int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
     a.scale_log2 = p->scale * 1.4426950408889634f;
     a.o = static_cast<__half*>(p->o);
     a.o_bs = p->o_bs_outer; a.o_rs = p->o_rs;
-    dim3 grid((p->nq + AT_BM - 1) / AT_BM, p->heads, p->outer);
+    a.nqt = (p->nq + AT_BM - 1) / AT_BM;
+    a.heads = p->heads;
+    const long long ntiles = (long long)a.nqt * p->heads * p->outer;
+    if (ntiles > 0x7fffffffLL) return VMV_ERR_UNSUPPORTED;
+    a.ntiles = (int)ntiles;
+    static int num_sms = 0;
+    if (num_sms == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;   // persistent: one CTA per SM (176 KiB smem, 512 TMEM columns)
     attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, a);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_attention (tcgen05)");

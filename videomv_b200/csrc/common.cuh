@@ -38,6 +38,14 @@ void set_error(const char* fmt, ...);   // api.cu: stores the message for vmv_la
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // 2 MUFU + 2 FP ops
 // exact (erf) GELU: F.gelu default, reference util.py:550.
+// 2^x on the MUFU pipe, one instruction (exp2f() adds a denormal-range rescale: FSETP + 2 FMUL per call).
+// ex2.approx.ftz: max rel. error 2^-22, ex2(-inf) = +0.
+__device__ __forceinline__ float ex2_approx_f(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // erf via Abramowitz-Stegun 7.1.26 (|abs error| <= 1.5e-7, far below the fp16 output rounding): two MUFU ops (ex2, rcp)
 // plus a 5-term Horner polynomial instead of erff()'s branchy ~30-instruction sequence.
 __device__ __forceinline__ float erf_as_f(float x) {

@@ -16,7 +16,8 @@ struct GnGeom {
     int rows_per_cta;
 };
 
-static GnGeom gn_geom(int C1, int C2, long long rows_per_batch, int nbatch) {
+// max_ctas > 0: never exceed that many CTAs in total (fused kernel: all CTAs must be co-resident)
+static GnGeom gn_geom(int C1, int C2, long long rows_per_batch, int nbatch, long long max_ctas = 0) {
     GnGeom g;
     g.C = C1 + C2;
     g.C1 = C1;
@@ -27,6 +28,10 @@ static GnGeom gn_geom(int C1, int C2, long long rows_per_batch, int nbatch) {
     // aim for >= ~4 CTAs per SM overall while keeping >= 8 rows per row lane
     long long target_ctas = 148LL * 4;
     long long per_batch = (target_ctas + nbatch - 1) / nbatch;
+    if (max_ctas > 0) {
+        per_batch = max_ctas / ((long long)nbatch * g.slabs);
+        if (per_batch < 1) per_batch = 1;
+    }
     long long rpc = (rows_per_batch + per_batch - 1) / per_batch;
     long long min_rpc = (long long)g.lanes * 8;
     if (rpc < min_rpc) rpc = min_rpc;
@@ -109,28 +114,33 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
                 int C, long long rows_per_batch, long long stat_rows, int rows_per_cta, int vw, int lanes,
                 const double* __restrict__ stats, const float* __restrict__ gamma, const float* __restrict__ beta,
                 float eps, int silu, __half* __restrict__ out, long long ldo) {
+    // Group mean / rstd once per CTA (32 threads do the fp64 part: E[x^2] - mean^2 cancels in fp32), not once per
+    // channel per thread: 256 threads x 8 channels of fp64 div/sqrt cost more than streaming the CTA's rows.
+    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int t = threadIdx.x;
     const int batch = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    if (t < GN_GROUPS) {
+        const double inv_cnt = 1.0 / ((double)stat_rows * cpg);   // stat_rows > rows_per_batch: stats all-reduced over shards
+        const double mean = stats[((long long)batch * GN_GROUPS + t) * 2] * inv_cnt;
+        double var = stats[((long long)batch * GN_GROUPS + t) * 2 + 1] * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[t] = (float)mean;
+        s_rstd[t] = rsqrtf((float)var + eps);
+    }
+    __syncthreads();
     const int tx = t % vw, ty = t / vw;
     const int vec = blockIdx.z * vw + tx;
     const int c0 = vec * 8;
     if (ty >= lanes || c0 >= C) return;
-    const int cpg = C / GN_GROUPS;
-    const double cnt = (double)stat_rows * cpg;       // > rows_per_batch when the statistics were all-reduced over shards
     float sc[8], sh[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int c = c0 + j;
         const int g = c / cpg;
-        const double sum = stats[((long long)batch * GN_GROUPS + g) * 2];
-        const double sq = stats[((long long)batch * GN_GROUPS + g) * 2 + 1];
-        const double mean = sum / cnt;
-        double var = sq / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = (float)(1.0 / sqrt(var + (double)eps));
-        const float ga = gamma[c] * rstd;
+        const float ga = __ldg(gamma + c) * s_rstd[g];
         sc[j] = ga;
-        sh[j] = beta[c] - (float)mean * ga;
+        sh[j] = __ldg(beta + c) - s_mean[g] * ga;
     }
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     long long r_end = r_begin + rows_per_cta;
@@ -158,6 +168,132 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
         apply(u0, r); apply(u1, r + lanes); apply(u2, r + 2LL * lanes); apply(u3, r + 3LL * lanes);
     }
     for (; r < r_end; r += lanes) apply(__ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0)), r);
+}
+
+// Single-launch GroupNorm: statistics, a per-batch arrival barrier, then apply -- the second read of x comes from L2
+// instead of HBM and the memset + two launches of the split path collapse into one graph node.  The barrier is a
+// plain global counter, so every CTA of the grid must be co-resident: the host wrapper checks the grid against the
+// occupancy of this kernel and refuses otherwise (the caller then uses the split kernels).  `stats` / `arrive` must
+// be zero on entry (the engine zeroes one arena per forward).
+__global__ void __launch_bounds__(GN_THREADS)
+gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
+                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats,
+                unsigned int* __restrict__ arrive, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu, __half* __restrict__ out, long long ldo) {
+    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+    const int t = threadIdx.x;
+    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
+    __syncthreads();
+    const int batch = blockIdx.y;
+    const int tx = t % vw, ty = t / vw;
+    const int vec = blockIdx.z * vw + tx;
+    const int c0 = vec * 8;
+    const int cpg = C / GN_GROUPS;
+    const bool active = ty < lanes && c0 < C;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    long long r_end = r_begin + rows_per_cta;
+    if (r_end > rows_per_batch) r_end = rows_per_batch;
+    const long long base = (long long)batch * rows_per_batch;
+    // ---- phase 1: partial sums of this CTA's rows
+    if (active) {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+        auto acc = [&](const uint4& u) {
+            uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float2 f = unpack_half2(w[j]);
+                s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+                s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+            }
+        };
+        long long r = r_begin + ty;
+        for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+            uint4 u0 = *gn_src(x1, ld1, C1, x2, ld2, base + r, c0);
+            uint4 u1 = *gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0);
+            uint4 u2 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0);
+            uint4 u3 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0);
+            acc(u0); acc(u1); acc(u2); acc(u3);
+        }
+        for (; r < r_end; r += lanes) acc(*gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
+        int g_prev = c0 / cpg;
+        float as = 0.f, aq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            int g = (c0 + j) / cpg;
+            if (g != g_prev) {
+                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+                as = 0.f; aq = 0.f; g_prev = g;
+            }
+            as += s[j]; aq += q[j];
+        }
+        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+    }
+    __syncthreads();
+    if (t < GN_GROUPS) {
+        float a = s_sum[t], b = s_sq[t];
+        if (a != 0.f || b != 0.f) {
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)a);
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)b);
+        }
+        __threadfence();
+    }
+    __syncthreads();
+    // ---- barrier over the CTAs of this batch (release: the fences above; acquire: the load below)
+    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    if (t == 0) {
+        const unsigned int expected = gridDim.x * gridDim.z;
+        atomicAdd(&arrive[batch], 1u);
+        unsigned int seen, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive + batch) : "memory");
+            if (++spins > (1u << 26)) __trap();               // co-residency was checked on the host; never a silent hang
+        } while (seen < expected);
+    }
+    __syncthreads();
+    // ---- phase 2: normalise; x is re-read (L2) -- not through the non-coherent path, `out` may alias x
+    if (t < GN_GROUPS) {
+        const double inv_cnt = 1.0 / ((double)rows_per_batch * cpg);
+        const double mean = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]) * inv_cnt;
+        double var = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]) * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[t] = (float)mean;
+        s_rstd[t] = rsqrtf((float)var + eps);
+    }
+    __syncthreads();
+    if (!active) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const int g = c / cpg;
+        const float ga = __ldg(gamma + c) * s_rstd[g];
+        sc[j] = ga;
+        sh[j] = __ldg(beta + c) - s_mean[g] * ga;
+    }
+    auto apply = [&](const uint4& u, long long r) {
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_half2(w[j]);
+            float a = f.x * sc[2 * j] + sh[2 * j];
+            float b = f.y * sc[2 * j + 1] + sh[2 * j + 1];
+            if (silu) { a = silu_f(a); b = silu_f(b); }
+            o[j] = pack_half2(a, b);
+        }
+        *reinterpret_cast<uint4*>(out + (base + r) * ldo + c0) = make_uint4(o[0], o[1], o[2], o[3]);
+    };
+    long long r = r_begin + ty;
+    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
+        uint4 u0 = *gn_src(x1, ld1, C1, x2, ld2, base + r, c0);
+        uint4 u1 = *gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0);
+        uint4 u2 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0);
+        uint4 u3 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0);
+        apply(u0, r); apply(u1, r + lanes); apply(u2, r + 2LL * lanes); apply(u3, r + 3LL * lanes);
+    }
+    for (; r < r_end; r += lanes) apply(*gn_src(x1, ld1, C1, x2, ld2, base + r, c0), r);
 }
 
 // One warp per row; the row lives in registers (<= 8 vectors of 8 halfs per lane => C <= 2048).
@@ -340,6 +476,45 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
                                                  static_cast<__half*>(out), ldo);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_apply");
+    return VMV_OK;
+}
+
+// Scratch for one fused call: nbatch*64 doubles (sums) followed by nbatch uint32 arrival counters, all zero on entry.
+extern "C" int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch) {
+    return (int64_t)nbatch * 2 * GN_GROUPS * 8 + (((int64_t)nbatch * 4 + 7) / 8) * 8;
+}
+
+extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                                   int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
+                                   const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
+    int rc = gn_check("vmv_groupnorm_fused", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
+    if (rc) return rc;
+    VMV_CHECK_ARG(scratch && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_fused: bad scratch/gamma/beta/out");
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    static int capacity = 0;                                   // co-resident CTAs of gn_fused_kernel on this device
+    if (capacity == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, GN_THREADS, 0);
+        if (e != cudaSuccess) { set_error("vmv_groupnorm_fused: occupancy query failed: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+        capacity = sms * per_sm;
+    }
+    GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch, capacity);
+    dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
+    if ((long long)grid.x * grid.y * grid.z > capacity) {
+        set_error("vmv_groupnorm_fused: grid of %u CTAs exceeds the %d co-resident CTAs the in-kernel barrier needs; "
+                  "use vmv_groupnorm_stats + vmv_groupnorm_apply", grid.x * grid.y * grid.z, capacity);
+        return VMV_ERR_UNSUPPORTED;
+    }
+    double* stats = static_cast<double*>(scratch);
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(stats + (size_t)nbatch * 2 * GN_GROUPS);
+    gn_fused_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+                                                 static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
+                                                 g.rows_per_cta, g.vw, g.lanes, stats, arrive, gamma, beta, eps, silu,
+                                                 static_cast<__half*>(out), ldo);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused");
     return VMV_OK;
 }
 

@@ -13,12 +13,17 @@ dispatch to.  Per-op reference citations live in include/videomv_b200.h.
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional, Tuple
 
 import torch
 import torch.nn.functional as F
 
-from . import ops, packing, parallel
+from . import _lib, ops, packing, parallel
+
+
+def _lib_scratch_bytes(nbatch: int) -> int:
+    return _lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch)
 
 SM_COUNT = 148
 
@@ -49,6 +54,9 @@ class UNetEngine:
         self._graphs: Dict[Tuple, "_Graph"] = {}
         self.use_graphs = False
         self.shard: Optional[parallel.ShardCtx] = None     # frame sharding of one sample over the ranks of a group
+        self._gn_arena: Optional[ops.GnArena] = None       # zeroed scratch of the single-launch GroupNorm (per forward)
+        self._gn_arenas: Dict[int, ops.GnArena] = {}
+        self.fused_groupnorm = os.environ.get("VMV_GN_FUSED", "1") != "0"
         self._pack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -203,9 +211,9 @@ class UNetEngine:
         B, Fr, H, W = S["B"], S["F"], S["H"], S["W"]
         HW = H * W
         emb = S["emb_all"][:, d["emb_off"]:d["emb_off"] + d["cout"]]
-        a0 = ops.groupnorm(x, *d["gn1"], rows_per_batch=HW, eps=1e-5, silu=True, x2=skip)
+        a0 = ops.groupnorm(x, *d["gn1"], rows_per_batch=HW, eps=1e-5, silu=True, x2=skip, scratch=self._gn_arena)
         h = self._gemm(a0, d["c1"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), rowbias=emb, rows_per_group=HW)
-        a1 = ops.groupnorm(h, *d["gn2"], rows_per_batch=HW, eps=1e-5, silu=True)
+        a1 = ops.groupnorm(h, *d["gn2"], rows_per_batch=HW, eps=1e-5, silu=True, scratch=self._gn_arena)
         if d["skip"] is not None:
             res = self._gemm(x, d["skip"], a2=skip)
         else:
@@ -216,7 +224,7 @@ class UNetEngine:
         h2t = self._to_pixels(h2, S)
         cur = h2t
         for i, (gn, wt) in enumerate(d["t"]):
-            a = ops.groupnorm(cur, *gn, rows_per_batch=Ff * HWt, eps=1e-5, silu=True, **self._gn5d_kw(S))
+            a = ops.groupnorm(cur, *gn, rows_per_batch=Ff * HWt, eps=1e-5, silu=True, scratch=self._gn_arena, **self._gn5d_kw(S))
             cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Ff, HWt, 1), residual=h2t if i == 3 else None)
         return to_frames(cur)
 
@@ -278,7 +286,7 @@ class UNetEngine:
 
     def _spatial(self, d, x, S):
         HW = S["H"] * S["W"]
-        a = ops.groupnorm(x, *d["gn"], rows_per_batch=HW, eps=1e-6, silu=False)
+        a = ops.groupnorm(x, *d["gn"], rows_per_batch=HW, eps=1e-6, silu=False, scratch=self._gn_arena)
         h = self._gemm(a, d["pin"])
         C = d["heads"] * self.head_dim
         kvall = S["kv_all"]
@@ -290,7 +298,7 @@ class UNetEngine:
     def _temporal(self, d, x, S):
         Ff, HWt, to_frames = self._enter_temporal(S)
         xt = self._to_pixels(x, S)
-        a = ops.groupnorm(xt, *d["gn"], rows_per_batch=Ff * HWt, eps=1e-6, silu=False, **self._gn5d_kw(S))
+        a = ops.groupnorm(xt, *d["gn"], rows_per_batch=Ff * HWt, eps=1e-6, silu=False, scratch=self._gn_arena, **self._gn5d_kw(S))
         h = self._gemm(a, d["pin"])
         h = self._tblock(d["tb"], h, S, d["heads"], temporal=True, Fr=Ff, HW=HWt)
         return to_frames(self._gemm(h, d["pout"], residual=xt))
@@ -399,6 +407,15 @@ class UNetEngine:
 
     def _forward_impl(self, x32, t, ctx, cam, fps, concat):
         B, _, Fr, H, W = x32.shape
+        if self.fused_groupnorm:
+            # one arena per (B*F) size class, kept alive for the CUDA graphs that captured pointers into it
+            nb = B * Fr
+            arena = self._gn_arenas.get(nb)
+            if arena is None:
+                per_call = int(_lib_scratch_bytes(nb)) + 256
+                arena = self._gn_arenas[nb] = ops.GnArena(x32.device, 192 * per_call)   # 166 GroupNorms per forward
+            self._gn_arena = arena
+            arena.reset()                              # one memset per forward; every GroupNorm call takes a fresh region
         sh = self.shard
         if sh is not None:
             # every rank receives the full [B,C,F,h,w] latent (as the sampler holds it) and computes its F/P frames
@@ -424,7 +441,7 @@ class UNetEngine:
             h = self._run_block(blk, h, None, S)
         for blk in self.dec:
             h = self._run_block(blk, h, skips.pop(), S)
-        a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True)
+        a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True, scratch=self._gn_arena)
         if self.head_gemm is not None:
             o16 = self._gemm(a, self.head_gemm, mode=ops.CONV3X3, geom=(1, B * Fr, S["H"], S["W"]))
             out = ops.rows_to_ncfhw(o16, B, Fr, S["H"], S["W"], self.head_cout)

@@ -113,12 +113,35 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     return out
 
 
+class GnArena:
+    """Zero-initialised scratch for the single-launch GroupNorm: one region per call, bump-allocated; `reset()` zeroes
+    the arena (one memset) and rewinds -- call it once per forward, before the first GroupNorm."""
+
+    def __init__(self, device, nbytes: int = 8 << 20):
+        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        self.off = 0
+
+    def reset(self):
+        self.buf.zero_()
+        self.off = 0
+
+    def take(self, nbatch: int) -> int:
+        n = int(_lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch))
+        if self.off + n > self.buf.numel():
+            raise RuntimeError("GnArena exhausted: raise its size or call reset() once per forward")
+        p = self.buf.data_ptr() + self.off
+        self.off += (n + 255) // 256 * 256
+        return p
+
+
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
               silu: bool, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
-              stats: Optional[torch.Tensor] = None, reduce_fn=None, stat_rows: int = 0) -> torch.Tensor:
+              stats: Optional[torch.Tensor] = None, reduce_fn=None, stat_rows: int = 0,
+              scratch: Optional["GnArena"] = None) -> torch.Tensor:
     """GroupNorm(32) over [x1 | x2] rows, statistics per chunk of `rows_per_batch` rows, optional SiLU.
     `reduce_fn(stats)` (e.g. an all-reduce over pixel shards) runs between the statistics and apply kernels;
-    `stat_rows` is then the global number of rows per chunk."""
+    `stat_rows` is then the global number of rows per chunk.  With a `scratch` arena (and no reduction) the
+    single-launch kernel is used: statistics + in-kernel barrier + apply."""
     _rows(x1, "groupnorm x1")
     rows, C1 = x1.shape
     C2 = 0
@@ -128,12 +151,21 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
     nbatch = rows // rows_per_batch
     if nbatch * rows_per_batch != rows:
         raise ValueError("groupnorm: rows not divisible by rows_per_batch")
+    L = _lib.lib()
+    st = _stream()
+    if scratch is not None and reduce_fn is None:
+        if out is None:
+            out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
+        e0 = _prof_begin()
+        check(L.vmv_groupnorm_fused(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
+                                    rows_per_batch, nbatch, scratch.take(nbatch), gamma.data_ptr(), beta.data_ptr(),
+                                    float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_fused")
+        _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))
+        return out
     if stats is None:
         stats = torch.empty(nbatch * 64, dtype=torch.float64, device=x1.device)
     if out is None:
         out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
-    L = _lib.lib()
-    st = _stream()
     e0 = _prof_begin()
     check(L.vmv_groupnorm_stats(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
                                 rows_per_batch, nbatch, stats.data_ptr(), st), "vmv_groupnorm_stats")
