@@ -290,7 +290,9 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches)}
 
-    if rank == 0:
+    if rank == 0 and args.quick:
+        print(json.dumps(line), flush=True)
+    elif rank == 0:
         # ---- roofline leg: one instrumented (eager, per-launch CUDA events) CFG-batched forward
         pk = _peaks()
         model.enable_cuda_graphs(False)
@@ -318,6 +320,12 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         from videomv_b200.profiling import gemm_shape_times
         rows = gemm_shape_times(prof)
         dev_ms = sum(n * us for _, n, _, us in rows) / 1e3
+        if args.shapes_out:
+            with open(args.shapes_out, "w") as f:
+                f.write("| shape | n | us each | total ms | share | TFLOP/s |\n|---|---:|---:|---:|---:|---:|\n")
+                for desc, n, fl, us in sorted(rows, key=lambda r: -r[1] * r[3]):
+                    f.write(f"| {desc} | {n} | {us:.1f} | {n * us / 1e3:.3f} | {100 * n * us / (dev_ms * 1e3):.1f}% | {fl / us / 1e6:.0f} |\n")
+                f.write(f"gemm total {dev_ms:.3f} ms per B=2 forward ({len(rows)} distinct shapes)\n")
         achieved = g[1] / (dev_ms * 1e-3) / 1e12
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,STAGES,.> (tcgen05 CTA-pair GEMM / implicit conv family)",
                             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
@@ -396,6 +404,8 @@ def main():
     ap.add_argument("--no-graphs", action="store_true")
     ap.add_argument("--two-call", action="store_true", help="cond and uncond as two B=1 UNet calls (reference call pattern)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--shapes-out", default="", help="write the per-shape GEMM device-time table of the roofline leg here")
+    ap.add_argument("--quick", action="store_true", help="A/B runs: value + e2e only (no roofline leg, no cpu baseline)")
     ap.add_argument("--parallel", default="replicas", choices=["replicas", "frames"],
                     help="N>1: 'replicas' = one independent sample per GPU (weak scaling, the reference's own mode); "
                          "'frames' = ONE sample, its 24 frames sharded over the GPUs (strong scaling, BASELINE config 5)")

@@ -75,6 +75,9 @@ typedef struct vmv_gemm_params {
     int32_t stages;             /* smem pipeline depth */
     int32_t split_k;            /* >1: K split across CTAs, fp32 partials in workspace, reduced by a 2nd kernel */
     int32_t variant;            /* 0 auto | 1 one tile per CTA (cta_group::1) | 2 persistent CTA pairs (cta_group::2) */
+    int32_t w_static;           /* != 0: W is not written by any earlier work of this stream that may still be in flight
+                                 * (model weights), so the kernel may fetch its first W tiles BEFORE it waits for the
+                                 * previous kernel (programmatic dependent launch); 0 = W is ordered like A */
     void* workspace; int64_t workspace_bytes;
 } vmv_gemm_params;
 

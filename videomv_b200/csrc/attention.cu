@@ -65,6 +65,8 @@ attention_kernel(const vmv_attn_params p) {
     const __half* vp = static_cast<const __half*>(p.v) + kbo * p.v_bs_outer + bi * p.v_bs_inner + h * HD;
     __half* op = static_cast<__half*>(p.o) + bo * p.o_bs_outer + bi * p.o_bs_inner + h * HD;
     const int q0 = qt * BR;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- stage Q (once) and the first K/V chunk
     for (int i = tid; i < BR * 8; i += NT) {
@@ -249,10 +251,10 @@ extern "C" int vmv_attention(const vmv_attn_params* p, void* stream) {
     }
     if (p->nq <= 32 && p->nk <= 32) {
         dim3 grid((p->nq + 31) / 32, p->heads, (unsigned)nb);
-        attention_kernel<2, 32><<<grid, 64, 0, st>>>(*p);
+        launch_kernel(attention_kernel<2, 32>, grid, dim3(64), 0, st, *p);
     } else {
         dim3 grid((p->nq + 63) / 64, p->heads, (unsigned)nb);
-        attention_kernel<4, 64><<<grid, 128, 0, st>>>(*p);
+        launch_kernel(attention_kernel<4, 64>, grid, dim3(128), 0, st, *p);
     }
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_attention");

@@ -99,6 +99,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();                                  // prologue done: let the next kernel start its own
+    pdl_wait();                                               // Q/K/V come from the previous kernel
 
     if (warp == 0) {
         if (lane == 0) {
@@ -322,7 +324,7 @@ int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
         cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
     }
     const int grid = a.ntiles < num_sms ? a.ntiles : num_sms;   // persistent: one CTA per SM (176 KiB smem, 512 TMEM columns)
-    attention_tc_kernel<<<grid, AT_THREADS, AT_SMEM, st>>>(tq, tk, tv, a);
+    launch_kernel(attention_tc_kernel, dim3(grid), dim3(AT_THREADS), AT_SMEM, st, tq, tk, tv, a);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_attention (tcgen05)");
     return VMV_OK;

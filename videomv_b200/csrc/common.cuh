@@ -34,6 +34,37 @@ void set_error(const char* fmt, ...);   // api.cu: stores the message for vmv_la
     } while (0)
 
 // ----------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  Every kernel of the library is launched through launch_kernel(), which sets
+// cudaLaunchAttributeProgrammaticStreamSerialization (unless VMV_PDL=0), and every kernel executes
+//     pdl_launch_dependents();  pdl_wait();
+// after its shared-memory-only prologue and BEFORE its first global-memory access to anything another kernel writes
+// or reads.  The next kernel of the stream / CUDA graph is therefore scheduled, made resident and through its own
+// prologue (barrier init, TMEM allocation, descriptor prefetch, weight-tile prefetch) while this one still runs, and
+// blocks in griddepcontrol.wait until this grid has completed and its writes are visible.  Ordering is transitive
+// because every kernel waits before it exits; without the launch attribute both instructions are no-ops.
+// ----------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();   // misc.cu: VMV_PDL != "0"
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                 Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ----------------------------------------------------------------------------
 // small math
 // ----------------------------------------------------------------------------
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.0f + __expf(-x)); }   // 2 MUFU + 2 FP ops
@@ -59,6 +90,26 @@ __device__ __forceinline__ float erf_as_f(float x) {
     return copysignf(e, x);
 }
 __device__ __forceinline__ float gelu_erf_f(float x) { return 0.5f * x * (1.0f + erf_as_f(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float rcp_approx_f(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// value * GELU_erf(gate) for the GEGLU epilogue (util.py:543-550), same Abramowitz-Stegun 7.1.26 erf as erf_as_f with the
+// argument scaling, the sign handling and the 0.5*(1+erf) folded in: 5 FMUL + 7 FFMA + 2 MUFU per output (the epilogue
+// of the K <= 640 GEGLU GEMMs is instruction-issue bound).
+//   erf(|g|/sqrt2) = 1 - (p(t) t) exp(-g^2/2),  t = 1/(1 + 0.3275911 |g|/sqrt2);   gelu(g) = g/2 + |g/2| erf(|g|/sqrt2)
+__device__ __forceinline__ float geglu_f(float val, float gate) {
+    const float h = 0.5f * gate;
+    const float t = rcp_approx_f(fmaf(fabsf(gate), 0.3275911f * 0.70710678118654752440f, 1.0f));
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float E = ex2_approx_f(gate * (gate * -0.72134752044448170368f));    // exp(-gate^2 / 2)
+    const float e = fmaf(-(p * t), E, 1.0f);
+    return val * fmaf(fabsf(h), e, h);
+}
 
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
@@ -71,6 +122,11 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// 128-bit shared-memory load by 32-bit shared address (pointers derived from the manually aligned dynamic smem base lose
+// their address space and would compile to scalar generic LD.E)
+__device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
 }
 
 __device__ __forceinline__ bool elect_one() {

@@ -54,6 +54,7 @@ struct GemmArgs {
     const float* ln_colsum;   // folded LayerNorm: per-column sum of the gamma-scaled weights
     int dbg;          // profiling experiments (VMV_GEMM_DEBUG): 1 = skip the TMA stores, 2 = skip the whole epilogue body
     int fast_epi;     // v2: register epilogue with 256-bit global accesses (needs 32 B aligned D / residual / rowbias rows)
+    int w_static;     // W may be fetched ahead of the programmatic-dependent-launch wait (model weights)
 };
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
@@ -298,6 +299,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -459,11 +462,33 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // Programmatic dependent launch: the prologue above ran while the previous kernel was still draining.  Everything
+    // that touches activations waits here; only the producer thread goes on first, to put the W tiles of its first
+    // pipeline stages in flight (weights are not produced by the previous kernel) before it waits as well.
+    pdl_launch_dependents();
+    const bool is_producer = warp == 0 && lane == 0;
+    if (!is_producer) pdl_wait();
 
     if (warp == 0) {
         if (lane == 0) {
             // ------------------------------ TMA producer (both CTAs) ------------------------------
             constexpr uint32_t tx_bytes = 2u * (A_STAGE_BYTES + L::B_STAGE_BYTES);
+            int pre = 0;                                    // stages whose barrier arrival + W load were issued pre-wait
+            if (a.w_static && !(a.dbg & 4) && cluster_id < total_tiles) {
+                const int split = cluster_id / tiles_mn;
+                const int nt = (cluster_id - split * tiles_mn) % n_tiles;
+                const int nt_cols = min(BN, a.N - nt * BN);
+                const int nrow = nt * BN + (int)rank * (nt_cols / 2);
+                const int kb_begin = split * a.kb_per_split;
+                const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
+                pre = min(STAGES, kb_end - kb_begin);
+                for (int i = 0; i < pre; ++i) {
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], tx_bytes);
+                    else mbar_arrive_remote(&full_bar[i], 0);
+                    tma_load_2d_2sm(smem + L::B_OFF + i * L::B_STAGE_BYTES, &tmW, &full_bar[i], (kb_begin + i) * BK, nrow);
+                }
+            }
+            pdl_wait();
             int it = 0;
             for (int t = cluster_id; t < total_tiles; t += num_clusters) {
                 const int split = t / tiles_mn;
@@ -492,14 +517,17 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    const bool prefetched = it < pre;      // first ring pass: arrival + W tile already issued
+                    if (!prefetched) mbar_wait(&empty_bar[s], ph ^ 1);
                     if (a.dbg & 4) {                       // experiment: no operand traffic, barrier protocol only
                         if (rank == 0) mbar_arrive(&full_bar[s]);
                         else mbar_arrive_remote(&full_bar[s], 0);
                         continue;
                     }
-                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
-                    else mbar_arrive_remote(&full_bar[s], 0);
+                    if (!prefetched) {
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                        else mbar_arrive_remote(&full_bar[s], 0);
+                    }
                     void* sa = smem + L::A_OFF + s * A_STAGE_BYTES;
                     void* sb = smem + L::B_OFF + s * L::B_STAGE_BYTES;
                     if (a.mode == VMV_GEMM_LINEAR) {
@@ -513,7 +541,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
                         tma_load_4d_2sm(sa, &tmA1, &full_bar[s], cb * BK, c1, c2 + tap - 1, c3);
                     }
-                    tma_load_2d_2sm(sb, &tmW, &full_bar[s], kb * BK, nrow);
+                    if (!prefetched) tma_load_2d_2sm(sb, &tmW, &full_bar[s], kb * BK, nrow);
                 }
             }
         }
@@ -594,7 +622,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         const int blk = hh + 2 * j;
                         const int n = geglu ? nt * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0 + blk * 32 + w;
                         sbias[i] = a.bias ? __ldg(a.bias + n) : 0.f;
-                        if (a.ln_colsum) scol[i] = __ldg(a.ln_colsum + n);
+                        scol[i] = a.ln_colsum ? __ldg(a.ln_colsum + n) : 0.f;
                     }
                 }
                 // (2) request the residual of my first block
@@ -610,10 +638,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 if (hh == 0) epilogue_store<BN>(a, nt, split, grow, valid, trow);     // split-K partials / unaligned outputs
             } else if (!(a.dbg & 2)) {
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
-                float2 ms = make_float2(0.f, 1.f);
-                const bool ln = a.ln_stats != nullptr && valid;
-                if (ln) ms = a.ln_stats[grow];
+                // folded LayerNorm as two FMAs per accumulator:  rstd*(acc - mean*colsum) + bias = acc*ln_a + (ln_b*colsum + bias)
+                const bool ln = a.ln_stats != nullptr;
+                float ln_a = 1.f, ln_b = 0.f;
+                if (ln && valid) {
+                    const float2 ms = a.ln_stats[grow];
+                    ln_a = ms.y;
+                    ln_b = -ms.y * ms.x;
+                }
                 const bool has_b = a.bias != nullptr;
+                const uint32_t sbias_a = smem_u32(sbias), scol_a = smem_u32(scol);
                 int j = 0;
 #pragma unroll 1
                 for (int blk = hh; blk < nvalid; blk += 2, ++j) {
@@ -627,17 +661,32 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         tmem_ld_32x32b_x16(trow + BN / 2 + c, *reinterpret_cast<uint32_t(*)[16]>(&g[0]));
                         tmem_ld_32x32b_x16(trow + BN / 2 + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&g[16]));
                         tmem_ld_wait();
-                        const float* bv = sbias + j * 64;
-                        const float* cv = scol + j * 64;
+                        const uint32_t bva = sbias_a + j * 256, cva = scol_a + j * 256;     // 64 floats per block pair
+                        if (ln) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float val = __uint_as_float(v[i]), gate = __uint_as_float(g[i]);
-                            if (ln) {
-                                val = ms.y * (val - ms.x * cv[i]);
-                                gate = ms.y * (gate - ms.x * cv[32 + i]);
+                            for (int i = 0; i < 32; i += 4) {
+                                float bv[4], bg[4], cv[4], cg[4];
+                                lds128(bva + i * 4, bv);
+                                lds128(bva + 128 + i * 4, bg);
+                                lds128(cva + i * 4, cv);
+                                lds128(cva + 128 + i * 4, cg);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) {
+                                    const float val = fmaf(__uint_as_float(v[i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                                    const float gate = fmaf(__uint_as_float(g[i + e]), ln_a, fmaf(ln_b, cg[e], bg[e]));
+                                    x[i + e] = geglu_f(val, gate);
+                                }
                             }
-                            if (has_b) { val += bv[i]; gate += bv[32 + i]; }
-                            x[i] = val * gelu_erf_f(gate);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float bv[4], bg[4];
+                                lds128(bva + i * 4, bv);             // zeros when there is no bias
+                                lds128(bva + 128 + i * 4, bg);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    x[i + e] = geglu_f(__uint_as_float(v[i + e]) + bv[e], __uint_as_float(g[i + e]) + bg[e]);
+                            }
                         }
                     } else {
                         tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -648,14 +697,28 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             ldg256(rb + col0 + c + 16, *reinterpret_cast<uint32_t(*)[8]>(&rbv[8]));
                         }
                         tmem_ld_wait();
-                        const float* bv = sbias + j * 32;
-                        const float* cv = scol + j * 32;
+                        const uint32_t bva = sbias_a + j * 128, cva = scol_a + j * 128;     // 32 floats per block
+                        if (ln) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            float val = __uint_as_float(v[i]);
-                            if (ln) val = ms.y * (val - ms.x * cv[i]);
-                            if (has_b) val += bv[i];
-                            x[i] = val;
+                            for (int i = 0; i < 32; i += 4) {
+                                float bv[4], cv[4];
+                                lds128(bva + i * 4, bv);
+                                lds128(cva + i * 4, cv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e)
+                                    x[i + e] = fmaf(__uint_as_float(v[i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                            }
+                        } else if (has_b) {
+#pragma unroll
+                            for (int i = 0; i < 32; i += 4) {
+                                float bv[4];
+                                lds128(bva + i * 4, bv);
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[i + e] = __uint_as_float(v[i + e]) + bv[e];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
                         }
                         if (rb) {
 #pragma unroll
@@ -708,6 +771,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 
 // Reduce split-K partials and apply the (non-GEGLU) epilogue.  One thread per 8 output columns.
 __global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int M, int N, GemmArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int nvec = N / 8;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long long)M * nvec) return;
@@ -819,7 +884,7 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
         }
         attr_set = true;
     }
-    gemm_tc_kernel<BN, STAGES><<<grid, 192, L::DYN_BYTES, st>>>(tA1, tA2, tW, a);
+    launch_kernel(gemm_tc_kernel<BN, STAGES>, grid, dim3(192), L::DYN_BYTES, st, tA1, tA2, tW, a);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm");
     return VMV_OK;
@@ -849,7 +914,8 @@ static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, cons
     const long long total = (long long)m_pairs * n_tiles * splits;
     int clusters = num_sms / 2;
     if (total < clusters) clusters = (int)total;
-    gemm_tc2_kernel<BN, STAGES, NBLK><<<dim3(2 * clusters), V2_THREADS, L::DYN_BYTES, st>>>(tA1, tA2, tW, a, m_pairs, n_tiles, splits);
+    launch_kernel(gemm_tc2_kernel<BN, STAGES, NBLK>, dim3(2 * clusters), dim3(V2_THREADS), L::DYN_BYTES, st, tA1, tA2, tW, a, m_pairs,
+                  n_tiles, splits);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
     return VMV_OK;
@@ -910,6 +976,7 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     a.rows_per_group = p->rows_per_group > 0 ? p->rows_per_group : 1;
     a.residual = static_cast<const __half*>(p->residual);
     a.ldr = p->ldr;
+    a.w_static = p->w_static;
     {
         static int dbg = -1;
         if (dbg < 0) { const char* e = getenv("VMV_GEMM_DEBUG"); dbg = e ? atoi(e) : 0; }
@@ -1081,7 +1148,8 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
     if (pl.splits > 1) {
         const long long nthreads = (long long)p->M * (p->N / 8);
         const int tb = 256;
-        splitk_finish_kernel<<<(unsigned)((nthreads + tb - 1) / tb), tb, 0, st>>>(a.partial, pl.splits, p->M, p->N, a);
+        launch_kernel(splitk_finish_kernel, dim3((unsigned)((nthreads + tb - 1) / tb)), dim3(tb), 0, st, (const float*)a.partial, pl.splits,
+                      p->M, p->N, a);
         count_launch();
         VMV_CUDA_LAUNCH_CHECK("vmv_gemm split-K finish");
     }

@@ -5,6 +5,7 @@
 
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <atomic>
 
 namespace vmv {
@@ -23,10 +24,20 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+bool pdl_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("VMV_PDL");       // VMV_PDL=0: plain stream-ordered launches (A/B switch)
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 __global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int cv, uint4* __restrict__ out,
                                   long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i % cv);
@@ -40,6 +51,8 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, int H, int W, int
 // out[(n,oh,ow), (ky,kx,c)] = x[n, 2*oh+ky-1, 2*ow+kx-1, c]  (zero outside)
 __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int H, int W, int cv, uint4* __restrict__ out,
                                  long long total) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= total) return;
     const int c = (int)(i % cv);
@@ -73,6 +86,8 @@ conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict_
         const int k = i / Cout, co = i % Cout;          // k = (ci*3 + ky)*3 + kx, matching w[co][ci][ky][kx]
         sw[i] = w[(long long)co * K + k];
     }
+    pdl_launch_dependents();                // the weights above are static: staged while the previous kernel drains
+    pdl_wait();
     for (int i = threadIdx.x; i < IN_PIX * K; i += blockDim.x) {
         const int p = i / K, k = i % K;
         const long long pix = pix0 + p;
@@ -125,6 +140,8 @@ conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int
         const int co = i % COUT, c = (i / COUT) % C, tap = i / (COUT * C);
         sm[i] = w[((long long)co * C + c) * 9 + tap];
     }
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long npix = (long long)B * F * H * W;
@@ -173,6 +190,8 @@ conv3x3_out_kernel(const __half* __restrict__ x, int B, int F, int H, int W, int
 // [M, ld] fp16 rows (first Cout columns valid) -> fp32 NCFHW [B,Cout,F,H,W]   (head conv output, unet_t2v.py:368)
 __global__ void rows_to_ncfhw_kernel(const __half* __restrict__ x, long long ld, int B, int F, long long HW, int Cout,
                                      float* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // over B*Cout*F*HW outputs
     const long long total = (long long)B * Cout * F * HW;
     if (i >= total) return;
@@ -184,6 +203,8 @@ __global__ void rows_to_ncfhw_kernel(const __half* __restrict__ x, long long ld,
 }
 
 __global__ void sinusoidal_kernel(const long long* __restrict__ t, int B, int dim, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int half_dim = dim / 2;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * half_dim) return;
@@ -198,6 +219,8 @@ __global__ void sinusoidal_kernel(const long long* __restrict__ t, int B, int di
 
 __global__ void embed_combine_silu_kernel(const __half* __restrict__ te, const __half* __restrict__ te2,
                                           const __half* __restrict__ cam, int B, int F, int E, __half* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * F * E) return;
     const int e = (int)(i % E);
@@ -211,6 +234,8 @@ __global__ void embed_combine_silu_kernel(const __half* __restrict__ te, const _
 
 __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __restrict__ y, const float* __restrict__ u,
                                 const float* __restrict__ coef, long long n, float* __restrict__ xprev) {
+    pdl_launch_dependents();
+    pdl_wait();
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float kx = coef[0], ko = coef[1], c_recip = coef[2], c_recipm1 = coef[3], sa_prev = coef[4],
@@ -227,7 +252,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
 using namespace vmv;
 
 extern "C" const char* vmv_last_error(void) { return g_err; }
-extern "C" int vmv_abi_version(void) { return 2; }
+extern "C" int vmv_abi_version(void) { return 3; }
 extern "C" long long vmv_launch_count(void) { return g_launches.load(); }
 extern "C" int vmv_sizeof_gemm_params(void) { return (int)sizeof(vmv_gemm_params); }
 extern "C" int vmv_sizeof_attn_params(void) { return (int)sizeof(vmv_attn_params); }
@@ -235,7 +260,7 @@ extern "C" int vmv_sizeof_attn_params(void) { return (int)sizeof(vmv_attn_params
 extern "C" int vmv_upsample_nearest2x(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
     VMV_CHECK_ARG(x && out && n > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, "vmv_upsample_nearest2x: bad args");
     const long long total = (long long)n * 4 * H * W * (C / 8);
-    upsample2x_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(upsample2x_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const uint4*>(x), H, W, C / 8, static_cast<uint4*>(out), total);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_upsample_nearest2x");
@@ -245,7 +270,7 @@ extern "C" int vmv_upsample_nearest2x(const void* x, int32_t n, int32_t H, int32
 extern "C" int vmv_im2col_3x3_s2(const void* x, int32_t n, int32_t H, int32_t W, int32_t C, void* out, void* stream) {
     VMV_CHECK_ARG(x && out && n > 0 && H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && C % 8 == 0, "vmv_im2col_3x3_s2: bad args");
     const long long total = (long long)n * (H / 2) * (W / 2) * 9 * (C / 8);
-    im2col_s2_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(im2col_s2_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const uint4*>(x), H, W, C / 8, static_cast<uint4*>(out), total);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_im2col_3x3_s2");
@@ -265,7 +290,7 @@ extern "C" int vmv_conv3x3_in(const float* x1, int32_t C1, const float* x2, int3
         if (e != cudaSuccess) { set_error("vmv_conv3x3_in: smem attribute: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
         smem_set = smem;
     }
-    conv3x3_in_kernel<<<(unsigned)((npix + IN_PIX - 1) / IN_PIX), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(conv3x3_in_kernel, dim3((unsigned)((npix + IN_PIX - 1) / IN_PIX)), dim3(256), smem, static_cast<cudaStream_t>(stream),
         x1, C1, x2, C2, B, F, H, W, w, bias, Cout, static_cast<__half*>(out));
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_in");
@@ -285,7 +310,7 @@ extern "C" int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, i
         smem_set = smem;
     }
     const int pix_per_cta = 8 * OUT_PIX_PER_WARP;
-    conv3x3_out_kernel<4><<<(unsigned)((npix + pix_per_cta - 1) / pix_per_cta), 256, smem, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(conv3x3_out_kernel<4>, dim3((unsigned)((npix + pix_per_cta - 1) / pix_per_cta)), dim3(256), smem, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(x), B, F, H, W, C, w, bias, out);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_out");
@@ -296,7 +321,7 @@ extern "C" int vmv_rows_to_ncfhw(const void* x, int64_t ldx, int32_t B, int32_t 
                                  float* out, void* stream) {
     VMV_CHECK_ARG(x && out && B > 0 && F > 0 && H > 0 && W > 0 && Cout > 0 && ldx >= Cout, "vmv_rows_to_ncfhw: bad args");
     const long long total = (long long)B * Cout * F * H * W;
-    rows_to_ncfhw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(rows_to_ncfhw_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(x), ldx, B, F, (long long)H * W, Cout, out);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_rows_to_ncfhw");
@@ -306,7 +331,7 @@ extern "C" int vmv_rows_to_ncfhw(const void* x, int64_t ldx, int32_t B, int32_t 
 extern "C" int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out, void* stream) {
     VMV_CHECK_ARG(t && out && B > 0 && dim > 0 && dim % 2 == 0, "vmv_sinusoidal_embedding: bad args");
     const int total = B * (dim / 2);
-    sinusoidal_kernel<<<(total + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(sinusoidal_kernel, dim3((total + 127) / 128), dim3(128), 0, static_cast<cudaStream_t>(stream),
         reinterpret_cast<const long long*>(t), B, dim, static_cast<__half*>(out));
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_sinusoidal_embedding");
@@ -317,7 +342,7 @@ extern "C" int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, con
                                       int32_t E, void* out, void* stream) {
     VMV_CHECK_ARG(t_emb && out && B > 0 && F > 0 && E > 0, "vmv_embed_combine_silu: bad args");
     const long long total = (long long)B * F * E;
-    embed_combine_silu_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+    launch_kernel(embed_combine_silu_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
         static_cast<const __half*>(t_emb), static_cast<const __half*>(t_emb2), static_cast<const __half*>(cam_emb), B,
         F, E, static_cast<__half*>(out));
     count_launch();
@@ -328,7 +353,8 @@ extern "C" int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, con
 extern "C" int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef7, int64_t n,
                                  float* x_prev, void* stream) {
     VMV_CHECK_ARG(xt && y_out && u_out && coef7 && x_prev && n > 0, "vmv_cfg_ddim_step: bad args");
-    cfg_ddim_kernel<<<(unsigned)((n + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(xt, y_out, u_out, coef7, n, x_prev);
+    launch_kernel(cfg_ddim_kernel, dim3((unsigned)((n + 255) / 256)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+        xt, y_out, u_out, coef7, n, x_prev);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_cfg_ddim_step");
     return VMV_OK;

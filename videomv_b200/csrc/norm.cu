@@ -52,6 +52,8 @@ gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
     const int t = threadIdx.x;
     if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     const int batch = blockIdx.y;
     const int tx = t % vw, ty = t / vw;
@@ -120,6 +122,8 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     const int t = threadIdx.x;
     const int batch = blockIdx.y;
     const int cpg = C / GN_GROUPS;
+    pdl_launch_dependents();
+    pdl_wait();
     if (t < GN_GROUPS) {
         const double inv_cnt = 1.0 / ((double)stat_rows * cpg);   // stat_rows > rows_per_batch: stats all-reduced over shards
         const double mean = stats[((long long)batch * GN_GROUPS + t) * 2] * inv_cnt;
@@ -183,6 +187,8 @@ gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
     const int t = threadIdx.x;
     if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
+    pdl_launch_dependents();
+    pdl_wait();
     __syncthreads();
     const int batch = blockIdx.y;
     const int tx = t % vw, ty = t / vw;
@@ -302,6 +308,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const __half* __restrict__ x, long long ldx, long long M, int C, const float* __restrict__ gamma,
                  const float* __restrict__ beta, float eps, __half* __restrict__ out, long long ldo) {
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= M) return;
     const int nvec = C / 8;
@@ -364,6 +372,8 @@ template <int NV, int ROWS>
 __global__ void __launch_bounds__(256)
 layernorm_stats_kernel(const __half* __restrict__ x, long long ldx, long long M, int C, float eps, float2* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
+    pdl_wait();
     const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS;
     if (row0 >= M) return;
     const int nvec = C / 8;
@@ -420,7 +430,7 @@ extern "C" int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const __half* xp = static_cast<const __half*>(x);
     float2* sp = static_cast<float2*>(stats);
-#define VMV_LNS(NV_, R_) layernorm_stats_kernel<NV_, R_><<<(unsigned)((M + wpb * R_ - 1) / (wpb * R_)), wpb * 32, 0, st>>>(xp, ldx, M, C, eps, sp)
+#define VMV_LNS(NV_, R_) launch_kernel(layernorm_stats_kernel<NV_, R_>, dim3((unsigned)((M + wpb * R_ - 1) / (wpb * R_))), dim3(wpb * 32), 0, st, xp, ldx, M, C, eps, sp)
     if (nv <= 1) VMV_LNS(1, 4);
     else if (nv == 2) VMV_LNS(2, 4);
     else if (nv == 3) VMV_LNS(3, 2);
@@ -451,7 +461,7 @@ extern "C" int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, con
     if (e != cudaSuccess) { set_error("vmv_groupnorm_stats: memset failed: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
     GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch);
     dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
-    gn_stats_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+    launch_kernel(gn_stats_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
                                                  g.rows_per_cta, g.vw, g.lanes, stats);
     count_launch();
@@ -469,7 +479,7 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch);
     dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
-    gn_apply_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+    launch_kernel(gn_apply_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
                                                  stat_rows > 0 ? stat_rows : rows_per_batch, g.rows_per_cta, g.vw,
                                                  g.lanes, stats, gamma, beta, eps, silu,
@@ -509,7 +519,7 @@ extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, con
     }
     double* stats = static_cast<double*>(scratch);
     unsigned int* arrive = reinterpret_cast<unsigned int*>(stats + (size_t)nbatch * 2 * GN_GROUPS);
-    gn_fused_kernel<<<grid, GN_THREADS, 0, st>>>(static_cast<const __half*>(x1), ldx1, C1,
+    launch_kernel(gn_fused_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
                                                  g.rows_per_cta, g.vw, g.lanes, stats, arrive, gamma, beta, eps, silu,
                                                  static_cast<__half*>(out), ldo);
@@ -525,7 +535,7 @@ extern "C" int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, c
     VMV_CHECK_ARG(ldx % 8 == 0 && ldo % 8 == 0 && M > 0, "vmv_layernorm: bad ld/M");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int wpb = 8;
-    layernorm_kernel<<<(unsigned)((M + wpb - 1) / wpb), wpb * 32, 0, st>>>(
+    launch_kernel(layernorm_kernel, dim3((unsigned)((M + wpb - 1) / wpb)), dim3(wpb * 32), 0, st,
         static_cast<const __half*>(x), ldx, M, C, gamma, beta, eps, static_cast<__half*>(out), ldo);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_layernorm");

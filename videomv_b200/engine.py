@@ -202,7 +202,9 @@ class UNetEngine:
                 if self._ws is None or self._ws.numel() < need:
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 kw["workspace"] = self._ws
-        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, ln_colsum=w.colsum if "ln_stats" in kw else None, **kw)
+        # w_static: every W here is a packed model weight, so the kernel may prefetch W tiles ahead of its PDL wait
+        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, ln_colsum=w.colsum if "ln_stats" in kw else None,
+                        w_static=True, **kw)
 
     # ------------------------------------------------------------------------------------------------------------
     # blocks

@@ -55,7 +55,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
          workspace: Optional[torch.Tensor] = None, variant: int = 0, ln_stats: Optional[torch.Tensor] = None,
-         ln_colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+         ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -94,6 +94,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
             raise ValueError("gemm ln_stats must be fp32 [M,2] and ln_colsum fp32 [N]")
         p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
     p.act, p.block_n, p.stages, p.split_k, p.variant = act, block_n, stages, split_k, variant
+    p.w_static = 1 if w_static else 0
     if split_k > 1:
         need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
         if need < 0:
