@@ -19,6 +19,9 @@ def _r(*shape, scale=1.0, seed=0, shift=0.0):
     (24, 1024, 320, 0, 1e-5, True), (1, 24 * 1024, 320, 0, 1e-6, False), (24, 256, 1280, 640, 1e-5, True),
     (2, 24 * 16, 1280, 0, 1e-5, True), (24, 16, 1280, 1280, 1e-5, True), (4, 256, 64, 0, 1e-5, True),
     (24, 64, 1280, 640, 1e-5, True), (4, 64, 128, 64, 1e-6, False), (48, 1024, 640, 320, 1e-5, True),
+    # smem-resident single-pass kernel at its capacity limit (213 / 214 KB per CTA), odd row counts, more chunks than SMs
+    (2, 24 * 1024, 320, 0, 1e-5, True), (48, 1024, 320, 0, 1e-5, True), (3, 1000, 320, 0, 1e-5, True),
+    (160, 16, 64, 0, 1e-5, True), (48, 16, 1280, 0, 1e-5, True), (2, 24 * 64, 1280, 0, 1e-6, False),
 ])
 @pytest.mark.parametrize("fused", [False, True], ids=["split", "fused"])
 def test_groupnorm(nb, rows, C1, C2, eps, silu, fused):
@@ -41,6 +44,23 @@ def test_groupnorm(nb, rows, C1, C2, eps, silu, fused):
         if C2 == 0:
             out2 = ops.groupnorm(x1, gamma, beta, rows_per_batch=rows, eps=eps, silu=silu, out=x1, scratch=arena)
             assert_close(f"groupnorm in-place nb{nb} rows{rows} C{C1}", out2, ref)
+
+
+def test_groupnorm_strided_views():
+    """Column slices of wider tensors as inputs / output (row stride != C): the smem kernel copies row by row."""
+    from videomv_b200 import ops
+    nb, rows, C1, C2 = 24, 256, 320, 192
+    big1, big2 = _r(nb * rows, C1 + 64, seed=1, shift=0.4), _r(nb * rows, C2 + 128, seed=2)
+    x1, x2 = big1[:, 64:], big2[:, :C2]
+    C = C1 + C2
+    gamma, beta = 1 + 0.1 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
+    big_out = torch.zeros(nb * rows, C + 32, dtype=torch.float16, device="cuda")
+    arena = ops.GnArena("cuda", 1 << 20)
+    ops.groupnorm(x1, gamma, beta, rows_per_batch=rows, eps=1e-5, silu=True, x2=x2, out=big_out[:, 32:], scratch=arena)
+    x = torch.cat([x1, x2], 1).float().reshape(nb, rows, C).permute(0, 2, 1)
+    ref = F.silu(F.group_norm(x, 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(nb * rows, C)
+    assert_close("groupnorm strided", big_out[:, 32:], ref)
+    assert (big_out[:, :32] == 0).all()
 
 
 @pytest.mark.parametrize("M,C", [(24576, 320), (6144, 640), (1536, 1280), (100, 512), (7, 64), (33, 2048)])

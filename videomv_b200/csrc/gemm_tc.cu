@@ -649,11 +649,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const bool has_b = a.bias != nullptr;
                 const uint32_t sbias_a = smem_u32(sbias), scol_a = smem_u32(scol);
                 int j = 0;
+                // The accumulators of block i+2 are requested from TMEM as soon as block i's have been consumed into x[],
+                // so the tcgen05.ld latency overlaps the residual / activation / pack / store part (VMV_GEMM_DEBUG 16: off).
+                const bool ld_ahead = !(a.dbg & 16);
+                bool requested = false;
+                uint32_t v[32];
 #pragma unroll 1
                 for (int blk = hh; blk < nvalid; blk += 2, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
                     float x[32];
-                    uint32_t v[32];
                     if (geglu) {
                         uint32_t g[32];
                         tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
@@ -689,8 +693,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             }
                         }
                     } else {
-                        tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                        tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                        if (!requested) {
+                            tmem_ld_32x32b_x16(trow + c, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                            tmem_ld_32x32b_x16(trow + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                        }
                         uint32_t rbv[16];
                         if (rb) {
                             ldg256(rb + col0 + c, *reinterpret_cast<uint32_t(*)[8]>(&rbv[0]));
@@ -719,6 +725,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         } else {
 #pragma unroll
                             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
+                        }
+                        requested = ld_ahead && blk + 2 < nvalid;
+                        if (requested) {
+                            tmem_ld_32x32b_x16(trow + c + 2 * EPI_BLK_COLS, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                            tmem_ld_32x32b_x16(trow + c + 2 * EPI_BLK_COLS + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                         }
                         if (rb) {
 #pragma unroll

@@ -4,6 +4,8 @@
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
+#include <stdlib.h>
+
 namespace vmv {
 
 void count_launch(int n = 1);
@@ -183,7 +185,9 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
                 int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats,
                 unsigned int* __restrict__ arrive, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int silu, __half* __restrict__ out, long long ldo) {
+                float eps, int silu, __half* __restrict__ out, long long ldo, int opt) {
+    // opt (VMV_GN_OPT, experiments): 1 = nanosleep back-off in the barrier spin; timing-only (wrong results):
+    // 4 = do not wait at the barrier, 8 = skip the apply phase, 16 = skip the global statistics atomics
     __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
     const int t = threadIdx.x;
     if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
@@ -239,7 +243,7 @@ gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     __syncthreads();
     if (t < GN_GROUPS) {
         float a = s_sum[t], b = s_sq[t];
-        if (a != 0.f || b != 0.f) {
+        if ((a != 0.f || b != 0.f) && !(opt & 16)) {
             atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)a);
             atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)b);
         }
@@ -255,9 +259,12 @@ gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive + batch) : "memory");
             if (++spins > (1u << 26)) __trap();               // co-residency was checked on the host; never a silent hang
+            if (opt & 4) break;
+            if ((opt & 1) && seen < expected) __nanosleep(100);
         } while (seen < expected);
     }
     __syncthreads();
+    if (opt & 8) return;
     // ---- phase 2: normalise; x is re-read (L2) -- not through the non-coherent path, `out` may alias x
     if (t < GN_GROUPS) {
         const double inv_cnt = 1.0 / ((double)rows_per_batch * cpg);
@@ -300,6 +307,171 @@ gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
         apply(u0, r); apply(u1, r + lanes); apply(u2, r + 2LL * lanes); apply(u3, r + 3LL * lanes);
     }
     for (; r < r_end; r += lanes) apply(*gn_src(x1, ld1, C1, x2, ld2, base + r, c0), r);
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass GroupNorm: the CTA's rows are brought into shared memory ONCE with bulk async copies (one mbarrier, the
+// whole slab in flight at a time -- no per-thread load latency chain), statistics are taken from smem, the CTAs of a
+// chunk meet at the same arrival barrier as gn_fused_kernel, and the apply phase reads smem and writes global: HBM sees
+// one read and one write of the tensor.  One CTA per SM; a [49152, 320] level-0 activation is 213 KB per SM, just inside
+// the 227 KB a CTA may own, the lower levels are smaller.  Inputs that do not fit (the widest skip concatenations) use
+// gn_fused_kernel.  `stats` / `arrive` must be zero on entry.
+// ------------------------------------------------------------------------------------------------
+constexpr int GNS_THREADS = 512;
+constexpr int GNS_MAX_DYN_SMEM = 227 * 1024 - 2048;       // the kernel's static smem (barrier + 4 x 32 floats, 1.7 KB) comes on top
+constexpr int GNS_CHUNK_BYTES = 16384;
+
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(GNS_THREADS, 1)
+gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2, int C2,
+               long long rows_per_batch, int rows_per_cta, double* __restrict__ stats, unsigned int* __restrict__ arrive,
+               const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
+               __half* __restrict__ out, long long ldo) {
+    extern __shared__ __align__(128) uint8_t gsm[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS], s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    const int t = threadIdx.x;
+    const int C = C1 + C2;
+    const int batch = blockIdx.y;
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    long long left = rows_per_batch - r_begin;
+    const int nrows = left <= 0 ? 0 : (left < rows_per_cta ? (int)left : rows_per_cta);
+    const long long base_row = (long long)batch * rows_per_batch + r_begin;
+    if (t == 0) {
+        mbar_init(&bar, 1);
+        fence_barrier_init();
+    }
+    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
+    // ---- load: the whole slab in flight at once
+    if (t < 32) {
+        const uint32_t row_bytes = (uint32_t)C * 2u;
+        if (t == 0) mbar_arrive_expect_tx(&bar, (uint32_t)nrows * row_bytes);
+        __syncwarp();
+        if (C2 == 0 && ld1 == C1) {                      // rows are contiguous in memory: 16 KB chunks
+            const int chunk_rows = max(1, GNS_CHUNK_BYTES / (int)row_bytes);
+            const int nchunks = (nrows + chunk_rows - 1) / chunk_rows;
+            for (int i = t; i < nchunks; i += 32) {
+                const int r0 = i * chunk_rows;
+                const int n = min(chunk_rows, nrows - r0);
+                bulk_g2s(gsm + (size_t)r0 * row_bytes, x1 + (base_row + r0) * ld1, (uint32_t)n * row_bytes, &bar);
+            }
+        } else {                                         // strided and / or two sources: one or two copies per row
+            for (int r = t; r < nrows; r += 32) {
+                bulk_g2s(gsm + (size_t)r * row_bytes, x1 + (base_row + r) * ld1, (uint32_t)C1 * 2u, &bar);
+                if (C2) bulk_g2s(gsm + (size_t)r * row_bytes + (size_t)C1 * 2, x2 + (base_row + r) * ld2, (uint32_t)C2 * 2u, &bar);
+            }
+        }
+    }
+    mbar_wait(&bar, 0);
+    // ---- phase 1: statistics from smem.  Thread = one 8-channel vector x every `lanes`-th row.
+    const int vw = C / 8;
+    const int lanes = GNS_THREADS / vw;                  // >= 1: the host guarantees C <= 8 * GNS_THREADS
+    const int tx = t % vw, ty = t / vw;
+    const int c0 = tx * 8;
+    const int cpg = C / GN_GROUPS;
+    const bool active = ty < lanes;
+    const uint8_t* colp = gsm + (size_t)c0 * 2;
+    const size_t rstride = (size_t)C * 2;
+    if (active) {
+        float s[8], q[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+#pragma unroll 4
+        for (int r = ty; r < nrows; r += lanes) {
+            const uint4 u = *reinterpret_cast<const uint4*>(colp + r * rstride);
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float2 f = unpack_half2(w[j]);
+                s[2 * j] += f.x; q[2 * j] = fmaf(f.x, f.x, q[2 * j]);
+                s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
+            }
+        }
+        int g_prev = c0 / cpg;
+        float as = 0.f, aq = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int g = (c0 + j) / cpg;
+            if (g != g_prev) {
+                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+                as = 0.f; aq = 0.f; g_prev = g;
+            }
+            as += s[j]; aq += q[j];
+        }
+        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+    }
+    __syncthreads();
+    const unsigned int expected = gridDim.x;
+    if (expected > 1) {
+        if (t < GN_GROUPS) {
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)s_sum[t]);
+            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)s_sq[t]);
+            __threadfence();
+        }
+        __syncthreads();
+        if (t == 0) {
+            atomicAdd(&arrive[batch], 1u);
+            unsigned int seen, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive + batch) : "memory");
+                if (++spins > (1u << 26)) __trap();           // co-residency is guaranteed by the host; never a silent hang
+            } while (seen < expected);
+        }
+        __syncthreads();
+    }
+    if (t < GN_GROUPS) {
+        const double inv_cnt = 1.0 / ((double)rows_per_batch * cpg);
+        double sum, sq;
+        if (expected > 1) {
+            sum = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]);
+            sq = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]);
+        } else {                                             // the chunk is mine alone: no global round trip
+            sum = (double)s_sum[t];
+            sq = (double)s_sq[t];
+        }
+        const double mean = sum * inv_cnt;
+        double var = sq * inv_cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[t] = (float)mean;
+        s_rstd[t] = rsqrtf((float)var + eps);
+    }
+    __syncthreads();
+    if (!active) return;
+    // ---- phase 2: normalise from smem, write global
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int c = c0 + j;
+        const int g = c / cpg;
+        const float ga = __ldg(gamma + c) * s_rstd[g];
+        sc[j] = ga;
+        sh[j] = __ldg(beta + c) - s_mean[g] * ga;
+    }
+    __half* op = out + base_row * ldo + c0;
+#pragma unroll 4
+    for (int r = ty; r < nrows; r += lanes) {
+        const uint4 u = *reinterpret_cast<const uint4*>(colp + r * rstride);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_half2(w[j]);
+            float a = fmaf(f.x, sc[2 * j], sh[2 * j]);
+            float b = fmaf(f.y, sc[2 * j + 1], sh[2 * j + 1]);
+            if (silu) { a = silu_f(a); b = silu_f(b); }
+            o[j] = pack_half2(a, b);
+        }
+        *reinterpret_cast<uint4*>(op + r * ldo) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
 }
 
 // One warp per row; the row lives in registers (<= 8 vectors of 8 halfs per lane => C <= 2048).
@@ -489,6 +661,11 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
     return VMV_OK;
 }
 
+static int gn_opt() {
+    const char* e = getenv("VMV_GN_OPT");          // read per call: the micro-benchmark switches it between launches
+    return e ? atoi(e) : 0;
+}
+
 // Scratch for one fused call: nbatch*64 doubles (sums) followed by nbatch uint32 arrival counters, all zero on entry.
 extern "C" int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch) {
     return (int64_t)nbatch * 2 * GN_GROUPS * 8 + (((int64_t)nbatch * 4 + 7) / 8) * 8;
@@ -501,6 +678,40 @@ extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, con
     if (rc) return rc;
     VMV_CHECK_ARG(scratch && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_fused: bad scratch/gamma/beta/out");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
+    double* stats = static_cast<double*>(scratch);
+    unsigned int* arrive = reinterpret_cast<unsigned int*>(stats + (size_t)nbatch * 2 * GN_GROUPS);
+    {
+        // smem-resident single pass whenever one CTA per SM can hold the tensor (VMV_GN_SMEM=0: always the re-read kernel)
+        static int use_smem = -1, num_sms = 0;
+        if (use_smem < 0) {
+            const char* e = getenv("VMV_GN_SMEM");
+            use_smem = (e && e[0] == '0') ? 0 : 1;
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+            if (use_smem) {
+                cudaError_t e2 = cudaFuncSetAttribute(gn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNS_MAX_DYN_SMEM);
+                if (e2 != cudaSuccess) { set_error("vmv_groupnorm_fused: smem attribute: %s", cudaGetErrorString(e2)); return VMV_ERR_CUDA; }
+            }
+        }
+        const int C = C1 + C2;
+        const bool al16 = ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+        if (use_smem && al16 && C <= 8 * GNS_THREADS && nbatch <= num_sms) {
+            long long cpb = num_sms / nbatch;                      // CTAs per chunk; all CTAs co-resident at one per SM
+            if (cpb > rows_per_batch) cpb = rows_per_batch;
+            const long long rpc = (rows_per_batch + cpb - 1) / cpb;
+            cpb = (rows_per_batch + rpc - 1) / rpc;                // drop CTAs that would own no rows
+            const long long smem = rpc * C * 2;
+            if (smem <= GNS_MAX_DYN_SMEM) {
+                launch_kernel(gn_smem_kernel, dim3((unsigned)cpb, nbatch), dim3(GNS_THREADS), (size_t)smem, st,
+                              static_cast<const __half*>(x1), ldx1, C1, static_cast<const __half*>(x2), ldx2, C2, rows_per_batch,
+                              (int)rpc, stats, arrive, gamma, beta, eps, silu, static_cast<__half*>(out), ldo);
+                count_launch();
+                VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused (smem)");
+                return VMV_OK;
+            }
+        }
+    }
     static int capacity = 0;                                   // co-resident CTAs of gn_fused_kernel on this device
     if (capacity == 0) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -517,12 +728,10 @@ extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, con
                   "use vmv_groupnorm_stats + vmv_groupnorm_apply", grid.x * grid.y * grid.z, capacity);
         return VMV_ERR_UNSUPPORTED;
     }
-    double* stats = static_cast<double*>(scratch);
-    unsigned int* arrive = reinterpret_cast<unsigned int*>(stats + (size_t)nbatch * 2 * GN_GROUPS);
     launch_kernel(gn_fused_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
                                                  g.rows_per_cta, g.vw, g.lanes, stats, arrive, gamma, beta, eps, silu,
-                                                 static_cast<__half*>(out), ldo);
+                                                 static_cast<__half*>(out), ldo, gn_opt());
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused");
     return VMV_OK;
