@@ -70,6 +70,14 @@ typedef struct vmv_gemm_params {
      * W*gamma, bias holds bias + W@beta, and the epilogue computes  rstd[m]*(acc - mean[m]*ln_colsum[n]) + bias[n]
      * with ln_stats[m] = {mean, rstd} (vmv_layernorm_stats) and ln_colsum[n] = sum_k W'[n,k].  NULL = off. */
     const void* ln_stats; const float* ln_colsum;
+    /* ln_stats_raw_c != 0: ln_stats[m] holds the RAW row sums {sum_c x, sum_c x^2} over ln_stats_raw_c channels (as
+     * accumulated by an upstream vmv_gemm through rowstats_out) instead of {mean, rstd}; the epilogue converts them with
+     * ln_eps.  0 = ln_stats is {mean, rstd}. */
+    int32_t ln_stats_raw_c; float ln_eps;
+    /* rowstats_out != NULL: fp32 [M,2]; the epilogue ADDS {sum_n D[m,n], sum_n D[m,n]^2} of the final (pre-rounding)
+     * output row to it with atomics -- the LayerNorm statistics of the tensor this GEMM produces, for the next GEMM's
+     * folded LayerNorm.  Must be zero on entry.  CTA-pair kernel without split-K / GEGLU only (else VMV_ERR_UNSUPPORTED). */
+    void* rowstats_out;
     /* tuning (0 = auto) */
     int32_t block_n;            /* 64 (variant 1 only), 128, 160 or 256 */
     int32_t stages;             /* smem pipeline depth */

@@ -227,6 +227,36 @@ def test_dependent_launch_chain():
     assert rel2 < 2e-3, rel2                     # (GroupNorm statistics use atomics: not bit-exact run to run)
 
 
+@pytest.mark.parametrize("M,N,K", [(24576, 320, 320), (6144, 640, 2560), (1536, 1280, 1280), (1000, 512, 320), (130, 128, 64)])
+def test_rowstats_feed_folded_layernorm(M, N, K):
+    """rowstats_out: the producing GEMM accumulates {sum, sum of squares} of its output rows; the consuming GEMM folds the
+    LayerNorm from those raw sums (ln_raw_c).  Same result as nn.LayerNorm -> nn.Linear on the producer's fp16 output."""
+    from videomv_b200 import ops, packing
+    a, w = _r(M, K, seed=1), _r(N, K, scale=K ** -0.5, seed=2)
+    bias = torch.randn(N, device="cuda") + 0.4
+    res = _r(M, N, seed=3)
+    rs = torch.zeros(M, 2, device="cuda")
+    h = ops.gemm(a, w, bias=bias, residual=res, rowstats_out=rs, variant=2)
+    ref_h = a.float() @ w.float().t() + bias + res.float()
+    assert_close(f"rowstats producer M{M} N{N} K{K}", h, ref_h)
+    assert torch.allclose(rs[:, 0], ref_h.sum(1), rtol=1e-4, atol=2e-3)
+    assert torch.allclose(rs[:, 1], (ref_h * ref_h).sum(1), rtol=1e-4, atol=2e-3)
+    N2 = 384
+    w2 = torch.randn(N2, N, device="cuda") * N ** -0.5
+    b2 = torch.randn(N2, device="cuda")
+    gamma, beta = 1 + 0.2 * torch.randn(N, device="cuda"), 0.2 * torch.randn(N, device="cuda")
+    wg, bf = packing.fold_layernorm(w2, b2, gamma, beta)
+    wp = wg.half().contiguous()
+    colsum = wp.float().sum(1).contiguous()
+    out = ops.gemm(h, wp, bias=bf, ln_stats=rs, ln_colsum=colsum, ln_raw_c=N, ln_eps=1e-5, variant=2)
+    base = ops.gemm(h, wp, bias=bf, ln_stats=ops.layernorm_stats(h), ln_colsum=colsum, variant=2)
+    ref = F.linear(F.layer_norm(h.float(), (N,), gamma, beta, 1e-5), w2, b2)
+    assert_close(f"rowstats consumer M{M} N{N}", out, ref, rtol=2e-3, atol=2e-3)
+    assert_close(f"rowstats consumer vs stats kernel M{M} N{N}", out, base.float(), rtol=1e-3, atol=1e-3)
+    with pytest.raises(RuntimeError):
+        ops.gemm(a, w, rowstats_out=rs, variant=1)
+
+
 def test_bad_args_raise():
     from videomv_b200 import ops
     a, w = _r(128, 100), _r(64, 100)

@@ -75,6 +75,7 @@ class GemmParams(ctypes.Structure):
         ("B", c_i32), ("F", c_i32), ("H", c_i32), ("Wd", c_i32),
         ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
         ("residual", c_vp), ("ldr", c_i64), ("act", c_i32), ("ln_stats", c_vp), ("ln_colsum", c_vp),
+        ("ln_stats_raw_c", c_i32), ("ln_eps", c_f32), ("rowstats_out", c_vp),
         ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32), ("variant", c_i32), ("w_static", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
@@ -138,7 +139,7 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if L.vmv_abi_version() != 3:
+    if L.vmv_abi_version() != 4:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
     if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
             L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams)):

@@ -55,7 +55,21 @@ struct GemmArgs {
     int dbg;          // profiling experiments (VMV_GEMM_DEBUG): 1 = skip the TMA stores, 2 = skip the whole epilogue body
     int fast_epi;     // v2: register epilogue with 256-bit global accesses (needs 32 B aligned D / residual / rowbias rows)
     int w_static;     // W may be fetched ahead of the programmatic-dependent-launch wait (model weights)
+    int ln_raw_c;     // != 0: ln_stats holds raw {sum, sum of squares} over ln_raw_c channels (see ln_row_stats)
+    float ln_eps, ln_inv_c;
+    float* rowstats;  // fp32 [M,2]: += {sum, sum of squares} of every output row (v2 register epilogue only)
 };
+
+// Folded-LayerNorm row statistics {mean, rstd}: stored as such, or derived from the raw sums an upstream GEMM accumulated.
+__device__ __forceinline__ float2 ln_finish(const GemmArgs& a, float2 ms) {
+    if (a.ln_raw_c) {
+        const float mean = ms.x * a.ln_inv_c;
+        const float var = fmaxf(fmaf(ms.y, a.ln_inv_c, -mean * mean), 0.f);
+        ms = make_float2(mean, rsqrtf(var + a.ln_eps));
+    }
+    return ms;
+}
+__device__ __forceinline__ float2 ln_row_stats(const GemmArgs& a, long long row) { return ln_finish(a, a.ln_stats[row]); }
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
 __device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int mt, int r) {
@@ -146,7 +160,7 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& a, int nt, int sp
                 for (int j = 0; j < 16; ++j) {
                     float val = __uint_as_float(v[j]), gate = __uint_as_float(g[j]);
                     if (a.ln_stats) {
-                        const float2 ms = a.ln_stats[grow];
+                        const float2 ms = ln_row_stats(a, grow);
                         val = ms.y * (val - ms.x * __ldg(a.ln_colsum + n0 + c + j));
                         gate = ms.y * (gate - ms.x * __ldg(a.ln_colsum + n0 + HB + c + j));
                     }
@@ -192,7 +206,7 @@ __device__ __forceinline__ void epilogue_store(const GemmArgs& a, int nt, int sp
 #pragma unroll
                 for (int j = 0; j < 16; ++j) x[j] = __uint_as_float(v[j]);
                 if (a.ln_stats) {
-                    const float2 ms = a.ln_stats[grow];
+                    const float2 ms = ln_row_stats(a, grow);
 #pragma unroll
                     for (int j = 0; j < 16; ++j) x[j] = ms.y * (x[j] - ms.x * __ldg(a.ln_colsum + n + j));
                 }
@@ -594,6 +608,34 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         float* scol = sbias + 128;
         const bool geglu = a.act == VMV_ACT_GEGLU;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
+        // Bias / LayerNorm column sums of this warp's columns are fetched ONE TILE AHEAD into registers (<= 128 values per
+        // array per warp = 4 per lane) and only copied to the smem scratch at the top of their tile: when the epilogue is
+        // the bottleneck (K <= 640) the accumulator is already waiting, and a global-load -> smem-store chain at that point
+        // was the largest stall of the kernel (ncu source view, profiles/r2_ncu_hot_kernels_summary.md).
+        // (always staged -- zeros when a pointer is null -- so the math below never reads an unwritten slot)
+        const int per = geglu ? 64 : 32;
+        float nb[4] = {0.f, 0.f, 0.f, 0.f}, nc[4] = {0.f, 0.f, 0.f, 0.f};
+        auto fetch_cols = [&](int tt) {
+            if (tt >= total_tiles) return;
+            const int rem_ = tt % tiles_mn;
+            const int nt_ = rem_ % n_tiles;
+            const int col0_ = nt_ * out_bn;
+            int nvalid_ = min(out_bn / EPI_BLK_COLS, (a.n_out - col0_ + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
+            if (nvalid_ < 0) nvalid_ = 0;
+            const int cnt = ((nvalid_ - hh + 1) / 2) * per;
+#pragma unroll
+            for (int qq = 0; qq < 4; ++qq) {
+                const int i = lane + 32 * qq;
+                if (i < cnt) {
+                    const int j = i / per, w = i - j * per;
+                    const int blk = hh + 2 * j;
+                    const int n = geglu ? nt_ * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0_ + blk * 32 + w;
+                    nb[qq] = a.bias ? __ldg(a.bias + n) : 0.f;
+                    nc[qq] = a.ln_colsum ? __ldg(a.ln_colsum + n) : 0.f;
+                }
+            }
+        };
+        if (a.fast_epi) fetch_cols(cluster_id);
         int acc_it = 0;
         for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
             const int split = t / tiles_mn;
@@ -610,26 +652,26 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             if (nvalid < 0) nvalid = 0;
             const __half* resrow = (a.residual && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
             uint32_t rcur[16];
+            float2 ln_ms = make_float2(0.f, 1.f);
             if (a.fast_epi) {
-                // (1) stage this warp's bias / column-sum slices.  Slot j*32+i holds column (hh+2j)*32+i of the tile;
-                //     GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
+                // (1) this warp's bias / column-sum slices (fetched one tile ago) go to the smem scratch.  Slot j*32+i holds
+                //     column (hh+2j)*32+i of the tile; GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
                 __syncwarp();                                   // previous tile's readers are done with the scratch
-                const int nmine = (nvalid - hh + 1) / 2;
-                if (a.bias || a.ln_colsum) {
-                    const int per = geglu ? 64 : 32;
-                    for (int i = lane; i < nmine * per; i += 32) {
-                        const int j = i / per, w = i - j * per;
-                        const int blk = hh + 2 * j;
-                        const int n = geglu ? nt * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0 + blk * 32 + w;
-                        sbias[i] = a.bias ? __ldg(a.bias + n) : 0.f;
-                        scol[i] = a.ln_colsum ? __ldg(a.ln_colsum + n) : 0.f;
+                {
+                    const int cnt = ((nvalid - hh + 1) / 2) * per;
+#pragma unroll
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int i = lane + 32 * qq;
+                        if (i < cnt) { sbias[i] = nb[qq]; scol[i] = nc[qq]; }
                     }
                 }
-                // (2) request the residual of my first block
+                fetch_cols(t + num_clusters);                   // next tile's values: a whole tile of latency hiding
+                // (2) request the residual of my first block and my row's LayerNorm statistics
                 if (resrow && hh < nvalid) {
                     ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
                     ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                 }
+                if (a.ln_stats != nullptr && valid) ln_ms = a.ln_stats[grow];
                 __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
@@ -642,7 +684,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const bool ln = a.ln_stats != nullptr;
                 float ln_a = 1.f, ln_b = 0.f;
                 if (ln && valid) {
-                    const float2 ms = a.ln_stats[grow];
+                    const float2 ms = ln_finish(a, ln_ms);
                     ln_a = ms.y;
                     ln_b = -ms.y * ms.x;
                 }
@@ -654,6 +696,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const bool ld_ahead = !(a.dbg & 16);
                 bool requested = false;
                 uint32_t v[32];
+                float row_s = 0.f, row_q = 0.f;                 // LayerNorm sums of my row over my blocks (rowstats)
 #pragma unroll 1
                 for (int blk = hh; blk < nvalid; blk += 2, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
@@ -756,6 +799,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             ldg256(resrow + (blk + 2) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                         }
                     }
+                    if (a.rowstats) {
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) {
+                            row_s += x[i];
+                            row_q = fmaf(x[i], x[i], row_q);
+                        }
+                    }
                     if (valid && !(a.dbg & 1)) {
                         uint32_t o[16];
 #pragma unroll
@@ -764,6 +814,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         stg256(dst, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
                         stg256(dst + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
                     }
+                }
+                if (a.rowstats && valid && hh < nvalid) {
+                    atomicAdd(a.rowstats + 2 * grow, row_s);
+                    atomicAdd(a.rowstats + 2 * grow + 1, row_q);
                 }
             }
             tc_fence_before();
@@ -799,7 +853,7 @@ __global__ void splitk_finish_kernel(const float* __restrict__ partial, int spli
         x[4] += w.x; x[5] += w.y; x[6] += w.z; x[7] += w.w;
     }
     if (a.ln_stats) {
-        const float2 ms = a.ln_stats[row];
+        const float2 ms = ln_row_stats(a, row);
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = ms.y * (x[j] - ms.x * a.ln_colsum[n + j]);
     }
@@ -995,6 +1049,11 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     }
     a.ln_stats = static_cast<const float2*>(p->ln_stats);
     a.ln_colsum = p->ln_colsum;
+    a.ln_raw_c = p->ln_stats ? p->ln_stats_raw_c : 0;
+    a.ln_eps = p->ln_eps;
+    a.ln_inv_c = a.ln_raw_c > 0 ? 1.0f / (float)a.ln_raw_c : 0.f;
+    a.rowstats = static_cast<float*>(p->rowstats_out);
+    VMV_CHECK_ARG(a.ln_raw_c >= 0, "vmv_gemm: ln_stats_raw_c must be >= 0");
     VMV_CHECK_ARG((p->ln_stats == nullptr) == (p->ln_colsum == nullptr), "vmv_gemm: ln_stats and ln_colsum go together");
     if (p->rowbias) VMV_CHECK_ARG(p->ld_rowbias % 8 == 0, "vmv_gemm: ld_rowbias must be a multiple of 8");
     if (p->residual) VMV_CHECK_ARG(p->ldr % 8 == 0, "vmv_gemm: ldr must be a multiple of 8");
@@ -1133,10 +1192,19 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                                  al32(p->rowbias, p->ld_rowbias)
                              ? 1 : 0;
         }
+        if (a.rowstats && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
+            set_error("vmv_gemm: rowstats_out needs the CTA-pair kernel's register epilogue (no split-K, no GEGLU, N %% 32 == 0, "
+                      "32 B aligned rows)");
+            return VMV_ERR_UNSUPPORTED;
+        }
         if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
         else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
         else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
+        if (a.rowstats) {
+            set_error("vmv_gemm: rowstats_out is not available in the one-tile-per-CTA kernel (variant 1)");
+            return VMV_ERR_UNSUPPORTED;
+        }
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);
         // stage count: deep ring for one CTA/SM; the shallow ring leaves room for two co-resident CTAs so one
         // CTA's epilogue overlaps the other's main loop.

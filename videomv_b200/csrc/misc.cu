@@ -68,28 +68,32 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, int H, int W, int 
     out[i] = v;
 }
 
-// Input conv: tiny Cin (4 or 8), K = 9*Cin <= 72.  A CTA owns IN_PIX consecutive pixels of one frame row-major; the
-// weights live in smem transposed to [k][Cout] so a thread reads its 8 output channels as two 16B loads per k, and the
-// K input taps of a pixel are gathered once into smem and broadcast to the Cout/8 threads that share the pixel.
+// Input conv: tiny Cin (4 or 8), K = 9*Cin <= 72, fp32 in, fp32 accumulate.  A CTA owns IN_PIX consecutive pixels.
+//   * weights: read coalesced in the reference layout [Cout][K] and scattered to smem transposed [k][Cout], so a thread
+//     reads the 8 output channels it owns as two 16 B loads per k;
+//   * the K input taps of the CTA's pixels are gathered once into smem as [k][pixel], so 4 consecutive pixels are one
+//     16 B load;
+//   * a thread computes 4 pixels x 8 channels per work item: 3 LDS.128 per 32 FMAs (the 1 x 8 version was shared-memory
+//     bound: 200 us for the 24 x 32 x 32 x 4 -> 320 stem).
 constexpr int IN_PIX = 128;
 constexpr int IN_MAXK = 72;
 __global__ void __launch_bounds__(256)
 conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict__ x2, int C2, int B, int F, int H, int W,
                   const float* __restrict__ w, const float* __restrict__ bias, int Cout, __half* __restrict__ out) {
-    extern __shared__ float sm[];
+    extern __shared__ __align__(16) float sm[];
     const int Cin = C1 + C2, K = 9 * Cin;
     float* sw = sm;                         // [K][Cout]
-    float* sx = sm + K * Cout;              // [IN_PIX][K]
+    float* sx = sm + K * Cout;              // [K][IN_PIX]
     const long long npix = (long long)B * F * H * W;
     const long long pix0 = (long long)blockIdx.x * IN_PIX;
     for (int i = threadIdx.x; i < K * Cout; i += blockDim.x) {
-        const int k = i / Cout, co = i % Cout;          // k = (ci*3 + ky)*3 + kx, matching w[co][ci][ky][kx]
-        sw[i] = w[(long long)co * K + k];
+        const int co = i / K, k = i - co * K;           // k = (ci*3 + ky)*3 + kx, matching w[co][ci][ky][kx]
+        sw[k * Cout + co] = __ldg(w + i);
     }
     pdl_launch_dependents();                // the weights above are static: staged while the previous kernel drains
     pdl_wait();
     for (int i = threadIdx.x; i < IN_PIX * K; i += blockDim.x) {
-        const int p = i / K, k = i % K;
+        const int k = i / IN_PIX, p = i - k * IN_PIX;   // consecutive threads = consecutive pixels of one tap
         const long long pix = pix0 + p;
         float v = 0.f;
         if (pix < npix) {
@@ -107,24 +111,38 @@ conv3x3_in_kernel(const float* __restrict__ x1, int C1, const float* __restrict_
     }
     __syncthreads();
     const int cov = Cout / 8;
-    for (int i = threadIdx.x; i < IN_PIX * cov; i += blockDim.x) {
-        const int p = i / cov, co0 = (i % cov) * 8;
-        const long long pix = pix0 + p;
-        if (pix >= npix) continue;
-        float acc[8];
+    for (int i = threadIdx.x; i < (IN_PIX / 4) * cov; i += blockDim.x) {
+        // channels of a work item: 4 from each half of Cout, so that both weight loads are lane-contiguous 16 B
+        // (conflict-free) instead of 16 B out of every 32 B
+        const int pq = i / cov, ca = (i - pq * cov) * 4, cb = Cout / 2 + ca;
+        float acc[4][8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[j] = bias[co0 + j];
-        const float* xp = sx + p * K;
+        for (int q = 0; q < 4; ++q)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[q][j] = 0.f;
         for (int k = 0; k < K; ++k) {
-            const float v = xp[k];
-            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + co0);
-            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + co0 + 4);
-            acc[0] += v * w0.x; acc[1] += v * w0.y; acc[2] += v * w0.z; acc[3] += v * w0.w;
-            acc[4] += v * w1.x; acc[5] += v * w1.y; acc[6] += v * w1.z; acc[7] += v * w1.w;
+            const float4 xv = *reinterpret_cast<const float4*>(sx + k * IN_PIX + pq * 4);
+            const float4 w0 = *reinterpret_cast<const float4*>(sw + k * Cout + ca);
+            const float4 w1 = *reinterpret_cast<const float4*>(sw + k * Cout + cb);
+            const float xs[4] = {xv.x, xv.y, xv.z, xv.w};
+            const float ws[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[q][j] = fmaf(xs[q], ws[j], acc[q][j]);
         }
-        *reinterpret_cast<uint4*>(out + pix * Cout + co0) =
-            make_uint4(pack_half2(acc[0], acc[1]), pack_half2(acc[2], acc[3]), pack_half2(acc[4], acc[5]),
-                       pack_half2(acc[6], acc[7]));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(bias + ca));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(bias + cb));
+        const float bs[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const long long pix = pix0 + pq * 4 + q;
+            if (pix >= npix) continue;
+            *reinterpret_cast<uint2*>(out + pix * Cout + ca) =
+                make_uint2(pack_half2(acc[q][0] + bs[0], acc[q][1] + bs[1]), pack_half2(acc[q][2] + bs[2], acc[q][3] + bs[3]));
+            *reinterpret_cast<uint2*>(out + pix * Cout + cb) =
+                make_uint2(pack_half2(acc[q][4] + bs[4], acc[q][5] + bs[5]), pack_half2(acc[q][6] + bs[6], acc[q][7] + bs[7]));
+        }
     }
 }
 
@@ -252,7 +270,7 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
 using namespace vmv;
 
 extern "C" const char* vmv_last_error(void) { return g_err; }
-extern "C" int vmv_abi_version(void) { return 3; }
+extern "C" int vmv_abi_version(void) { return 4; }
 extern "C" long long vmv_launch_count(void) { return g_launches.load(); }
 extern "C" int vmv_sizeof_gemm_params(void) { return (int)sizeof(vmv_gemm_params); }
 extern "C" int vmv_sizeof_attn_params(void) { return (int)sizeof(vmv_attn_params); }

@@ -57,6 +57,10 @@ class UNetEngine:
         self._gn_arena: Optional[ops.GnArena] = None       # zeroed scratch of the single-launch GroupNorm (per forward)
         self._gn_arenas: Dict[int, ops.GnArena] = {}
         self.fused_groupnorm = os.environ.get("VMV_GN_FUSED", "1") != "0"
+        # LayerNorm row sums accumulated by the epilogue of the GEMM that produces the rows (no separate statistics pass);
+        # needs the CTA-pair kernel's register epilogue and the zeroed per-forward arena
+        self.fused_ln_stats = (self.fused_groupnorm and os.environ.get("VMV_LN_FUSED", "1") != "0"
+                               and os.environ.get("VMV_GEMM_VARIANT", "2") != "1")
         self._pack()
 
     # ------------------------------------------------------------------------------------------------------------
@@ -203,8 +207,18 @@ class UNetEngine:
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 kw["workspace"] = self._ws
         # w_static: every W here is a packed model weight, so the kernel may prefetch W tiles ahead of its PDL wait
-        return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, ln_colsum=w.colsum if "ln_stats" in kw else None,
-                        w_static=True, **kw)
+        ln = kw.pop("ln", None)                    # (stats tensor, raw_c): statistics of the rows of `a` for the folded LayerNorm
+        if ln is not None:
+            kw.update(ln_stats=ln[0], ln_raw_c=ln[1], ln_colsum=w.colsum)
+        want_stats = kw.pop("want_stats", False)   # the output feeds a LayerNorm: also return its row statistics
+        if not want_stats:
+            return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, w_static=True, **kw)
+        if self.fused_ln_stats and split == 0 and N % 32 == 0 and self._gn_arena is not None:
+            rs = self._gn_arena.take_rowstats(M)
+            out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, rowstats_out=rs, **kw)
+            return out, (rs, N)
+        out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, w_static=True, **kw)
+        return out, (ops.layernorm_stats(out), 0)
 
     # ------------------------------------------------------------------------------------------------------------
     # blocks
@@ -251,7 +265,8 @@ class UNetEngine:
         return dict(reduce_fn=lambda st: parallel.allreduce_stats(st, ctx),
                     stat_rows=S["F"] * ctx.world * S["H"] * S["W"])
 
-    def _tblock(self, tb, h, S, heads, temporal: bool, kv=None, Fr=None, HW=None):
+    def _tblock(self, tb, h, hst, S, heads, temporal: bool, kv=None, Fr=None, HW=None):
+        """BasicTransformerBlock (util.py:536-540) on rows `h` whose LayerNorm statistics are `hst`."""
         B = S["B"]
         Fr = S["F"] if Fr is None else Fr
         HW = S["H"] * S["W"] if HW is None else HW
@@ -271,38 +286,39 @@ class UNetEngine:
                               q_strides=st, k_strides=st, v_strides=st, o_strides=(HW * C, 0, C))
             return o
 
-        # the three LayerNorms are folded into the GEMMs that consume them: only per-row {mean, rstd} is computed
-        h = self._gemm(self_attn(self._gemm(h, tb["qkv1"], ln_stats=ops.layernorm_stats(h))), tb["o1"], residual=h)
+        # The three LayerNorms are folded into the GEMMs that consume them, and their row statistics come out of the
+        # epilogue of the GEMM that produced the rows (proj_in, attn1.to_out, attn2.to_out): no LayerNorm kernel at all.
+        h, hst = self._gemm(self_attn(self._gemm(h, tb["qkv1"], ln=hst)), tb["o1"], residual=h, want_stats=True)
         if temporal:
-            h = self._gemm(self_attn(self._gemm(h, tb["qkv2"], ln_stats=ops.layernorm_stats(h))), tb["o2"], residual=h)
+            h, hst = self._gemm(self_attn(self._gemm(h, tb["qkv2"], ln=hst)), tb["o2"], residual=h, want_stats=True)
         else:
-            q = self._gemm(h, tb["q2"], ln_stats=ops.layernorm_stats(h))
+            q = self._gemm(h, tb["q2"], ln=hst)
             kview, vview, L, ldkv = kv
             o = torch.empty((M, C), dtype=torch.float16, device=h.device)
             ops.attention(q, kview, vview, o, outer=B * Fr, inner=1, heads=heads, nq=HW, nk=L,
                           q_strides=(HW * C, 0, C), k_strides=(L * ldkv, 0, ldkv), v_strides=(L * ldkv, 0, ldkv),
                           o_strides=(HW * C, 0, C), kv_group=Fr)
-            h = self._gemm(o, tb["o2"], residual=h)
-        g = self._gemm(h, tb["ff1"], act=ops.ACT_GEGLU, ln_stats=ops.layernorm_stats(h))
+            h, hst = self._gemm(o, tb["o2"], residual=h, want_stats=True)
+        g = self._gemm(h, tb["ff1"], act=ops.ACT_GEGLU, ln=hst)
         return self._gemm(g, tb["ff2"], residual=h)
 
     def _spatial(self, d, x, S):
         HW = S["H"] * S["W"]
         a = ops.groupnorm(x, *d["gn"], rows_per_batch=HW, eps=1e-6, silu=False, scratch=self._gn_arena)
-        h = self._gemm(a, d["pin"])
+        h, hst = self._gemm(a, d["pin"], want_stats=True)
         C = d["heads"] * self.head_dim
         kvall = S["kv_all"]
         off = d["kv_off"]
         kv = (kvall[:, off:off + C], kvall[:, off + C:off + 2 * C], S["L"], kvall.stride(0))
-        h = self._tblock(d["tb"], h, S, d["heads"], temporal=False, kv=kv)
+        h = self._tblock(d["tb"], h, hst, S, d["heads"], temporal=False, kv=kv)
         return self._gemm(h, d["pout"], residual=x)
 
     def _temporal(self, d, x, S):
         Ff, HWt, to_frames = self._enter_temporal(S)
         xt = self._to_pixels(x, S)
         a = ops.groupnorm(xt, *d["gn"], rows_per_batch=Ff * HWt, eps=1e-6, silu=False, scratch=self._gn_arena, **self._gn5d_kw(S))
-        h = self._gemm(a, d["pin"])
-        h = self._tblock(d["tb"], h, S, d["heads"], temporal=True, Fr=Ff, HW=HWt)
+        h, hst = self._gemm(a, d["pin"], want_stats=True)
+        h = self._tblock(d["tb"], h, hst, S, d["heads"], temporal=True, Fr=Ff, HW=HWt)
         return to_frames(self._gemm(h, d["pout"], residual=xt))
 
     def _run_block(self, d, x, skip, S):
@@ -415,7 +431,9 @@ class UNetEngine:
             arena = self._gn_arenas.get(nb)
             if arena is None:
                 per_call = int(_lib_scratch_bytes(nb)) + 256
-                arena = self._gn_arenas[nb] = ops.GnArena(x32.device, 192 * per_call)   # 166 GroupNorms per forward
+                # 166 GroupNorms per forward + the LayerNorm row-sum accumulators (99 LayerNorms: 30 at each of the three
+                # transformer levels, 9 in the middle block = 39.5 x (level-0 rows) x 8 B; sized with margin)
+                arena = self._gn_arenas[nb] = ops.GnArena(x32.device, 192 * per_call + 64 * nb * H * W * 8)
             self._gn_arena = arena
             arena.reset()                              # one memset per forward; every GroupNorm call takes a fresh region
         sh = self.shard

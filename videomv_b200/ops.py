@@ -55,7 +55,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
          workspace: Optional[torch.Tensor] = None, variant: int = 0, ln_stats: Optional[torch.Tensor] = None,
-         ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False) -> torch.Tensor:
+         ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False, ln_raw_c: int = 0, ln_eps: float = 1e-5,
+         rowstats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -93,6 +94,11 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         if ln_stats.dtype != torch.float32 or ln_stats.numel() != 2 * M or ln_colsum is None or ln_colsum.numel() != N:
             raise ValueError("gemm ln_stats must be fp32 [M,2] and ln_colsum fp32 [N]")
         p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
+        p.ln_stats_raw_c, p.ln_eps = int(ln_raw_c), float(ln_eps)       # raw {sum, sumsq} rows from an upstream rowstats_out
+    if rowstats_out is not None:
+        if rowstats_out.dtype != torch.float32 or rowstats_out.numel() != 2 * M or not rowstats_out.is_contiguous():
+            raise ValueError("gemm rowstats_out must be a contiguous (zeroed) fp32 [M,2] tensor")
+        p.rowstats_out = rowstats_out.data_ptr()
     p.act, p.block_n, p.stages, p.split_k, p.variant = act, block_n, stages, split_k, variant
     p.w_static = 1 if w_static else 0
     if split_k > 1:
@@ -106,7 +112,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
     if e0 is not None:
         ktot = w.shape[1]
-        keep = (a1, a2, w, out, bias, rowbias, residual, workspace)          # keep the operands alive for replays
+        keep = (a1, a2, w, out, bias, rowbias, residual, workspace, ln_stats, ln_colsum, rowstats_out)   # alive for replays
         replay = lambda p=p, keep=keep: check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
         _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out),
                   f"mode{mode} M{M} N{N} K{ktot} act{act} res{int(residual is not None)} rb{int(rowbias is not None)} "
@@ -115,24 +121,34 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
 
 
 class GnArena:
-    """Zero-initialised scratch for the single-launch GroupNorm: one region per call, bump-allocated; `reset()` zeroes
-    the arena (one memset) and rewinds -- call it once per forward, before the first GroupNorm."""
+    """Zero-initialised scratch, bump-allocated: one region per single-launch GroupNorm call (`take`) and one fp32 [M,2]
+    row-statistics accumulator per LayerNorm whose sums are produced by the upstream GEMM's epilogue (`take_rowstats`).
+    `reset()` zeroes what the previous forward used (one memset) and rewinds -- call it once per forward."""
 
     def __init__(self, device, nbytes: int = 8 << 20):
         self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
         self.off = 0
+        self.high = 0
 
     def reset(self):
-        self.buf.zero_()
+        self.high = max(self.high, self.off)
+        if self.high:
+            self.buf[:self.high].zero_()
         self.off = 0
 
-    def take(self, nbatch: int) -> int:
-        n = int(_lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch))
+    def _bump(self, n: int) -> int:
         if self.off + n > self.buf.numel():
             raise RuntimeError("GnArena exhausted: raise its size or call reset() once per forward")
-        p = self.buf.data_ptr() + self.off
+        o = self.off
         self.off += (n + 255) // 256 * 256
-        return p
+        return o
+
+    def take(self, nbatch: int) -> int:
+        return self.buf.data_ptr() + self._bump(int(_lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch)))
+
+    def take_rowstats(self, rows: int) -> torch.Tensor:
+        o = self._bump(rows * 8)
+        return self.buf[o:o + rows * 8].view(torch.float32).view(rows, 2)
 
 
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
