@@ -327,9 +327,27 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                     f.write(f"| {desc} | {n} | {us:.1f} | {n * us / 1e3:.3f} | {100 * n * us / (dev_ms * 1e3):.1f}% | {fl / us / 1e6:.0f} |\n")
                 f.write(f"gemm total {dev_ms:.3f} ms per B=2 forward ({len(rows)} distinct shapes)\n")
         achieved = g[1] / (dev_ms * 1e-3) / 1e12
+        # DRAM traffic of the same kernel family from the committed ncu capture of one forward (profiles/r1_traffic.json,
+        # made by tools/summarize_traffic.py): bytes per launch, like `achieved` is FLOPs per launch / time per launch
+        traffic, alg_bytes = None, sum(r_[2] for r_ in prof if r_[0] == "gemm_tc")
+        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        if os.path.isfile(tj):
+            try:
+                tr = json.load(open(tj)).get("gemm_tc2_kernel")
+                traffic = tr["dram_bytes_per_launch"] if tr else None
+            except Exception:  # noqa: BLE001
+                traffic = None
+        # binding roofline per launch shape: max(FLOPs / tensor peak, algorithmic bytes / HBM peak), summed over the forward
+        shape_bytes = {}
+        for r_ in prof:
+            if r_[0] == "gemm_tc":
+                shape_bytes.setdefault(r_[5], r_[2])
+        t_bind = sum(n * max(fl / (pk["tflops"] * 1e12), shape_bytes.get(desc, 0.0) / (pk["hbm"] * 1e9)) for desc, n, fl, _ in rows)
         line["roofline"] = {"bound": "tensor", "kernel": "gemm_tc2_kernel<BN,STAGES,.> (tcgen05 CTA-pair GEMM / implicit conv family)",
                             "achieved": achieved, "peak": pk["tflops"], "unit": "TFLOP/s", "frac": achieved / pk["tflops"],
-                            "traffic": None, "peak_source": pk["src"] + " bf16_tflops_sustained",
+                            "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes / max(g[0], 1),
+                            "frac_of_binding_roofline": t_bind / (dev_ms * 1e-3),
+                            "peak_source": pk["src"] + " bf16_tflops_sustained",
                             "launches_per_forward": g[0], "distinct_shapes": len(rows),
                             "algorithmic_tflop_per_forward_b2": g[1] / 1e12, "kernel_ms_per_forward_b2": dev_ms,
                             "how": "algorithmic FLOPs of the 422 launches of one CFG-batched forward / their device time "

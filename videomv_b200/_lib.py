@@ -14,7 +14,8 @@ from concurrent.futures import ThreadPoolExecutor
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
-LIBPATH = os.path.join(LIBDIR, "libvideomv_b200.so")
+# VMV_LIB: load another build of the same ABI instead (same-box A/B runs of two source revisions; tools/ab_build.sh)
+LIBPATH = os.environ.get("VMV_LIB") or os.path.join(LIBDIR, "libvideomv_b200.so")
 SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]

@@ -420,15 +420,12 @@ struct SmemLayout2 {
     static constexpr int NBLK = NBLK_;
     static constexpr int A_OFF = 0;
     static constexpr int B_OFF = STAGES * A_STAGE_BYTES;
-    // per-epilogue-warp scratch: 128 bias floats + 128 LayerNorm column sums for the columns the warp owns in the
-    // current tile (fetched before the accumulator is ready, read back with LDS on the critical path)
-    static constexpr int SCR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
-    static constexpr int SCR_BYTES_PER_WARP = 2 * 128 * 4;
-    static constexpr int BAR_OFF = SCR_OFF + V2_EPI_WARPS * SCR_BYTES_PER_WARP;
+    static constexpr int BAR_OFF = B_OFF + STAGES * B_STAGE_BYTES;
     static constexpr int NBARS = 2 * STAGES + 4;
     static constexpr int TOTAL = BAR_OFF + NBARS * 8 + 16;
     static constexpr int DYN_BYTES = TOTAL + 1024;
-    static_assert(DYN_BYTES <= 232448, "shared memory budget exceeded");
+    // + the kernel's static smem: the per-epilogue-warp bias / column-sum scratch (V2_EPI_WARPS x 1 KiB)
+    static_assert(DYN_BYTES + V2_EPI_WARPS * 1024 + 1024 <= 232448, "shared memory budget exceeded");
 };
 
 // NBLK is unused by the register epilogue (kept so instantiations stay distinct per use)
@@ -440,6 +437,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     using L = SmemLayout2<BN, STAGES, NBLK>;
     constexpr int TCOLS = TmemCols<2 * BN>::value;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
+    // Per-epilogue-warp scratch: 128 bias floats + 128 LayerNorm column sums of the columns the warp owns in the current
+    // tile.  A static __shared__ array (not carved out of the manually aligned dynamic buffer) so that the compiler knows
+    // the address space and alignment: plain C++ float4 reads become LDS.128 that it is free to schedule among the math.
+    __shared__ __align__(16) float s_epi_scr[V2_EPI_WARPS][256];
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
@@ -604,7 +605,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int q = warp & 3;
         const int hh = (warp - 2) >> 2;                         // 0: even blocks, 1: odd blocks
         const int r = q * 32 + lane;
-        float* sbias = reinterpret_cast<float*>(smem + L::SCR_OFF + (warp - 2) * L::SCR_BYTES_PER_WARP);
+        float* sbias = s_epi_scr[warp - 2];
         float* scol = sbias + 128;
         const bool geglu = a.act == VMV_ACT_GEGLU;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
@@ -689,7 +690,6 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     ln_b = -ms.y * ms.x;
                 }
                 const bool has_b = a.bias != nullptr;
-                const uint32_t sbias_a = smem_u32(sbias), scol_a = smem_u32(scol);
                 int j = 0;
                 // The accumulators of block i+2 are requested from TMEM as soon as block i's have been consumed into x[],
                 // so the tcgen05.ld latency overlaps the residual / activation / pack / store part (VMV_GEMM_DEBUG 16: off).
@@ -708,31 +708,29 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         tmem_ld_32x32b_x16(trow + BN / 2 + c, *reinterpret_cast<uint32_t(*)[16]>(&g[0]));
                         tmem_ld_32x32b_x16(trow + BN / 2 + c + 16, *reinterpret_cast<uint32_t(*)[16]>(&g[16]));
                         tmem_ld_wait();
-                        const uint32_t bva = sbias_a + j * 256, cva = scol_a + j * 256;     // 64 floats per block pair
+                        const float4* bv4 = reinterpret_cast<const float4*>(sbias + j * 64);    // [0,8) value, [8,16) gate
+                        const float4* cv4 = reinterpret_cast<const float4*>(scol + j * 64);
                         if (ln) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float bv[4], bg[4], cv[4], cg[4];
-                                lds128(bva + i * 4, bv);
-                                lds128(bva + 128 + i * 4, bg);
-                                lds128(cva + i * 4, cv);
-                                lds128(cva + 128 + i * 4, cg);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b4 = bv4[i], g4 = bv4[8 + i], c4 = cv4[i], d4 = cv4[8 + i];
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, bg[4] = {g4.x, g4.y, g4.z, g4.w};
+                                const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, cg[4] = {d4.x, d4.y, d4.z, d4.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e) {
-                                    const float val = fmaf(__uint_as_float(v[i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
-                                    const float gate = fmaf(__uint_as_float(g[i + e]), ln_a, fmaf(ln_b, cg[e], bg[e]));
-                                    x[i + e] = geglu_f(val, gate);
+                                    const float val = fmaf(__uint_as_float(v[4 * i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                                    const float gate = fmaf(__uint_as_float(g[4 * i + e]), ln_a, fmaf(ln_b, cg[e], bg[e]));
+                                    x[4 * i + e] = geglu_f(val, gate);
                                 }
                             }
                         } else {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float bv[4], bg[4];
-                                lds128(bva + i * 4, bv);             // zeros when there is no bias
-                                lds128(bva + 128 + i * 4, bg);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b4 = bv4[i], g4 = bv4[8 + i];                  // zeros when there is no bias
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, bg[4] = {g4.x, g4.y, g4.z, g4.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    x[i + e] = geglu_f(__uint_as_float(v[i + e]) + bv[e], __uint_as_float(g[i + e]) + bg[e]);
+                                    x[4 * i + e] = geglu_f(__uint_as_float(v[4 * i + e]) + bv[e], __uint_as_float(g[4 * i + e]) + bg[e]);
                             }
                         }
                     } else {
@@ -746,24 +744,24 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             ldg256(rb + col0 + c + 16, *reinterpret_cast<uint32_t(*)[8]>(&rbv[8]));
                         }
                         tmem_ld_wait();
-                        const uint32_t bva = sbias_a + j * 128, cva = scol_a + j * 128;     // 32 floats per block
+                        const float4* bv4 = reinterpret_cast<const float4*>(sbias + j * 32);
+                        const float4* cv4 = reinterpret_cast<const float4*>(scol + j * 32);
                         if (ln) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float bv[4], cv[4];
-                                lds128(bva + i * 4, bv);
-                                lds128(cva + i * 4, cv);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b4 = bv4[i], c4 = cv4[i];
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
                                 for (int e = 0; e < 4; ++e)
-                                    x[i + e] = fmaf(__uint_as_float(v[i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                                    x[4 * i + e] = fmaf(__uint_as_float(v[4 * i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
                             }
                         } else if (has_b) {
 #pragma unroll
-                            for (int i = 0; i < 32; i += 4) {
-                                float bv[4];
-                                lds128(bva + i * 4, bv);
+                            for (int i = 0; i < 8; ++i) {
+                                const float4 b4 = bv4[i];
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                                for (int e = 0; e < 4; ++e) x[i + e] = __uint_as_float(v[i + e]) + bv[e];
+                                for (int e = 0; e < 4; ++e) x[4 * i + e] = __uint_as_float(v[4 * i + e]) + bv[e];
                             }
                         } else {
 #pragma unroll

@@ -114,7 +114,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         ktot = w.shape[1]
         keep = (a1, a2, w, out, bias, rowbias, residual, workspace, ln_stats, ln_colsum, rowstats_out)   # alive for replays
         replay = lambda p=p, keep=keep: check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
-        _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * K1 + N * ktot + M * n_out),
+        k_in = K1 + (a2.shape[1] if a2 is not None else 0)               # activation columns actually read (conv modes: Cin)
+        _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * k_in + N * ktot + M * n_out * (2 if residual is not None else 1)),
                   f"mode{mode} M{M} N{N} K{ktot} act{act} res{int(residual is not None)} rb{int(rowbias is not None)} "
                   f"split{split_k}", replay)
     return out
