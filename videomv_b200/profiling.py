@@ -13,14 +13,19 @@ import torch
 
 
 def replay_us(replay, reps: int = 8, rounds: int = 3) -> float:
+    pre = getattr(replay, "pre", None)          # e.g. GroupNorm: zero its scratch arena once per graph
     side = torch.cuda.Stream()
     side.wait_stream(torch.cuda.current_stream())
     with torch.cuda.stream(side):
+        if pre is not None:
+            pre()
         replay()
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
     g = torch.cuda.CUDAGraph()
     with torch.cuda.graph(g):
+        if pre is not None:
+            pre()
         for _ in range(reps):
             replay()
     g.replay()
@@ -34,12 +39,16 @@ def replay_us(replay, reps: int = 8, rounds: int = 3) -> float:
     return e0.elapsed_time(e1) * 1e3 / (reps * rounds)
 
 
-def gemm_shape_times(prof):
+def family_shape_times(prof, family):
     """prof: the list collected in ops.PROFILE during ONE forward.  Returns rows (desc, launches, flops each, device us
-    each) for every distinct GEMM shape, timed by graph replay."""
+    each, bytes each) for every distinct shape of one kernel family, timed by graph replay."""
     shapes = collections.OrderedDict()
     for name, fl, by, a, b, desc, replay in prof:
-        if name == "gemm_tc":
-            g = shapes.setdefault(desc, [0, fl, replay])
+        if name == family and replay is not None:
+            g = shapes.setdefault(desc, [0, fl, replay, by])
             g[0] += 1
-    return [(desc, n, fl, replay_us(replay)) for desc, (n, fl, replay) in shapes.items()]
+    return [(desc, n, fl, replay_us(replay), by) for desc, (n, fl, replay, by) in shapes.items()]
+
+
+def gemm_shape_times(prof):
+    return [r[:4] for r in family_shape_times(prof, "gemm_tc")]
