@@ -55,7 +55,7 @@ class UNetEngine:
         self.use_graphs = False
         self.shard: Optional[parallel.ShardCtx] = None     # frame sharding of one sample over the ranks of a group
         self._gn_arena: Optional[ops.GnArena] = None       # zeroed scratch of the single-launch GroupNorm (per forward)
-        self._gn_arenas: Dict[int, ops.GnArena] = {}
+        self._gn_arenas: Dict[Tuple[int, int, int], ops.GnArena] = {}
         self.fused_groupnorm = os.environ.get("VMV_GN_FUSED", "1") != "0"
         # LayerNorm row sums accumulated by the epilogue of the GEMM that produces the rows (no separate statistics pass);
         # needs the CTA-pair kernel's register epilogue and the zeroed per-forward arena
@@ -428,12 +428,12 @@ class UNetEngine:
         if self.fused_groupnorm:
             # one arena per (B*F) size class, kept alive for the CUDA graphs that captured pointers into it
             nb = B * Fr
-            arena = self._gn_arenas.get(nb)
+            arena = self._gn_arenas.get((nb, H, W))
             if arena is None:
                 per_call = int(_lib_scratch_bytes(nb)) + 256
                 # 166 GroupNorms per forward + the LayerNorm row-sum accumulators (99 LayerNorms: 30 at each of the three
                 # transformer levels, 9 in the middle block = 39.5 x (level-0 rows) x 8 B; sized with margin)
-                arena = self._gn_arenas[nb] = ops.GnArena(x32.device, 192 * per_call + 64 * nb * H * W * 8)
+                arena = self._gn_arenas[(nb, H, W)] = ops.GnArena(x32.device, 192 * per_call + 64 * nb * H * W * 8)
             self._gn_arena = arena
             arena.reset()                              # one memset per forward; every GroupNorm call takes a fresh region
         sh = self.shard
