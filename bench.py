@@ -281,8 +281,10 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                        else cls.__name__ + " (configs/i2vgen_xl_infer.yaml)",
                        "frames": FRAMES, "latent": [4, FRAMES, hw, hw], "ddim_steps": DDIM_STEPS,
                        "guidance": f"cfg {gs}, cond+uncond as one batch-2 UNet call" if not args.two_call else f"cfg {gs}, two calls",
-                       "parallelism": (f"frames/{world}: one sample, 24 frames sharded, all-to-all at temporal segments + "
-                                       f"GroupNorm-stat all-reduce ({model._engine().shard.collectives} collectives per UNet call)"
+                       "parallelism": (f"frames/{world}: one sample, 24 frames sharded; layout exchange at temporal segments + "
+                                       f"GroupNorm-stat all-reduce via {model._engine().shard.mode} "
+                                       f"({model._engine().shard.peer_ops} peer-memory kernels + "
+                                       f"{model._engine().shard.collectives} NCCL collectives per UNet call)"
                                        if sharded else f"replicas x{world} (one sample per GPU, no collective)"),
                        "cuda_graphs": not args.no_graphs,
                        "l2": "working set > L2: 2.83 GB of fp16 weights streamed per UNet call (no explicit flush)"},

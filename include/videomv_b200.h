@@ -185,6 +185,49 @@ int vmv_embed_combine_silu(const void* t_emb, const void* t_emb2, const void* ca
 int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, const float* coef7, int64_t n,
                       float* x_prev, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Multi-GPU frame sharding of ONE sample (BASELINE config 5; new design, no reference counterpart -- the reference's
+ * multi-GPU mode is independent replicas, inference_text2video_entrance.py:79,152-170).  Around every temporal segment
+ * (util.py:1043-1089 TemporalTransformer, :1381-1392 TemporalConvBlock_v2) the activation switches between
+ *   layout A "frame shard"  rows (b, f_local, pixel)   [B*Fl*HW, C]      and
+ *   layout B "pixel shard"  rows (b, f, pixel_local)   [B*F*HWl, C]      (F = Fl*world, HW = HWl*world).
+ * vmv_peer_exchange does that switch as ONE kernel per rank over NVLink peer memory: remote 16 B stores of the slices
+ * the other ranks need into THEIR output tensors, then an epoch flag barrier (st.release.sys / ld.acquire.sys); it
+ * returns (stream-ordered) only when this rank's whole output is in its memory.  vmv_peer_allreduce_f64 sums the 5-D
+ * GroupNorm partial statistics (util.py:1014,1358-1372) the same way, in rank order (bit-identical on all ranks).
+ * dst[q] / flags[q] / slots[q] are the SAME arena offsets in every rank q's memory, mapped here through CUDA IPC
+ * (vmv_ipc_export on the owner, vmv_ipc_import on the peers); [rank] entries are local pointers.  flags: `world`
+ * uint32 per call site, zero at start; epoch: local uint32 per call site (zero at start); done: local uint32, zero.
+ * All ranks must issue the same sequence of calls.  nowait != 0 skips the wait (single-process tests of the data
+ * movement only).
+ * ---------------------------------------------------------------------------------------------- */
+#define VMV_PEER_MAX_RANKS 8
+typedef struct vmv_peer_exchange_params {
+    const void* src;                      /* local fp16 rows in the source layout, contiguous */
+    void* dst[VMV_PEER_MAX_RANKS];        /* output tensor (destination layout) in every rank's arena */
+    void* flags[VMV_PEER_MAX_RANKS];
+    void* epoch; void* done;
+    int32_t world, rank;
+    int32_t direction;                    /* 0: A -> B (frames to pixels), 1: B -> A */
+    int32_t B, Fl, HWl, C;                /* samples, frames per rank, pixels per rank, channels */
+    int32_t nowait;
+} vmv_peer_exchange_params;
+int vmv_peer_exchange(const vmv_peer_exchange_params* p, void* stream);
+
+typedef struct vmv_peer_allreduce_params {
+    double* data;                         /* local [n], in/out */
+    double* slots[VMV_PEER_MAX_RANKS];    /* [world][n] in every rank's arena */
+    void* flags[VMV_PEER_MAX_RANKS];
+    void* epoch;
+    int32_t world, rank, n, nowait;
+} vmv_peer_allreduce_params;
+int vmv_peer_allreduce_f64(const vmv_peer_allreduce_params* p, void* stream);
+
+/* CUDA IPC plumbing for the peer arenas: export = 64-byte handle of the allocation containing ptr + ptr's offset in it;
+ * import = map a peer's allocation (peer access enabled lazily) and return base + offset. */
+int vmv_ipc_export(const void* ptr, void* handle64, int64_t* offset);
+int vmv_ipc_import(const void* handle64, int64_t offset, void** out);
+
 /* sizeof() of the two parameter structs as compiled, so a foreign-language binding can verify its mirror. */
 int vmv_sizeof_gemm_params(void);
 int vmv_sizeof_attn_params(void);

@@ -42,24 +42,39 @@ def main():
     ref = model(x, d["t"].cuda(), **kw)
     torch.cuda.synchronize()
     say("single-GPU reference forward done")
-    model.set_frame_sharding()
-    out = model(x, d["t"].cuda(), **kw)
-    torch.cuda.synchronize()
-    rel = ((out - ref).norm() / ref.norm()).item()
-    ncoll = model._engine().shard.collectives
-    print(f"[sharded] rank {rank}/{world}: rel_l2 vs single-GPU {rel:.3e}, {ncoll} collectives per forward", flush=True)
-    ok = torch.tensor([1 if rel < 6e-3 else 0], device="cuda")
-    # graphs with captured NCCL collectives
-    try:
-        model.enable_cuda_graphs(True)
-        og = model(x, d["t"].cuda(), **kw)
-        og2 = model(x, d["t"].cuda(), **kw)
-        relg = ((og2 - ref).norm() / ref.norm()).item()
-        print(f"[sharded] rank {rank}: graph replay rel_l2 {relg:.3e}", flush=True)
-        ok *= 1 if relg < 6e-3 else 0
-    except Exception as e:  # noqa: BLE001
-        print(f"[sharded] rank {rank}: graph capture with NCCL failed: {e!r}", flush=True)
-        ok *= 0
+    ok = torch.tensor([1], device="cuda")
+    outs = {}
+    for exch in os.environ.get("VMV_CHECK_EXCHANGES", "peer,gather").split(","):
+        # "peer": ONE kernel per exchange over NVLink peer memory (csrc/peer.cu); "gather": the NCCL baseline
+        model.enable_cuda_graphs(False)
+        model.set_frame_sharding(exchange=exch)
+        out = model(x, d["t"].cuda(), **kw)
+        torch.cuda.synchronize()
+        rel = ((out - ref).norm() / ref.norm()).item()
+        sh = model._engine().shard
+        print(f"[sharded] rank {rank}/{world} [{exch}]: rel_l2 vs single-GPU {rel:.3e}, {sh.peer_ops} peer-memory kernels + "
+              f"{sh.collectives} NCCL collectives per forward", flush=True)
+        ok *= 1 if rel < 6e-3 else 0
+        outs[exch] = out
+        # graphs with the captured exchanges
+        try:
+            model.enable_cuda_graphs(True)
+            og = model(x, d["t"].cuda(), **kw)
+            for _ in range(3):
+                og2 = model(x, d["t"].cuda(), **kw)
+            torch.cuda.synchronize()
+            relg = ((og2 - ref).norm() / ref.norm()).item()
+            print(f"[sharded] rank {rank} [{exch}]: graph replay rel_l2 {relg:.3e}", flush=True)
+            ok *= 1 if relg < 6e-3 else 0
+        except Exception as e:  # noqa: BLE001
+            print(f"[sharded] rank {rank} [{exch}]: graph capture failed: {e!r}", flush=True)
+            ok *= 0
+        model.enable_cuda_graphs(False)
+        model._engine()._graphs.clear()
+        torch.cuda.synchronize()
+    if len(outs) == 2:
+        a_, b_ = list(outs.values())
+        print(f"[sharded] rank {rank}: peer vs gather rel_l2 {((a_ - b_).norm() / ref.norm()).item():.3e}", flush=True)
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     dist.barrier()
     code = 0 if int(ok.item()) == 1 else 1

@@ -1,0 +1,89 @@
+"""Peer-memory layout exchange / statistics all-reduce kernels (csrc/peer.cu) on ONE GPU: the P ranks are simulated one
+after the other in this process (their "peer" pointers are local buffers, nowait skips the flag wait), which checks the data
+movement, the flag / epoch protocol state and the world=1 path with the real wait.  The true multi-process path (CUDA IPC,
+NVLink, concurrent waits) is tests/test_sharded_gpu.py."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _exchange(src, dsts, flags, ctrl, world, rank, direction, B, Fl, HWl, C, nowait):
+    from videomv_b200 import _lib, ops
+    p = _lib.PeerExchangeParams()
+    p.src = src.data_ptr()
+    for q in range(world):
+        p.dst[q] = dsts[q].data_ptr()
+        p.flags[q] = flags[q].data_ptr()
+    p.epoch = ctrl.data_ptr()
+    p.done = ctrl.data_ptr() + 4
+    p.world, p.rank, p.direction = world, rank, direction
+    p.B, p.Fl, p.HWl, p.C, p.nowait = B, Fl, HWl, C, nowait
+    _lib.check(_lib.lib().vmv_peer_exchange(ctypes.byref(p), ops._stream()), "vmv_peer_exchange")
+
+
+@pytest.mark.parametrize("P,B,F,HW,C", [(2, 2, 24, 1024, 320), (4, 1, 24, 64, 1280), (8, 2, 24, 16, 1280), (2, 1, 4, 16, 8)])
+def test_exchange_simulated_ranks(P, B, F, HW, C):
+    Fl, HWl = F // P, HW // P
+    g = torch.Generator(device="cuda").manual_seed(0)
+    full = torch.randn(B, F, HW, C, generator=g, device="cuda").half()
+    xa = [full[:, r * Fl:(r + 1) * Fl].reshape(B * Fl * HW, C).contiguous() for r in range(P)]          # layout A per rank
+    want_b = [full[:, :, q * HWl:(q + 1) * HWl].reshape(B * F * HWl, C).contiguous() for q in range(P)]  # layout B per rank
+    yb = [torch.zeros(B * F * HWl, C, dtype=torch.float16, device="cuda") for _ in range(P)]
+    flags = [torch.zeros(8, dtype=torch.int32, device="cuda") for _ in range(P)]
+    ctrl = [torch.zeros(2, dtype=torch.int32, device="cuda") for _ in range(P)]
+    for r in range(P):
+        _exchange(xa[r], yb, flags, ctrl[r], P, r, 0, B, Fl, HWl, C, nowait=1)
+    torch.cuda.synchronize()
+    for q in range(P):
+        assert torch.equal(yb[q], want_b[q]), f"frames->pixels, rank {q}"
+        assert flags[q][:P].tolist() == [1] * P and ctrl[q].tolist() == [1, 0]
+    ya = [torch.zeros(B * Fl * HW, C, dtype=torch.float16, device="cuda") for _ in range(P)]
+    for r in range(P):
+        _exchange(yb[r], ya, flags, ctrl[r], P, r, 1, B, Fl, HWl, C, nowait=1)
+    torch.cuda.synchronize()
+    for q in range(P):
+        assert torch.equal(ya[q], xa[q]), f"pixels->frames, rank {q}"
+        assert flags[q][:P].tolist() == [2] * P and ctrl[q].tolist() == [2, 0]
+
+
+def test_world1_with_real_wait_and_allreduce():
+    from videomv_b200 import _lib, ops
+    x = torch.randn(24 * 64, 320, device="cuda").half()
+    y = torch.zeros_like(x)
+    flags = torch.zeros(8, dtype=torch.int32, device="cuda")
+    ctrl = torch.zeros(2, dtype=torch.int32, device="cuda")
+    for it in range(3):
+        _exchange(x, [y], [flags], ctrl, 1, 0, it & 1, 1, 24, 64, 320, nowait=0)
+    torch.cuda.synchronize()
+    assert torch.equal(x, y) and flags[0].item() == 3
+
+    # statistics all-reduce, 4 simulated ranks: pass 1 fills every rank's slots (sums incomplete: nowait), pass 2 repeats
+    # the same partials and must produce the full sum on every rank, in rank order
+    P, n = 4, 128
+    parts = [torch.randn(n, dtype=torch.float64, device="cuda") for _ in range(P)]
+    slots = [torch.zeros(P * n, dtype=torch.float64, device="cuda") for _ in range(P)]
+    fl = [torch.zeros(8, dtype=torch.int32, device="cuda") for _ in range(P)]
+    ep = [torch.zeros(1, dtype=torch.int32, device="cuda") for _ in range(P)]
+    res = None
+    for _ in range(2):
+        res = []
+        for r in range(P):
+            d = parts[r].clone()
+            p = _lib.PeerAllreduceParams()
+            p.data = d.data_ptr()
+            for q in range(P):
+                p.slots[q] = slots[q].data_ptr()
+                p.flags[q] = fl[q].data_ptr()
+            p.epoch = ep[r].data_ptr()
+            p.world, p.rank, p.n, p.nowait = P, r, n, 1
+            _lib.check(_lib.lib().vmv_peer_allreduce_f64(ctypes.byref(p), ops._stream()), "vmv_peer_allreduce_f64")
+            res.append(d)
+    torch.cuda.synchronize()
+    want = parts[0].clone()
+    for r in range(1, P):
+        want = want + parts[r]
+    for r in range(P):
+        assert torch.equal(res[r], want), r

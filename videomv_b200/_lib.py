@@ -16,7 +16,7 @@ CSRC = os.path.join(_HERE, "csrc")
 LIBDIR = os.path.join(_HERE, "lib")
 # VMV_LIB: load another build of the same ABI instead (same-box A/B runs of two source revisions; tools/ab_build.sh)
 LIBPATH = os.environ.get("VMV_LIB") or os.path.join(LIBDIR, "libvideomv_b200.so")
-SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu"]
+SOURCES = ["gemm_tc.cu", "norm.cu", "attention.cu", "attention_tc.cu", "misc.cu", "peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 
@@ -95,6 +95,22 @@ class AttnParams(ctypes.Structure):
     ]
 
 
+PEER_MAX = 8
+
+
+class PeerExchangeParams(ctypes.Structure):
+    """Mirror of `vmv_peer_exchange_params`."""
+    _fields_ = [("src", c_vp), ("dst", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp), ("done", c_vp),
+                ("world", c_i32), ("rank", c_i32), ("direction", c_i32), ("B", c_i32), ("Fl", c_i32), ("HWl", c_i32),
+                ("C", c_i32), ("nowait", c_i32)]
+
+
+class PeerAllreduceParams(ctypes.Structure):
+    """Mirror of `vmv_peer_allreduce_params`."""
+    _fields_ = [("data", c_vp), ("slots", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp),
+                ("world", c_i32), ("rank", c_i32), ("n", c_i32), ("nowait", c_i32)]
+
+
 # every symbol include/videomv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "vmv_last_error": (ctypes.c_char_p, []),
@@ -121,6 +137,10 @@ SYMBOLS = {
     "vmv_sinusoidal_embedding": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "vmv_embed_combine_silu": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "vmv_cfg_ddim_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
+    "vmv_peer_exchange": (ctypes.c_int, [ctypes.POINTER(PeerExchangeParams), c_vp]),
+    "vmv_peer_allreduce_f64": (ctypes.c_int, [ctypes.POINTER(PeerAllreduceParams), c_vp]),
+    "vmv_ipc_export": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(c_i64)]),
+    "vmv_ipc_import": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
 }
 
 _LIB = None

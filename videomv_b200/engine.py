@@ -440,7 +440,7 @@ class UNetEngine:
         if sh is not None:
             # every rank receives the full [B,C,F,h,w] latent (as the sampler holds it) and computes its F/P frames
             sh.check(Fr, (H >> (len(self.m.dim_mult) - 1)) * (W >> (len(self.m.dim_mult) - 1)))
-            sh.collectives = 0
+            sh.begin_forward()
             Fl = Fr // sh.world
             lo = sh.rank * Fl
             x32 = x32[:, :, lo:lo + Fl].contiguous()

@@ -250,13 +250,14 @@ class _VideoUNetBase(nn.Module):
         self._engine().use_graphs = bool(on)
         return self
 
-    def set_frame_sharding(self, group=None, enable: bool = True):
+    def set_frame_sharding(self, group=None, enable: bool = True, exchange=None):
         """Spread ONE sample's frames over the ranks of `group` (default: WORLD): rank r computes frames
         [r*F/P, (r+1)*F/P); see videomv_b200/parallel.py. Every rank must make the same calls with the same inputs and
         receives the full output."""
         from . import parallel
         eng = self._engine()
-        eng.shard = parallel.ShardCtx(group) if enable else None
+        # exchange: None (= VMV_SHARD_EXCHANGE, default "peer": one kernel per exchange over NVLink peer memory) | "gather" | "a2a"
+        eng.shard = parallel.ShardCtx(group, device=eng.device, exchange=exchange) if enable else None
         eng._graphs.clear()
         return self
 
