@@ -120,6 +120,27 @@ int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2
                         int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
                         float eps, int32_t silu, void* out, int64_t ldo, void* stream);
 
+/* vmv_groupnorm_fused for a chunk whose rows are spread over `world` GPUs (5-D GroupNorm in the pixel-sharded layout of
+ * multi-GPU frame sharding, see vmv_peer_exchange below): the cross-GPU sum of the statistics happens INSIDE the kernel
+ * over NVLink peer memory (the first CTA of a chunk publishes this rank's partial sums into every rank's slot + an epoch
+ * flag; all CTAs wait for the `world` epochs and sum the slots in rank order).  slots[q]: [world][nbatch][64] doubles,
+ * flags[q]: [nbatch][16] uint32 (zero at start) at the same arena offset of every rank q; epoch: local [nbatch] uint32
+ * (zero at start); stat_rows = rows of a chunk over all ranks.  VMV_ERR_UNSUPPORTED when the tensor does not fit the
+ * smem-resident kernel (callers then use stats + vmv_peer_allreduce_f64 + apply). */
+#ifndef VMV_PEER_MAX_RANKS
+#define VMV_PEER_MAX_RANKS 8
+#endif
+typedef struct vmv_gn_peer {
+    int32_t world, rank;
+    double* slots[VMV_PEER_MAX_RANKS];
+    void* flags[VMV_PEER_MAX_RANKS];
+    void* epoch;
+    int64_t stat_rows;
+} vmv_gn_peer;
+int vmv_groupnorm_fused_peer(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                             int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
+                             float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer, void* stream);
+
 /* Per-row LayerNorm statistics only: stats[m] = {mean, 1/sqrt(var+eps)} fp32 (for the folded form in vmv_gemm). */
 int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float eps, void* stats, void* stream);
 /* LayerNorm over the last dim (eps 1e-5): nn.LayerNorm util.py:528-530.  x,out fp16 [M,C]. */
@@ -201,7 +222,9 @@ int vmv_cfg_ddim_step(const float* xt, const float* y_out, const float* u_out, c
  * All ranks must issue the same sequence of calls.  nowait != 0 skips the wait (single-process tests of the data
  * movement only).
  * ---------------------------------------------------------------------------------------------- */
+#ifndef VMV_PEER_MAX_RANKS
 #define VMV_PEER_MAX_RANKS 8
+#endif
 typedef struct vmv_peer_exchange_params {
     const void* src;                      /* local fp16 rows in the source layout, contiguous */
     void* dst[VMV_PEER_MAX_RANKS];        /* output tensor (destination layout) in every rank's arena */

@@ -87,3 +87,42 @@ def test_world1_with_real_wait_and_allreduce():
         want = want + parts[r]
     for r in range(P):
         assert torch.equal(res[r], want), r
+
+
+# grids are sized so that ALL simulated ranks' kernels are co-resident on one GPU (P * B * min(148 // B, rows) <= 148 CTAs):
+# on real multi-GPU runs every rank has its own device
+@pytest.mark.parametrize("P,B,rows,C", [(2, 2, 32, 320), (4, 1, 16, 1280), (2, 1, 64, 640)])
+def test_groupnorm_fused_peer_two_streams(P, B, rows, C):
+    """vmv_groupnorm_fused_peer: P simulated ranks run CONCURRENTLY on P streams of one GPU (small grids, so all kernels are
+    co-resident) and exchange their partial statistics through local "peer" buffers.  Result == GroupNorm over all ranks' rows."""
+    import torch.nn.functional as F
+    from videomv_b200 import _lib, ops
+    from tests.util import assert_close
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [(torch.randn(B * rows, C, generator=g, device="cuda") * 1.5 + 0.3 * (r + 1)).half() for r in range(P)]
+    gamma, beta = 1 + 0.1 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
+    outs = [torch.empty_like(x) for x in xs]
+    slots = [torch.zeros(P * B * 64, dtype=torch.float64, device="cuda") for _ in range(P)]
+    ctrl = [torch.zeros(B * 16 + 16, dtype=torch.int32, device="cuda") for _ in range(P)]
+    arenas = [ops.GnArena("cuda", 1 << 20) for _ in range(P)]
+    streams = [torch.cuda.Stream() for _ in range(P)]
+    torch.cuda.synchronize()
+    for it in range(2):                                   # twice: the epochs advance
+        for r in range(P):
+            gp = _lib.GnPeer()
+            gp.world, gp.rank, gp.stat_rows = P, r, P * rows
+            for q in range(P):
+                gp.slots[q] = slots[q].data_ptr()
+                gp.flags[q] = ctrl[q].data_ptr()
+            gp.epoch = ctrl[r].data_ptr() + B * 64
+            with torch.cuda.stream(streams[r]):
+                arenas[r].reset()
+                _lib.check(_lib.lib().vmv_groupnorm_fused_peer(xs[r].data_ptr(), C, C, None, 0, 0, rows, B, arenas[r].take(B),
+                                                               gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, outs[r].data_ptr(), C,
+                                                               ctypes.byref(gp), streams[r].cuda_stream), "vmv_groupnorm_fused_peer")
+        torch.cuda.synchronize()
+    full = torch.stack([x.float().reshape(B, rows, C) for x in xs], 1).reshape(B, P * rows, C)      # all ranks' rows of a sample
+    ref = F.silu(F.group_norm(full.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(B, P, rows, C)
+    for r in range(P):
+        assert_close(f"fused peer GN rank {r}", outs[r], ref[:, r].reshape(B * rows, C))
+    assert all(c[B * 16:B * 16 + B].tolist() == [2] * B for c in ctrl)

@@ -105,6 +105,12 @@ class PeerExchangeParams(ctypes.Structure):
                 ("C", c_i32), ("nowait", c_i32)]
 
 
+class GnPeer(ctypes.Structure):
+    """Mirror of `vmv_gn_peer`."""
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("slots", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp),
+                ("stat_rows", c_i64)]
+
+
 class PeerAllreduceParams(ctypes.Structure):
     """Mirror of `vmv_peer_allreduce_params`."""
     _fields_ = [("data", c_vp), ("slots", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp),
@@ -126,6 +132,8 @@ SYMBOLS = {
     "vmv_groupnorm_fused_scratch_bytes": (c_i64, [c_i32]),
     "vmv_groupnorm_fused": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
+    "vmv_groupnorm_fused_peer": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+                                                c_f32, c_i32, c_vp, c_i64, ctypes.POINTER(GnPeer), c_vp]),
     "vmv_layernorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
     "vmv_attention": (ctypes.c_int, [ctypes.POINTER(AttnParams), c_vp]),

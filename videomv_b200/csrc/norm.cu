@@ -5,6 +5,7 @@
 #include "../../include/videomv_b200.h"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace vmv {
 
@@ -322,6 +323,27 @@ constexpr int GNS_THREADS = 512;
 constexpr int GNS_MAX_DYN_SMEM = 227 * 1024 - 2048;       // the kernel's static smem (barrier + 4 x 32 floats, 1.7 KB) comes on top
 constexpr int GNS_CHUNK_BYTES = 16384;
 
+// Cross-GPU part of a 5-D GroupNorm in the pixel-sharded layout (multi-GPU frame sharding, csrc/peer.cu): every rank holds
+// all frames of HW/P pixels, so the statistics of a sample are the sum over ranks.  The first CTA of a chunk publishes this
+// rank's 64 partial sums into every rank's slot and raises an epoch flag there; every CTA of the chunk waits for the P epochs
+// in the local flag array and sums the P slots in rank order.  world <= 1: single-GPU behaviour.
+struct GnPeer {
+    int world, rank;
+    double* slots[VMV_PEER_MAX_RANKS];            // [world][nbatch][64] doubles in every rank's arena
+    unsigned int* flags[VMV_PEER_MAX_RANKS];      // [nbatch][16] u32 in every rank's arena (8 used per chunk)
+    unsigned int* epoch;                          // local [nbatch]
+    long long stat_rows;                          // rows per chunk summed over all ranks
+};
+
+__device__ __forceinline__ void gn_st_release_sys(unsigned int* p, unsigned int v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int gn_ld_acquire_sys(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -332,7 +354,7 @@ __global__ void __launch_bounds__(GNS_THREADS, 1)
 gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2, int C2,
                long long rows_per_batch, int rows_per_cta, double* __restrict__ stats, unsigned int* __restrict__ arrive,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
-               __half* __restrict__ out, long long ldo) {
+               __half* __restrict__ out, long long ldo, const GnPeer pe) {
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS], s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
@@ -351,6 +373,9 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
+    // the epoch this launch will use: read before this CTA arrives anywhere, i.e. before the publisher can advance it
+    unsigned int peer_epoch = 0;
+    if (pe.world > 1 && t == 0) peer_epoch = *(pe.epoch + batch) + 1;
     // ---- load: the whole slab in flight at once
     if (t < 32) {
         const uint32_t row_bytes = (uint32_t)C * 2u;
@@ -428,10 +453,50 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
         }
         __syncthreads();
     }
+    if (pe.world > 1) {
+        const int nb = gridDim.y;
+        if (blockIdx.x == 0) {                               // publisher of this chunk
+            if (t < GN_GROUPS) {
+                double sum, sq;
+                if (expected > 1) {
+                    sum = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]);
+                    sq = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]);
+                } else {
+                    sum = (double)s_sum[t];
+                    sq = (double)s_sq[t];
+                }
+                const long long o = (((long long)pe.rank * nb + batch) * GN_GROUPS + t) * 2;
+                for (int q = 0; q < pe.world; ++q) { pe.slots[q][o] = sum; pe.slots[q][o + 1] = sq; }
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (t == 0)
+                for (int q = 0; q < pe.world; ++q) gn_st_release_sys(pe.flags[q] + batch * 16 + pe.rank, peer_epoch);
+        }
+        if (t == 0) {
+            for (int q = 0; q < pe.world; ++q) {
+                unsigned long long spins = 0;
+                while ((int)(gn_ld_acquire_sys(pe.flags[pe.rank] + batch * 16 + q) - peer_epoch) < 0) {
+                    if (++spins > (1ull << 27)) __trap();        // seconds: a peer that never arrives fails the launch
+                    __nanosleep(20);
+                }
+            }
+            if (blockIdx.x == 0) *(pe.epoch + batch) = peer_epoch;
+        }
+        __syncthreads();
+    }
     if (t < GN_GROUPS) {
-        const double inv_cnt = 1.0 / ((double)rows_per_batch * cpg);
+        const double inv_cnt = 1.0 / ((double)(pe.world > 1 ? pe.stat_rows : rows_per_batch) * cpg);
         double sum, sq;
-        if (expected > 1) {
+        if (pe.world > 1) {                                  // sum of the ranks' partials, in rank order
+            const int nb = gridDim.y;
+            sum = 0.0; sq = 0.0;
+            for (int q = 0; q < pe.world; ++q) {
+                const long long o = (((long long)q * nb + batch) * GN_GROUPS + t) * 2;
+                sum += __ldcg(pe.slots[pe.rank] + o);
+                sq += __ldcg(pe.slots[pe.rank] + o + 1);
+            }
+        } else if (expected > 1) {
             sum = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]);
             sq = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]);
         } else {                                             // the chunk is mine alone: no global round trip
@@ -671,9 +736,9 @@ extern "C" int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch) {
     return (int64_t)nbatch * 2 * GN_GROUPS * 8 + (((int64_t)nbatch * 4 + 7) / 8) * 8;
 }
 
-extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                                   int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
-                                   const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
+static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                         int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
+                         float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer, void* stream) {
     int rc = gn_check("vmv_groupnorm_fused", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
     if (rc) return rc;
     VMV_CHECK_ARG(scratch && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_fused: bad scratch/gamma/beta/out");
@@ -703,14 +768,29 @@ extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, con
             cpb = (rows_per_batch + rpc - 1) / rpc;                // drop CTAs that would own no rows
             const long long smem = rpc * C * 2;
             if (smem <= GNS_MAX_DYN_SMEM) {
+                GnPeer pe;
+                memset(&pe, 0, sizeof(pe));
+                if (peer != nullptr && peer->world > 1) {
+                    pe.world = peer->world; pe.rank = peer->rank; pe.stat_rows = peer->stat_rows;
+                    pe.epoch = static_cast<unsigned int*>(peer->epoch);
+                    for (int q = 0; q < peer->world; ++q) {
+                        pe.slots[q] = peer->slots[q];
+                        pe.flags[q] = static_cast<unsigned int*>(peer->flags[q]);
+                    }
+                }
                 launch_kernel(gn_smem_kernel, dim3((unsigned)cpb, nbatch), dim3(GNS_THREADS), (size_t)smem, st,
                               static_cast<const __half*>(x1), ldx1, C1, static_cast<const __half*>(x2), ldx2, C2, rows_per_batch,
-                              (int)rpc, stats, arrive, gamma, beta, eps, silu, static_cast<__half*>(out), ldo);
+                              (int)rpc, stats, arrive, gamma, beta, eps, silu, static_cast<__half*>(out), ldo, pe);
                 count_launch();
                 VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused (smem)");
                 return VMV_OK;
             }
         }
+    }
+    if (peer != nullptr && peer->world > 1) {
+        set_error("vmv_groupnorm_fused_peer: the tensor does not fit the smem-resident kernel (%lld rows x %d channels per chunk); "
+                  "use vmv_groupnorm_stats + vmv_peer_allreduce_f64 + vmv_groupnorm_apply", (long long)rows_per_batch, C1 + C2);
+        return VMV_ERR_UNSUPPORTED;
     }
     static int capacity = 0;                                   // co-resident CTAs of gn_fused_kernel on this device
     if (capacity == 0) {
@@ -735,6 +815,24 @@ extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, con
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused");
     return VMV_OK;
+}
+
+extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                                   int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
+                                   const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
+    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, scratch, gamma, beta, eps, silu, out, ldo, nullptr, stream);
+}
+
+extern "C" int vmv_groupnorm_fused_peer(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
+                                        int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
+                                        const float* beta, float eps, int32_t silu, void* out, int64_t ldo,
+                                        const vmv_gn_peer* peer, void* stream) {
+    VMV_CHECK_ARG(peer && peer->world >= 1 && peer->world <= VMV_PEER_MAX_RANKS && peer->rank >= 0 && peer->rank < peer->world,
+                  "vmv_groupnorm_fused_peer: bad world/rank");
+    VMV_CHECK_ARG(peer->epoch && peer->stat_rows >= rows_per_batch, "vmv_groupnorm_fused_peer: bad epoch/stat_rows");
+    for (int q = 0; q < peer->world; ++q)
+        VMV_CHECK_ARG(peer->slots[q] && peer->flags[q], "vmv_groupnorm_fused_peer: null slots/flags for rank %d", q);
+    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, scratch, gamma, beta, eps, silu, out, ldo, peer, stream);
 }
 
 extern "C" int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,

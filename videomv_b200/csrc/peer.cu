@@ -52,7 +52,7 @@ __device__ __forceinline__ void peer_signal_and_wait(unsigned int* const* flags,
     for (int q = 0; q < world; ++q) {
         unsigned long long spins = 0;
         while ((int)(ld_acquire_sys(flags[rank] + q) - e) < 0) {
-            if (++spins > (1ull << 31)) __trap();
+            if (++spins > (1ull << 27)) __trap();                // seconds: a peer that never arrives fails the launch
             __nanosleep(20);
         }
     }

@@ -262,8 +262,10 @@ class UNetEngine:
         if self.shard is None:
             return {}
         ctx = self.shard
-        return dict(reduce_fn=lambda st: parallel.allreduce_stats(st, ctx),
-                    stat_rows=S["F"] * ctx.world * S["H"] * S["W"])
+        kw = dict(reduce_fn=lambda st: parallel.allreduce_stats(st, ctx), stat_rows=S["F"] * ctx.world * S["H"] * S["W"])
+        if ctx.mode == "peer" and ctx.fused_gn:
+            kw["peer"] = ctx            # single-pass GroupNorm with the cross-GPU sum inside the kernel (when it fits smem)
+        return kw
 
     def _tblock(self, tb, h, hst, S, heads, temporal: bool, kv=None, Fr=None, HW=None):
         """BasicTransformerBlock (util.py:536-540) on rows `h` whose LayerNorm statistics are `hst`."""

@@ -155,7 +155,7 @@ class GnArena:
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
               silu: bool, x2: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
               stats: Optional[torch.Tensor] = None, reduce_fn=None, stat_rows: int = 0,
-              scratch: Optional["GnArena"] = None) -> torch.Tensor:
+              scratch: Optional["GnArena"] = None, peer=None) -> torch.Tensor:
     """GroupNorm(32) over [x1 | x2] rows, statistics per chunk of `rows_per_batch` rows, optional SiLU.
     `reduce_fn(stats)` (e.g. an all-reduce over pixel shards) runs between the statistics and apply kernels;
     `stat_rows` is then the global number of rows per chunk.  With a `scratch` arena (and no reduction) the
@@ -171,6 +171,25 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
         raise ValueError("groupnorm: rows not divisible by rows_per_batch")
     L = _lib.lib()
     st = _stream()
+    if scratch is not None and peer is not None and _gn_smem_fits(x1.device, rows_per_batch, nbatch, C1 + C2):
+        # multi-GPU pixel-sharded chunk: single-pass kernel with the cross-GPU statistics sum inside (NVLink peer memory)
+        if out is None:
+            out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
+        ar = peer.peer
+        d_off = ar.take_data(peer.world * nbatch * 64 * 8)
+        c_off = ar.take_ctrl(nbatch * 64 + 64)               # [nbatch][16] u32 flags, then [nbatch] u32 epochs
+        gp = _lib.GnPeer()
+        gp.world, gp.rank, gp.stat_rows = peer.world, peer.rank, int(stat_rows)
+        for q in range(peer.world):
+            gp.slots[q] = ar.base[q] + d_off
+            gp.flags[q] = ar.base[q] + c_off
+        gp.epoch = ar.base[peer.rank] + c_off + nbatch * 64
+        check(L.vmv_groupnorm_fused_peer(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
+                                         rows_per_batch, nbatch, scratch.take(nbatch), gamma.data_ptr(), beta.data_ptr(),
+                                         float(eps), int(silu), out.data_ptr(), out.stride(0), ctypes.byref(gp), st),
+              "vmv_groupnorm_fused_peer")
+        peer.peer_ops += 1
+        return out
     if scratch is not None and reduce_fn is None:
         if out is None:
             out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
@@ -202,6 +221,24 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
                                 float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
     _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))     # stats read + apply read + write
     return out
+
+
+_SM_COUNT = {}
+
+
+def _gn_smem_fits(device, rows_per_batch: int, nbatch: int, C: int) -> bool:
+    """Mirror of the dispatch in vmv_groupnorm_fused (norm.cu): does the smem-resident single-pass kernel take this shape?"""
+    import os
+    if os.environ.get("VMV_GN_SMEM", "1") == "0" or C > 4096 or nbatch > 16:
+        return False
+    sms = _SM_COUNT.get(device)
+    if sms is None:
+        sms = _SM_COUNT[device] = torch.cuda.get_device_properties(device).multi_processor_count
+    if nbatch > sms:
+        return False
+    cpb = min(sms // nbatch, rows_per_batch)
+    rpc = -(-rows_per_batch // cpb)
+    return rpc * C * 2 <= 227 * 1024 - 2048
 
 
 def layernorm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -104,6 +104,9 @@ class ShardCtx:
         if mode not in ("peer", "gather", "a2a"):
             raise ValueError(f"VMV_SHARD_EXCHANGE={mode!r}: expected peer, gather or a2a")
         self.mode = mode
+        # 5-D GroupNorm in the pixel layout: "1" = one smem-resident kernel with the cross-GPU statistics sum inside
+        # (vmv_groupnorm_fused_peer); "0" = statistics kernel + peer all-reduce kernel + apply kernel
+        self.fused_gn = os.environ.get("VMV_SHARD_FUSED_GN", "1") != "0"
         self.peer: Optional[PeerArena] = None
         if mode == "peer":
             if self.world > 8:
