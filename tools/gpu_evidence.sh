@@ -1,6 +1,6 @@
 #!/bin/bash
 # Final evidence run: full GPU test suite, full bench (t2v256), quick benches of the other configs, launch list with DRAM traffic.
-tag=${1:-s8}
+tag=${1:-ev}
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 t0=$(date +%s)

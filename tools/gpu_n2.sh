@@ -1,5 +1,5 @@
 #!/bin/bash
-tag=${1:-n2b}
+tag=${1:-n2}
 cd "${GRAFT_REPO_ROOT:-/root/repo}"
 mkdir -p gpurun_out
 t0=$(date +%s)

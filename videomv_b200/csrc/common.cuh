@@ -123,12 +123,6 @@ __device__ __forceinline__ float2 unpack_half2(uint32_t u) {
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-// 128-bit shared-memory load by 32-bit shared address (pointers derived from the manually aligned dynamic smem base lose
-// their address space and would compile to scalar generic LD.E)
-__device__ __forceinline__ void lds128(uint32_t addr, float (&v)[4]) {
-    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr) : "memory");
-}
-
 __device__ __forceinline__ bool elect_one() {
     uint32_t pred = 0;
     asm volatile(
