@@ -251,9 +251,12 @@ int vmv_peer_allreduce_f64(const vmv_peer_allreduce_params* p, void* stream);
 int vmv_ipc_export(const void* ptr, void* handle64, int64_t* offset);
 int vmv_ipc_import(const void* handle64, int64_t offset, void** out);
 
-/* sizeof() of the two parameter structs as compiled, so a foreign-language binding can verify its mirror. */
+/* sizeof() of the parameter structs as compiled, so a foreign-language binding can verify its mirrors. */
 int vmv_sizeof_gemm_params(void);
 int vmv_sizeof_attn_params(void);
+int vmv_sizeof_peer_exchange_params(void);
+int vmv_sizeof_peer_allreduce_params(void);
+int vmv_sizeof_gn_peer(void);
 
 #ifdef __cplusplus
 }

@@ -53,6 +53,9 @@ def test_library_exports_every_declared_symbol():
     assert _lib.lib().vmv_abi_version() == 4
     assert ctypes.sizeof(_lib.GemmParams) == _lib.lib().vmv_sizeof_gemm_params()
     assert ctypes.sizeof(_lib.AttnParams) == _lib.lib().vmv_sizeof_attn_params()
+    assert ctypes.sizeof(_lib.PeerExchangeParams) == _lib.lib().vmv_sizeof_peer_exchange_params()
+    assert ctypes.sizeof(_lib.PeerAllreduceParams) == _lib.lib().vmv_sizeof_peer_allreduce_params()
+    assert ctypes.sizeof(_lib.GnPeer) == _lib.lib().vmv_sizeof_gn_peer()
 
 
 def test_cpu_call_fails_loudly():

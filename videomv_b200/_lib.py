@@ -124,6 +124,9 @@ SYMBOLS = {
     "vmv_launch_count": (ctypes.c_longlong, []),
     "vmv_sizeof_gemm_params": (ctypes.c_int, []),
     "vmv_sizeof_attn_params": (ctypes.c_int, []),
+    "vmv_sizeof_peer_exchange_params": (ctypes.c_int, []),
+    "vmv_sizeof_peer_allreduce_params": (ctypes.c_int, []),
+    "vmv_sizeof_gn_peer": (ctypes.c_int, []),
     "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
     "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
@@ -171,7 +174,10 @@ def lib() -> ctypes.CDLL:
     if L.vmv_abi_version() != 4:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
     if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
-            L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams)):
+            L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams) or
+            L.vmv_sizeof_peer_exchange_params() != ctypes.sizeof(PeerExchangeParams) or
+            L.vmv_sizeof_peer_allreduce_params() != ctypes.sizeof(PeerAllreduceParams) or
+            L.vmv_sizeof_gn_peer() != ctypes.sizeof(GnPeer)):
         raise RuntimeError("videomv_b200: ctypes struct mirrors do not match the compiled vmv_*_params layouts")
     _LIB = L
     return L
