@@ -612,7 +612,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         // Bias / LayerNorm column sums of this warp's columns are fetched ONE TILE AHEAD into registers (<= 128 values per
         // array per warp = 4 per lane) and only copied to the smem scratch at the top of their tile: when the epilogue is
         // the bottleneck (K <= 640) the accumulator is already waiting, and a global-load -> smem-store chain at that point
-        // was the largest stall of the kernel (ncu source view, profiles/r2_ncu_hot_kernels_summary.md).
+        // was the largest stall of the kernel (ncu source view, profiles/r1_s2_ncu_hot_kernels_summary.md).
         // (always staged -- zeros when a pointer is null -- so the math below never reads an unwritten slot)
         const int per = geglu ? 64 : 32;
         float nb[4] = {0.f, 0.f, 0.f, 0.f}, nc[4] = {0.f, 0.f, 0.f, 0.f};
