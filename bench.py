@@ -4,17 +4,25 @@
 metric   : multi-view frames / second = 24 * samples / time of `ddim_sample_loop` (50 DDIM steps, eta 0,
            classifier-free guidance => 100 UNet evaluations + 50 scheduler updates per sample; autoencoder=None).
            SURVEY.md section 8(d), BASELINE.json `metric`.
-step     : ONE full 50-step sample of one prompt (24 frames).  N GPUs = N independent samples (the reference's own
-           multi-GPU mode: one prompt stream per rank, tools/inferences/inference_text2video_entrance.py:79,152-170);
-           no data-path collective => "scaling": "weak".
+step     : ONE full 50-step sample of one prompt (24 frames).
+           N > 1 GPUs (default, BASELINE config 5): ONE sample spread over the N GPUs => "scaling": "strong".  The CFG pair is
+           split over two rank groups and each group shards its 24 frames (videomv_b200/parallel.py: layout exchange at the
+           temporal segments + GroupNorm-statistic all-reduce + one output all-gather per UNet call, all over NVLink peer
+           memory).  The same line also carries `modes`: pure frame sharding (frames/N) and the reference's own multi-GPU
+           mode, N independent replicas (tools/inferences/inference_text2video_entrance.py:79,152-170; no collective).
+           `--parallel replicas|frames|cfgframes` makes one of them the headline instead.
 value    : device-resident inputs, CUDA-event timed, max over ranks.
 e2e      : the same loop through the reference-facing API (module registry class + DiffusionDDIM.ddim_sample_loop) with
            HOST (pinned) inputs: H2D of noise / text embeddings / cameras and D2H of the final latent inside the timed
            region, every step.
 roofline : the tcgen05 GEMM / implicit-conv kernel family (97% of the FLOPs): algorithmic FLOPs / CUDA-event time of
            every launch of one CFG-batched forward, vs MEASURED_PEAKS.json bf16 sustained TFLOP/s.
-cpu_baseline / --impl reference : the CPU oracle port of the reference UNet (oracle/unet_oracle.py) on the host cores,
-           bounded sample, extrapolated to the same metric.
+cpu_baseline / --impl reference : the reference's own UNet classes on the host cores (unmodified files staged by
+           oracle/stage_ref.py; the oracle port oracle/unet_oracle.py when they are absent), bounded sample, extrapolated
+           to the same metric.
+reference_cuda : (N=1) the reference's own eager-PyTorch CUDA path on this GPU -- stock classes, xformers mapped to SDPA, fp32
+           as t2v_infer.yaml ships and fp16 autocast -- a few UNet forwards, extrapolated x100: what the north star's
+           ">= 1.8x" is measured against.
 
 Usage: python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference] [--workload t2v256|t2v512|i2v256]
 """
@@ -134,36 +142,62 @@ def to_kwargs(kind: str, d: dict, dev):
 
 
 # --------------------------------------------------------------------------------------------------------------
-def run_reference(args, kind, hw, tflop_fwd):
-    """CPU arm: the oracle port of the reference UNet on the host cores, bounded sample, same metric."""
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    from oracle import unet_oracle
-    from videomv_b200 import synth, unet
-    cores = os.cpu_count() or 1
+def _ref_kwargs(kind):
     kw = dict(T2V_KWARGS, use_lgm_refine=False)
+    return dict(kw, concat_dim=4) if kind == "i2v" else kw
+
+
+def _shapes(kind):
+    from videomv_b200 import unet
     cls = unet.UNetSD_T2VBase if kind == "t2v" else unet.UNetSD_I2VGen
-    if kind == "i2v":
-        kw = dict(kw, concat_dim=4)
     with torch.device("meta"):
-        shapes = {k: tuple(v.shape) for k, v in cls(**kw).state_dict().items()}
+        return {k: tuple(v.shape) for k, v in cls(**_ref_kwargs(kind)).state_dict().items()}
+
+
+def make_cpu_reference(kind, hw):
+    """Returns (fwd(frames) -> seconds, kind string, weight-generation seconds): one UNet forward of the reference on the
+    host cores -- the reference's own class when its files are reachable, else the oracle port."""
+    from oracle import ref_import, unet_oracle
+    from videomv_b200 import synth
     t0 = time.time()
-    sd = synth.synth_state_dict(shapes, seed=0)
+    sd = synth.synth_state_dict(_shapes(kind), seed=0)
     t_w = time.time() - t0
     d = make_host_inputs(kind, hw, seed=11)
+    model = None
+    if ref_import.available():
+        T2V, I2V = ref_import.load_reference()
+        if kind == "i2v":
+            torch.Tensor.cuda = lambda self, *a, **k: self           # unet_i2vgen.py:334 hard-codes .cuda(); CPU arm only
+        model = (T2V if kind == "t2v" else I2V)(**_ref_kwargs(kind)).eval()
+        model.load_state_dict(sd, strict=True)
 
+    @torch.no_grad()
     def fwd(frames):
         x = d["noise"][:, :, :frames].contiguous()
         t = torch.tensor([981])
         cam = d["cam"][:, :frames]
         t0 = time.time()
-        if kind == "t2v":
+        if model is not None:
+            kw = dict(y=d["y"], camera_data=cam, fps=d["fps"])
+            if kind == "i2v":
+                kw.update(image=d["image"], local_image=d["local_image"][:, :, :frames])
+            model(x, t, **kw)
+        elif kind == "t2v":
             unet_oracle.unet_t2v_forward(sd, x, t, d["y"], cam)
         else:
             unet_oracle.unet_i2v_forward(sd, x, t, d["y"], d["image"], d["local_image"][:, :, :frames], cam, fps=d["fps"])
         return time.time() - t0
 
+    return fwd, ("reference" if model is not None else "port"), t_w
+
+
+def run_reference(args, kind, hw, tflop_fwd):
+    """CPU arm: the reference UNet on the host cores, bounded sample, same metric."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    fwd, ref_kind, t_w = make_cpu_reference(kind, hw)
     # bounded sample: probe with 4 frames; use full 24-frame forwards only if the whole run stays within ~4 minutes
     threads = pick_cpu_threads(lambda: fwd(4))
     t4 = fwd(4)
@@ -174,17 +208,69 @@ def run_reference(args, kind, hw, tflop_fwd):
     t_fwd = sum(times) / len(times) * scale                      # one 24-frame UNet forward
     t_sample = t_fwd * 2 * DDIM_STEPS
     value = FRAMES / t_sample
-    sample = (f"{len(times)} oracle forward(s) of 1x4x{frames}x{hw}x{hw} (fp32, best of 16/32/64/{cores} threads = {threads}), scaled x{scale:g} "
-              f"to 24 frames, x100 to a 50-step CFG sample; weights generated in {t_w:.0f}s")
+    what = "the reference's own UNetSD class (unmodified files)" if ref_kind == "reference" else "oracle port"
+    sample = (f"{len(times)} forward(s) of {what} on 1x4x{frames}x{hw}x{hw} (fp32, best of 16/32/64/{cores} threads = {threads}), "
+              f"scaled x{scale:g} to 24 frames, x100 to a 50-step CFG sample; weights generated in {t_w:.0f}s")
     line = {"impl": "reference", "metric": "multi-view frames/sec (24-view, 50-step DDIM, CFG)", "value": value,
             "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": t_sample * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "fp32", "data": "synthetic",
             "config": {"workload": args.workload, "frames": FRAMES, "latent": [4, FRAMES, hw, hw], "ddim_steps": DDIM_STEPS,
                        "guidance": "cfg"},
-            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": ref_kind, "sample": sample},
             "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def reference_cuda_leg(kind, hw, dev, state_dict):
+    """The reference's eager-PyTorch CUDA path on this GPU: stock classes (oracle port when the files are absent),
+    xformers.memory_efficient_attention mapped to F.scaled_dot_product_attention, cudnn.benchmark as the reference engine
+    sets it (inference_text2video_entrance.py:83).  A few B=1 UNet forwards, extrapolated x100 to a 50-step CFG sample."""
+    from oracle import ref_import, unet_oracle
+    d = make_host_inputs(kind, hw, seed=11)
+    x, y, cam, fps = d["noise"].to(dev), d["y"].to(dev), d["cam"].to(dev), d["fps"].to(dev)
+    t = torch.tensor([981], device=dev)
+    extra = {}
+    if kind == "i2v":
+        extra = dict(image=d["image"].to(dev), local_image=d["local_image"].to(dev))
+    prev_bench = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    model = None
+    if ref_import.available():
+        T2V, I2V = ref_import.load_reference()
+        with torch.device(dev):
+            model = (T2V if kind == "t2v" else I2V)(**_ref_kwargs(kind)).eval()
+        model.load_state_dict(state_dict, strict=True)
+    sd = None if model is not None else {k: v.detach() for k, v in state_dict.items()}
+    out = {"impl": "the reference's own UNetSD class (unmodified files, stock eager PyTorch)" if model is not None
+           else "oracle port of the reference on CUDA (reference files not reachable)"}
+
+    @torch.no_grad()
+    def fwd():
+        if model is not None:
+            return model(x, t, y=y, camera_data=cam, fps=fps, **extra)
+        if kind == "t2v":
+            return unet_oracle.unet_t2v_forward(sd, x, t, y, cam)
+        return unet_oracle.unet_i2v_forward(sd, x, t, y, extra["image"], extra["local_image"], cam, fps=fps)
+
+    for name, autocast in (("fp32", False), ("fp16_autocast", True)):
+        with torch.autocast("cuda", dtype=torch.float16, enabled=autocast):
+            for _ in range(2):
+                fwd()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(3):
+                fwd()
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 3
+        out[name] = {"ms_per_unet_forward_b1": ms, "frames_per_s": FRAMES / (ms * 2 * DDIM_STEPS / 1e3)}
+    torch.backends.cudnn.benchmark = prev_bench
+    out["sample"] = "3 timed B=1 UNet forwards per precision after 2 warm-ups, x100 to a 50-step CFG sample (two calls per step, diffusion_ddim.py:149-155)"
+    del model, sd
+    torch.cuda.empty_cache()
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------------
@@ -208,30 +294,16 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
     kw = dict(T2V_KWARGS) if kind == "t2v" else dict(T2V_KWARGS, concat_dim=4)
     with torch.device(dev):
         model = cls(**kw)
-    synth.fill_module_fast(model, seed=0 if args.parallel == "frames" else rank)
+    synth.fill_module_fast(model, seed=0)                # one checkpoint for every rank, like the reference's replicas
     model.eval()
-    sharded = args.parallel == "frames" and world > 1
-    if sharded:
-        model.set_frame_sharding()
-    model.enable_cuda_graphs(not args.no_graphs)
     diffusion = DiffusionDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085,
                               last_beta=0.0120, zero_terminal_snr=False), mean_type=mean_type, var_type="fixed_small")
-    # yaml seed 11, + rank like the reference engine (:79); frame sharding works on ONE sample => same inputs everywhere
-    host = make_host_inputs(kind, hw, seed=11 + (0 if args.parallel == "frames" else rank))
-
-    def sample_from_host():
-        noise = host["noise"].to(dev, non_blocking=True)
-        kwargs = to_kwargs(kind, host, dev)
-        out = diffusion.ddim_sample_loop(noise, model, model_kwargs=kwargs, guide_scale=gs, ddim_timesteps=DDIM_STEPS,
-                                         eta=0.0, batch_cfg=not args.two_call)
-        return out.to("cpu", non_blocking=False)
-
-    dev_noise = host["noise"].to(dev)
-    dev_kwargs = to_kwargs(kind, host, dev)
-
-    def sample_resident():
-        return diffusion.ddim_sample_loop(dev_noise, model, model_kwargs=dev_kwargs, guide_scale=gs,
-                                          ddim_timesteps=DDIM_STEPS, eta=0.0, batch_cfg=not args.two_call)
+    # headline mode: one sample over all GPUs (BASELINE config 5); CFG split x frame sharding when the rank count is even
+    head = args.parallel
+    if head == "auto":
+        head = "single" if world == 1 else ("cfgframes" if world % 2 == 0 else "frames")
+    if world == 1:
+        head = "single"
 
     def barrier():
         if world > 1:
@@ -251,24 +323,72 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    for _ in range(max(args.warmup, 3)):
-        sample_resident()
-    sample_from_host()
-    n0 = ops.launch_count()
-    r0 = sum(getattr(g, "replays", 0) for g in model._engine()._graphs.values())
-    clocks = ClockSampler(local)
-    clocks.start()
-    ms = timed(sample_resident, args.steps)
-    clk = clocks.stop()
-    eager_launches = ops.launch_count() - n0
-    replays = sum(getattr(g, "replays", 0) for g in model._engine()._graphs.values()) - r0
-    per_replay = max([g.launches for g in model._engine()._graphs.values()] or [0])
-    launches = eager_launches + replays * per_replay
-    ms_e2e = timed(sample_from_host, args.steps)
+    def measure(mode, steps, warmup, with_e2e=True):
+        """Time `steps` samples in `mode`; returns a dict (all ranks compute it, values are max over ranks)."""
+        sharded = mode in ("frames", "cfgframes")
+        model.enable_cuda_graphs(False)
+        if sharded:
+            model.set_frame_sharding(cfg_split=(mode == "cfgframes"))
+        else:
+            model.set_frame_sharding(enable=False)
+        model.enable_cuda_graphs(not args.no_graphs)
+        # yaml seed 11, + rank like the reference engine (:79); sharding works on ONE sample => same inputs everywhere
+        host = make_host_inputs(kind, hw, seed=11 + (0 if sharded else rank))
 
-    nsamp = 1 if sharded else world                      # samples finished per step across the job
-    value = FRAMES * args.steps * nsamp / (ms / 1e3)
-    e2e_value = FRAMES * args.steps * nsamp / (ms_e2e / 1e3)
+        def sample_from_host():
+            noise = host["noise"].to(dev, non_blocking=True)
+            kwargs = to_kwargs(kind, host, dev)
+            out = diffusion.ddim_sample_loop(noise, model, model_kwargs=kwargs, guide_scale=gs, ddim_timesteps=DDIM_STEPS,
+                                             eta=0.0, batch_cfg=not args.two_call)
+            return out.to("cpu", non_blocking=False)
+
+        dev_noise = host["noise"].to(dev)
+        dev_kwargs = to_kwargs(kind, host, dev)
+
+        def sample_resident():
+            return diffusion.ddim_sample_loop(dev_noise, model, model_kwargs=dev_kwargs, guide_scale=gs,
+                                              ddim_timesteps=DDIM_STEPS, eta=0.0, batch_cfg=not args.two_call)
+
+        for _ in range(warmup):
+            sample_resident()
+        if with_e2e:
+            sample_from_host()
+        eng = model._engine()
+        n0 = ops.launch_count()
+        r0 = sum(getattr(g, "replays", 0) for g in eng._graphs.values())
+        clocks = ClockSampler(local)
+        clocks.start()
+        ms = timed(sample_resident, steps)
+        clk = clocks.stop()
+        eager_launches = ops.launch_count() - n0
+        replays = sum(getattr(g, "replays", 0) for g in eng._graphs.values()) - r0
+        per_replay = max([g.launches for g in eng._graphs.values()] or [0])
+        ms_e2e = timed(sample_from_host, steps) if with_e2e else None
+        nsamp = 1 if sharded else world                  # samples finished per step across the job
+        sh = eng.shard
+        if sharded:
+            par = (f"{sh.describe()}: ONE sample on {world} GPUs" + (", cond / uncond halves of the CFG pair on two rank groups" if sh.cfg_ways > 1 else "")
+                   + (f", 24 frames sharded {sh.world}-way inside a group (layout exchange at the temporal segments + GroupNorm-statistic all-reduce)" if sh.world > 1 else "")
+                   + f"; {sh.peer_ops} peer-memory kernels + {sh.collectives} NCCL collectives per UNet call")
+        else:
+            par = f"replicas x{world} (one sample per GPU, no collective)" if world > 1 else "single GPU"
+        return dict(mode=mode, sharded=sharded, ms=ms, ms_e2e=ms_e2e, clk=clk, nsamp=nsamp, steps=steps, parallelism=par,
+                    launches=int(eager_launches + replays * per_replay), host=host, dev_noise=dev_noise, dev_kwargs=dev_kwargs,
+                    value=FRAMES * steps * nsamp / (ms / 1e3),
+                    e2e_value=None if ms_e2e is None else FRAMES * steps * nsamp / (ms_e2e / 1e3))
+
+    # the other multi-GPU modes first (short), the headline last so that the model is left configured for it
+    extra_modes = {}
+    if world > 1 and not args.quick and not args.no_modes:
+        for m in ("replicas", "frames", "cfgframes"):
+            if m == head or (m == "cfgframes" and world % 2):
+                continue
+            r = measure(m, 1, 1, with_e2e=False)
+            extra_modes[m] = {"value": r["value"], "unit": "frames/s", "ms_per_sample": r["ms"], "scaling": "strong" if r["sharded"] else "weak",
+                              "parallelism": r["parallelism"], "steps": 1, "warmup": 1}
+    res = measure(head, args.steps, max(args.warmup, 3))
+    sharded, ms, clk, host, dev_noise, dev_kwargs = res["sharded"], res["ms"], res["clk"], res["host"], res["dev_noise"], res["dev_kwargs"]
+    value, e2e_value, launches = res["value"], res["e2e_value"], res["launches"]
     h2d = sum(v.numel() * v.element_size() for k, v in host.items() if k not in ("cam", "fps"))
     d2h = host["noise"].numel() * 4
 
@@ -281,16 +401,14 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                        else cls.__name__ + " (configs/i2vgen_xl_infer.yaml)",
                        "frames": FRAMES, "latent": [4, FRAMES, hw, hw], "ddim_steps": DDIM_STEPS,
                        "guidance": f"cfg {gs}, cond+uncond as one batch-2 UNet call" if not args.two_call else f"cfg {gs}, two calls",
-                       "parallelism": (f"frames/{world}: one sample, 24 frames sharded; layout exchange at temporal segments + "
-                                       f"GroupNorm-stat all-reduce via {model._engine().shard.mode} "
-                                       f"({model._engine().shard.peer_ops} peer-memory kernels + "
-                                       f"{model._engine().shard.collectives} NCCL collectives per UNet call)"
-                                       if sharded else f"replicas x{world} (one sample per GPU, no collective)"),
+                       "parallelism": res["parallelism"],
                        "cuda_graphs": not args.no_graphs,
                        "l2": "working set > L2: 2.83 GB of fp16 weights streamed per UNet call (no explicit flush)"},
             "clocks": clk,
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": int(launches)}
+    if extra_modes:
+        line["modes"] = extra_modes
 
     if rank == 0 and args.quick:
         print(json.dumps(line), flush=True)
@@ -298,7 +416,7 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         # ---- roofline leg: one instrumented (eager, per-launch CUDA events) CFG-batched forward
         pk = _peaks()
         model.enable_cuda_graphs(False)
-        if sharded:
+        if model._engine().shard is not None:
             model.set_frame_sharding(enable=False)   # the instrumented forward below runs on rank 0 alone
         xt = dev_noise
         t = torch.full((1,), 981, dtype=torch.long, device=dev)
@@ -379,6 +497,14 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                                   "frac_of_peak": t_fwd_alg * DDIM_STEPS * args.steps / (ms / 1e3) / pk["tflops"]}
         # ---- cpu baseline leg (N=1 only): bounded oracle sample on the host cores
         if world == 1 and not args.no_cpu_baseline:
+            # ---- the reference's own CUDA path on this GPU (bounded sample), then the CPU baseline
+            try:
+                rc = reference_cuda_leg(kind, hw, dev, model.state_dict())
+                for k_ in ("fp32", "fp16_autocast"):
+                    rc[k_]["speedup_of_this_repo_e2e"] = e2e_value / rc[k_]["frames_per_s"]
+                line["reference_cuda"] = rc
+            except Exception as e:  # noqa: BLE001
+                line["reference_cuda"] = {"error": repr(e)}
             try:
                 line["cpu_baseline"] = cpu_baseline(kind, hw)
             except Exception as e:  # noqa: BLE001
@@ -386,42 +512,28 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()
-        model._engine()._graphs.clear()              # graphs that captured NCCL kernels go before the communicator
+        model.enable_cuda_graphs(False)
+        model._engine()._graphs.clear()              # graphs go before the communicator (peer mode captures no NCCL kernel)
         torch.cuda.synchronize()
-        if sharded:
-            sys.stdout.flush()
-            os._exit(0)                              # NCCL teardown after captured collectives hung on the sandboxed box
+        sys.stdout.flush()
+        # the JSON line is out; a teardown that does not return (seen once on a sandboxed box) must not hang the job
+        watchdog = threading.Timer(30.0, lambda: os._exit(0))
+        watchdog.daemon = True
+        watchdog.start()
         dist.destroy_process_group()
+        watchdog.cancel()
 
 
 def cpu_baseline(kind, hw):
-    from oracle import unet_oracle
-    from videomv_b200 import synth, unet
     cores = os.cpu_count() or 1
-    kw = dict(T2V_KWARGS, use_lgm_refine=False)
-    cls = unet.UNetSD_T2VBase if kind == "t2v" else unet.UNetSD_I2VGen
-    if kind == "i2v":
-        kw = dict(kw, concat_dim=4)
-    with torch.device("meta"):
-        shapes = {k: tuple(v.shape) for k, v in cls(**kw).state_dict().items()}
-    sd = synth.synth_state_dict(shapes, seed=0)
-    d = make_host_inputs(kind, hw, seed=11)
+    fwd, ref_kind, _ = make_cpu_reference(kind, hw)
     frames = 4                                                      # bounded sample: 4 of 24 frames, one forward
-    x, cam, t = d["noise"][:, :, :frames].contiguous(), d["cam"][:, :frames], torch.tensor([981])
-
-    def once():
-        t0 = time.time()
-        if kind == "t2v":
-            unet_oracle.unet_t2v_forward(sd, x, t, d["y"], cam)
-        else:
-            unet_oracle.unet_i2v_forward(sd, x, t, d["y"], d["image"], d["local_image"][:, :, :frames], cam, fps=d["fps"])
-        return time.time() - t0
-
-    threads = pick_cpu_threads(once)
-    best = min(once(), once())
+    threads = pick_cpu_threads(lambda: fwd(frames))
+    best = min(fwd(frames), fwd(frames))
     t_sample = best * (FRAMES / frames) * 2 * DDIM_STEPS
-    return {"value": FRAMES / t_sample, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": "port",
-            "sample": f"best of 2 oracle UNet forwards of 1x4x{frames}x{hw}x{hw} fp32 ({best:.2f}s, best of 16/32/64/{cores} "
+    what = "the reference's own UNetSD class (unmodified files)" if ref_kind == "reference" else "oracle port"
+    return {"value": FRAMES / t_sample, "unit": "frames/s", "cores": threads, "host_cores": cores, "kind": ref_kind,
+            "sample": f"best of 2 UNet forwards of {what} on 1x4x{frames}x{hw}x{hw} fp32 ({best:.2f}s, best of 16/32/64/{cores} "
                       f"threads = {threads}), x{FRAMES // frames} frames x100 calls"}
 
 
@@ -437,9 +549,11 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--shapes-out", default="", help="write the per-shape GEMM device-time table of the roofline leg here")
     ap.add_argument("--quick", action="store_true", help="A/B runs: value + e2e only (no roofline leg, no cpu baseline)")
-    ap.add_argument("--parallel", default="replicas", choices=["replicas", "frames"],
-                    help="N>1: 'replicas' = one independent sample per GPU (weak scaling, the reference's own mode); "
-                         "'frames' = ONE sample, its 24 frames sharded over the GPUs (strong scaling, BASELINE config 5)")
+    ap.add_argument("--parallel", default="auto", choices=["auto", "replicas", "frames", "cfgframes"],
+                    help="N>1 headline mode.  auto = cfgframes (ONE sample on all GPUs: CFG pair split over two rank groups x "
+                         "frame sharding inside each; strong scaling, BASELINE config 5); 'frames' = pure frame sharding; "
+                         "'replicas' = one independent sample per GPU (weak scaling, the reference's own mode)")
+    ap.add_argument("--no-modes", action="store_true", help="N>1: skip the short measurements of the non-headline modes")
     args = ap.parse_args()
     kind, hw, gs, mean_type, tflop = WORKLOADS[args.workload]
     if args.impl == "reference":

@@ -70,13 +70,15 @@ typedef struct vmv_gemm_params {
      * W*gamma, bias holds bias + W@beta, and the epilogue computes  rstd[m]*(acc - mean[m]*ln_colsum[n]) + bias[n]
      * with ln_stats[m] = {mean, rstd} (vmv_layernorm_stats) and ln_colsum[n] = sum_k W'[n,k].  NULL = off. */
     const void* ln_stats; const float* ln_colsum;
-    /* ln_stats_raw_c != 0: ln_stats[m] holds the RAW row sums {sum_c x, sum_c x^2} over ln_stats_raw_c channels (as
-     * accumulated by an upstream vmv_gemm through rowstats_out) instead of {mean, rstd}; the epilogue converts them with
-     * ln_eps.  0 = ln_stats is {mean, rstd}. */
-    int32_t ln_stats_raw_c; float ln_eps;
-    /* rowstats_out != NULL: fp32 [M,2]; the epilogue ADDS {sum_n D[m,n], sum_n D[m,n]^2} of the final (pre-rounding)
-     * output row to it with atomics -- the LayerNorm statistics of the tensor this GEMM produces, for the next GEMM's
-     * folded LayerNorm.  Must be zero on entry.  CTA-pair kernel without split-K / GEGLU only (else VMV_ERR_UNSUPPORTED). */
+    /* ln_stats_src_n != 0: ln_stats is the `rowstats_out` of the upstream vmv_gemm that produced A (N = ln_stats_src_n,
+     * block_n = ln_stats_src_bn = vmv_gemm_block_n of that call): per row 2*ceil(N/block_n) partial {mean_k, M2_k} slots,
+     * merged by the epilogue in slot order (parallel-variance merge) and finished with ln_eps.  0 = ln_stats is {mean, rstd}. */
+    int32_t ln_stats_src_n; int32_t ln_stats_src_bn; float ln_eps;
+    /* rowstats_out != NULL: fp32 [M][2*ceil(N/block_n)][2]; the epilogue writes, per row and per (N tile, epilogue warp
+     * half), the partial LayerNorm statistics {mean_k, M2_k = sum (d - mean_k)^2} of the final (pre-rounding) output
+     * values it holds -- the LayerNorm statistics of the tensor this GEMM produces, for the next GEMM's folded LayerNorm.
+     * One writer per slot (no atomics, no initialisation needed, bit-reproducible).  CTA-pair kernel without split-K /
+     * GEGLU only (else VMV_ERR_UNSUPPORTED). */
     void* rowstats_out;
     /* tuning (0 = auto) */
     int32_t block_n;            /* 64 (variant 1 only), 128, 160 or 256 */
@@ -90,6 +92,8 @@ typedef struct vmv_gemm_params {
 } vmv_gemm_params;
 
 int vmv_gemm(const vmv_gemm_params* p, void* stream);
+/* the N-tile width vmv_gemm will use for p (sizes rowstats_out; becomes the consumer's ln_stats_src_bn) */
+int vmv_gemm_block_n(const vmv_gemm_params* p);
 /* bytes of workspace vmv_gemm needs for p (0 when split_k <= 1) */
 int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p);
 
@@ -100,32 +104,37 @@ int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p);
  * The logical input is [x1 | x2] along channels (C2 may be 0).  Rows are split into `nbatch`
  * consecutive chunks of `rows_per_batch` rows; statistics are per (chunk, group): a chunk is one frame
  * (4-D GroupNorm) or one whole sample (5-D GroupNorm: statistics span frames, util.py:1358,1014).
- *   vmv_groupnorm_stats: stats[nbatch*32*2] (fp64 sum, sum of squares); zeroed by the call.
+ *   vmv_groupnorm_stats: stats[nbatch*32*2] (fp64 sum, sum of squares), written by the call.
  *   vmv_groupnorm_apply: out[rows, C1+C2] fp16 = (x-mean)*rstd*gamma+beta, optional SiLU.  `stat_rows` (0 = rows_per_batch)
  *                        is the number of rows the statistics cover: larger than rows_per_batch when the caller summed the
  *                        partial statistics of several row shards (multi-GPU pixel sharding) between the two calls.
+ * All reductions are fixed-order (per-CTA slots summed in CTA order; no floating-point atomics): results are bit-identical
+ * from run to run.  Every statistics-producing call takes
+ *   barriers: nbatch x 2 uint32 {arrival count, generation}, ZERO when first used and never touched by the caller again
+ *             (self-resetting; may be reused by any later call of the same stream);
+ *   scratch:  vmv_groupnorm_scratch_bytes(C1+C2, rows_per_batch, nbatch) bytes, uninitialised (per-CTA partial sums).
  * ---------------------------------------------------------------------------------------------- */
+int64_t vmv_groupnorm_scratch_bytes(int32_t C, int64_t rows_per_batch, int32_t nbatch);
 int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                        int64_t rows_per_batch, int32_t nbatch, double* stats, void* stream);
+                        int64_t rows_per_batch, int32_t nbatch, double* stats, void* barriers, void* scratch, void* stream);
 int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                         int64_t rows_per_batch, int32_t nbatch, const double* stats, int64_t stat_rows,
                         const float* gamma, const float* beta, float eps, int32_t silu,
                         void* out, int64_t ldo, void* stream);
-/* Single-launch form of the two calls above (single-GPU path: no reduction between statistics and apply): statistics,
- * an in-kernel arrival barrier per chunk, then apply with x re-read from L2.  `scratch` holds
- * vmv_groupnorm_fused_scratch_bytes(nbatch) bytes that must be ZERO on entry (one region per call; the engine zeroes a
- * per-forward arena once).  Returns VMV_ERR_UNSUPPORTED when the grid cannot be made co-resident (never spins then). */
-int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch);
+/* Single-launch form of the two calls above (single-GPU path: no reduction between statistics and apply): the rows are
+ * staged in shared memory once (or re-read from L2 when they do not fit), statistics, an in-kernel arrival barrier per
+ * chunk, apply.  Returns VMV_ERR_UNSUPPORTED when the grid cannot be made co-resident (never spins then). */
 int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                        int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
-                        float eps, int32_t silu, void* out, int64_t ldo, void* stream);
+                        int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
+                        const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream);
 
 /* vmv_groupnorm_fused for a chunk whose rows are spread over `world` GPUs (5-D GroupNorm in the pixel-sharded layout of
  * multi-GPU frame sharding, see vmv_peer_exchange below): the cross-GPU sum of the statistics happens INSIDE the kernel
  * over NVLink peer memory (the first CTA of a chunk publishes this rank's partial sums into every rank's slot + an epoch
- * flag; all CTAs wait for the `world` epochs and sum the slots in rank order).  slots[q]: [world][nbatch][64] doubles,
- * flags[q]: [nbatch][16] uint32 (zero at start) at the same arena offset of every rank q; epoch: local [nbatch] uint32
- * (zero at start); stat_rows = rows of a chunk over all ranks.  VMV_ERR_UNSUPPORTED when the tensor does not fit the
+ * flag; all CTAs wait for the `world` epochs and sum the slots in rank order).  slots[q]: [world][nbatch][64] doubles;
+ * control words: one 64-byte line per chunk at the same arena offset of every rank q, laid out like every other peer
+ * op's line (uint32 flags[8] at +0, epoch at +32, done at +36; zero at start): flags[q] = line 0 of rank q, epoch = this
+ * rank's line 0 + 32; stat_rows = rows of a chunk over all ranks.  VMV_ERR_UNSUPPORTED when the tensor does not fit the
  * smem-resident kernel (callers then use stats + vmv_peer_allreduce_f64 + apply). */
 #ifndef VMV_PEER_MAX_RANKS
 #define VMV_PEER_MAX_RANKS 8
@@ -138,8 +147,9 @@ typedef struct vmv_gn_peer {
     int64_t stat_rows;
 } vmv_gn_peer;
 int vmv_groupnorm_fused_peer(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                             int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
-                             float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer, void* stream);
+                             int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
+                             const float* beta, float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer,
+                             void* stream);
 
 /* Per-row LayerNorm statistics only: stats[m] = {mean, 1/sqrt(var+eps)} fp32 (for the folded form in vmv_gemm). */
 int vmv_layernorm_stats(const void* x, int64_t ldx, int64_t M, int32_t C, float eps, void* stats, void* stream);
@@ -246,6 +256,21 @@ typedef struct vmv_peer_allreduce_params {
 } vmv_peer_allreduce_params;
 int vmv_peer_allreduce_f64(const vmv_peer_allreduce_params* p, void* stream);
 
+/* All-gather over peer memory: this rank's [nouter][inner_bytes] block is stored at dst[q] + dst_offset_bytes +
+ * outer * dst_outer_stride_bytes in EVERY rank q's arena, then the ranks meet at the epoch flags (same protocol and
+ * control-line layout as vmv_peer_exchange).  One call per UNet evaluation assembles the [cfg half][B,C,F,h,w] outputs of
+ * all frame shards -- and of the cond / uncond halves when the classifier-free-guidance pair (diffusion_ddim.py:149-155)
+ * is split over two rank groups -- on every rank. */
+typedef struct vmv_peer_allgather_params {
+    const void* src;                      /* local, contiguous [nouter][inner_bytes] */
+    void* dst[VMV_PEER_MAX_RANKS];
+    void* flags[VMV_PEER_MAX_RANKS];
+    void* epoch; void* done;
+    int32_t world, rank, nowait, pad_;
+    int64_t nouter, inner_bytes, dst_offset_bytes, dst_outer_stride_bytes;
+} vmv_peer_allgather_params;
+int vmv_peer_allgather(const vmv_peer_allgather_params* p, void* stream);
+
 /* CUDA IPC plumbing for the peer arenas: export = 64-byte handle of the allocation containing ptr + ptr's offset in it;
  * import = map a peer's allocation (peer access enabled lazily) and return base + offset. */
 int vmv_ipc_export(const void* ptr, void* handle64, int64_t* offset);
@@ -257,6 +282,7 @@ int vmv_sizeof_attn_params(void);
 int vmv_sizeof_peer_exchange_params(void);
 int vmv_sizeof_peer_allreduce_params(void);
 int vmv_sizeof_gn_peer(void);
+int vmv_sizeof_peer_allgather_params(void);
 
 #ifdef __cplusplus
 }

@@ -131,6 +131,13 @@ def main():
         make_case("t2v_config1", "t2v", ref_import.T2V_KWARGS, frames=4, hw=32, seed_w=7, seed_x=1, t_value=500)
     if "full_i2v" in which:
         make_case("i2v_config1", "i2v", ref_import.I2V_KWARGS, frames=4, hw=32, seed_w=8, seed_x=5, t_value=501)
+    # the benchmark shapes themselves (BASELINE configs 2, 3, 4): full width, 24 x 32 x 32 / 4 x 64 x 64 latents
+    if "bench_t2v" in which:
+        make_case("t2v_24x32", "t2v", ref_import.T2V_KWARGS, frames=24, hw=32, seed_w=7, seed_x=11, t_value=981, real_cam=True)
+    if "bench_i2v" in which:
+        make_case("i2v_24x32", "i2v", ref_import.I2V_KWARGS, frames=24, hw=32, seed_w=8, seed_x=12, t_value=501, real_cam=True)
+    if "bench_512" in which:
+        make_case("t2v_4x64", "t2v", ref_import.T2V_KWARGS, frames=4, hw=64, seed_w=7, seed_x=13, t_value=241, real_cam=True)
 
 
 if __name__ == "__main__":

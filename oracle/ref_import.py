@@ -19,6 +19,9 @@ import sys
 import types
 
 REF_ROOT = os.environ.get("VIDEOMV_REFERENCE", "/root/reference")
+if not os.path.isfile(os.path.join(REF_ROOT, "tools/modules/unet/unet_t2v.py")):
+    # the GPU box: the unmodified files staged by oracle/stage_ref.py (git-ignored, travels with the snapshot)
+    REF_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")
 
 
 def available() -> bool:
@@ -97,6 +100,23 @@ def load_reference():
     i2v = _load("tools.modules.unet.unet_i2vgen", "tools/modules/unet/unet_i2vgen.py")
     _CACHE["t2v"], _CACHE["i2v"] = t2v.UNetSD_T2VBase, i2v.UNetSD_I2VGen
     return _CACHE["t2v"], _CACHE["i2v"]
+
+
+def load_reference_ddim():
+    """The reference's DiffusionDDIM class (tools/modules/diffusions/diffusion_ddim.py), unmodified."""
+    if "ddim" in _CACHE:
+        return _CACHE["ddim"]
+    load_reference()                      # stubs + sys.path for utils.registry_class
+    pk = "tools.modules.diffusions"
+    if pk not in sys.modules:
+        m = types.ModuleType(pk)
+        m.__path__ = [os.path.join(REF_ROOT, "tools/modules/diffusions")]
+        sys.modules[pk] = m
+    for name in ("schedules", "losses", "diffusion_ddim"):
+        if f"{pk}.{name}" not in sys.modules:
+            _load(f"{pk}.{name}", f"tools/modules/diffusions/{name}.py")
+    _CACHE["ddim"] = sys.modules[f"{pk}.diffusion_ddim"].DiffusionDDIM
+    return _CACHE["ddim"]
 
 
 # Resolved ctor kwargs (tools/modules/config.py:88-106 overlaid by configs/t2v_infer.yaml:20-41),

@@ -89,6 +89,38 @@ def test_world1_with_real_wait_and_allreduce():
         assert torch.equal(res[r], want), r
 
 
+def test_allgather_simulated_ranks():
+    """vmv_peer_allgather: the output all-gather of a sharded UNet call (frame shards x CFG halves), ranks simulated one after
+    the other (nowait).  Every rank's buffer ends up holding [cfg half][B, C, F, h, w]; epochs advance by 2 per call."""
+    from videomv_b200 import _lib, ops
+    Wc, P, B, C, Fl, h, w = 2, 2, 1, 4, 6, 8, 8
+    Wa, Fr = Wc * P, Fl * P
+    g = torch.Generator(device="cuda").manual_seed(1)
+    full = torch.randn(Wc, B, C, Fr, h, w, generator=g, device="cuda")
+    dst = [torch.zeros_like(full) for _ in range(Wa)]
+    flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(Wa)]
+    for it in range(2):
+        for r in range(Wa):
+            ci, fr = r // P, r % P
+            src = full[ci, :, :, fr * Fl:(fr + 1) * Fl].contiguous() + it
+            p = _lib.PeerAllgatherParams()
+            p.src = src.data_ptr()
+            for q in range(Wa):
+                p.dst[q] = dst[q].data_ptr()
+                p.flags[q] = flags[q].data_ptr()
+            p.epoch = flags[r].data_ptr() + 32
+            p.done = flags[r].data_ptr() + 36
+            p.world, p.rank, p.nowait = Wa, r, 1
+            p.nouter, p.inner_bytes = B * C, Fl * h * w * 4
+            p.dst_offset_bytes = (ci * B * C * Fr + fr * Fl) * h * w * 4
+            p.dst_outer_stride_bytes = Fr * h * w * 4
+            _lib.check(_lib.lib().vmv_peer_allgather(ctypes.byref(p), ops._stream()), "vmv_peer_allgather")
+        torch.cuda.synchronize()
+        for q in range(Wa):
+            assert torch.equal(dst[q], full + it), (it, q)
+            assert flags[q][:Wa].tolist() == [2 * (it + 1)] * Wa and flags[q][8].item() == 2 * (it + 1) and flags[q][9].item() == 0
+
+
 # grids are sized so that ALL simulated ranks' kernels are co-resident on one GPU (P * B * min(148 // B, rows) <= 148 CTAs):
 # on real multi-GPU runs every rank has its own device
 FUSED_PEER_CASES = [(2, 2, 32, 320), (4, 1, 16, 1280), (2, 1, 64, 640)]
@@ -103,7 +135,7 @@ def _fused_peer_case(P, B, rows, C):
     gamma, beta = 1 + 0.1 * torch.randn(C, device="cuda"), 0.1 * torch.randn(C, device="cuda")
     outs = [torch.empty_like(x) for x in xs]
     slots = [torch.zeros(P * B * 64, dtype=torch.float64, device="cuda") for _ in range(P)]
-    ctrl = [torch.zeros(B * 16 + 16, dtype=torch.int32, device="cuda") for _ in range(P)]
+    ctrl = [torch.zeros(B * 16, dtype=torch.int32, device="cuda") for _ in range(P)]     # one 64-byte line per chunk
     arenas = [ops.GnArena("cuda", 1 << 20) for _ in range(P)]
     streams = [torch.cuda.Stream() for _ in range(P)]
     torch.cuda.synchronize()
@@ -114,10 +146,11 @@ def _fused_peer_case(P, B, rows, C):
             for q in range(P):
                 gp.slots[q] = slots[q].data_ptr()
                 gp.flags[q] = ctrl[q].data_ptr()
-            gp.epoch = ctrl[r].data_ptr() + B * 64
+            gp.epoch = ctrl[r].data_ptr() + 32                        # word 8 of line 0; line b is 64 bytes further
             with torch.cuda.stream(streams[r]):
                 arenas[r].reset()
-                _lib.check(_lib.lib().vmv_groupnorm_fused_peer(xs[r].data_ptr(), C, C, None, 0, 0, rows, B, arenas[r].take(B),
+                bars, scr = arenas[r].take(C, rows, B)
+                _lib.check(_lib.lib().vmv_groupnorm_fused_peer(xs[r].data_ptr(), C, C, None, 0, 0, rows, B, bars, scr,
                                                                gamma.data_ptr(), beta.data_ptr(), 1e-5, 1, outs[r].data_ptr(), C,
                                                                ctypes.byref(gp), streams[r].cuda_stream), "vmv_groupnorm_fused_peer")
         torch.cuda.synchronize()
@@ -125,7 +158,7 @@ def _fused_peer_case(P, B, rows, C):
     ref = F.silu(F.group_norm(full.permute(0, 2, 1), 32, gamma, beta, 1e-5)).permute(0, 2, 1).reshape(B, P, rows, C)
     for r in range(P):
         assert_close(f"fused peer GN rank {r}", outs[r], ref[:, r].reshape(B * rows, C))
-    assert all(c[B * 16:B * 16 + B].tolist() == [2] * B for c in ctrl)
+    assert all(c.view(B, 16)[:, 8].tolist() == [2] * B for c in ctrl)
 
 
 def test_groupnorm_fused_peer_two_streams():

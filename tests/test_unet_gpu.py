@@ -18,13 +18,24 @@ E2E_REL_L2 = 4e-3
 E2E_MAX_ABS = 3e-2
 
 
-def build(meta, seed_w):
+_MODELS = {}
+
+
+def build(meta, seed_w, share=False):
+    """share=True: full-size models (1.4 B parameters, ~40 s of weight synthesis) are built once per (kind, seed)."""
     from videomv_b200 import synth, unet
+    key = (meta["kind"], json.dumps(meta["kwargs"], sort_keys=True), seed_w)
+    if share and key in _MODELS:
+        return _MODELS[key]
     cls = unet.UNetSD_T2VBase if meta["kind"] == "t2v" else unet.UNetSD_I2VGen
     model = cls(**meta["kwargs"])
     sd = synth.synth_state_dict(meta["shapes"], seed=seed_w)
     model.load_state_dict(sd, strict=True)
-    return model.cuda().eval(), sd
+    model = model.cuda().eval()
+    if share:
+        _MODELS.clear()                      # one full-size model resident at a time
+        _MODELS[key] = (model, sd)
+    return model, sd
 
 
 def call(model, meta, d):
@@ -56,18 +67,95 @@ def test_small_models_match_reference_golden(case):
 
 def test_full_size_config1_matches_reference_golden():
     meta, d, _ = load_case("t2v_config1")
-    model, _ = build(meta, meta["seed_w"])
+    model, _ = build(meta, meta["seed_w"], share=True)
     out = call(model, meta, d)
     rel, mx = metrics("t2v_config1 (1.41B params, 1x4x4x32x32) vs reference golden", out, d["ref"])
     assert rel < E2E_REL_L2 and mx < E2E_MAX_ABS
 
 
+# The benchmark shapes themselves (BASELINE configs 2 and 3): full width, 24 x 32 x 32 and 4 x 64 x 64 latents, orbit
+# cameras, against outputs of the UNMODIFIED reference (oracle/gen_golden.py bench_t2v / bench_512).
+@pytest.mark.parametrize("case", ["t2v_24x32", "t2v_4x64"])
+def test_full_size_benchmark_shapes_match_reference_golden(case):
+    meta, d, _ = load_case(case)
+    model, _ = build(meta, meta["seed_w"], share=True)
+    out = call(model, meta, d)
+    rel, mx = metrics(f"{case} (benchmark shape) vs reference golden", out, d["ref"])
+    assert rel < E2E_REL_L2 and mx < E2E_MAX_ABS
+    model.enable_cuda_graphs(True)
+    g1 = call(model, meta, d)
+    g2 = call(model, meta, d)
+    model.enable_cuda_graphs(False)
+    assert torch.equal(g1, g2) and torch.equal(g1, out), "eager, graph capture and graph replay must be bit-identical"
+
+
+def test_fp16_reference_drifts_as_far_as_we_do():
+    """The north-star tolerance (rtol 1e-3 / atol 1e-4) is stated for fp16.  The reference's own fp16 mode is autocast
+    (i2vgen_xl_infer.yaml use_fp16: True, inference_*_entrance.py:243-249).  Evidence that our distance to the fp32 golden
+    is the fp16 storage floor and not an implementation difference: the reference arithmetic (oracle restatement, pinned
+    to the unmodified reference at 2.6e-6) run under torch.autocast(fp16) on the same inputs lands at least as far from
+    the fp32 golden as this implementation does (SURVEY.md section 7 'hard parts', VERDICT r1 weak #1)."""
+    from oracle import unet_oracle
+    meta, d, _ = load_case("t2v_24x32")
+    model, sd = build(meta, meta["seed_w"], share=True)
+    ours = call(model, meta, d).float().cpu()
+    sd_cuda = {k: v.cuda() for k, v in sd.items()}
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        ref16 = unet_oracle.unet_t2v_forward(sd_cuda, d["x"].cuda(), d["t"].cuda(), d["y"].cuda(), d["cam"].cuda(),
+                                             fps=d["fps"].cuda()).float().cpu()
+    del sd_cuda
+    gold = d["ref"]
+    rel_ours = ((ours - gold).norm() / gold.norm()).item()
+    rel_ref16 = ((ref16 - gold).norm() / gold.norm()).item()
+    mx_ours, mx_ref16 = (ours - gold).abs().max().item(), (ref16 - gold).abs().max().item()
+    print(f"[e2e] distance to the fp32 reference golden (24x32x32): ours rel_l2 {rel_ours:.3e} max {mx_ours:.3e} | "
+          f"reference arithmetic under fp16 autocast rel_l2 {rel_ref16:.3e} max {mx_ref16:.3e}")
+    assert rel_ours <= rel_ref16 * 1.05 and mx_ours <= mx_ref16 * 1.5
+
+
 def test_full_size_i2v_config1_matches_reference_golden():
     meta, d, _ = load_case("i2v_config1")
-    model, _ = build(meta, meta["seed_w"])
+    model, _ = build(meta, meta["seed_w"], share=True)
     out = call(model, meta, d)
     rel, mx = metrics("i2v_config1 vs reference golden", out, d["ref"])
     assert rel < E2E_REL_L2 and mx < E2E_MAX_ABS
+
+
+def test_full_size_i2v_benchmark_shape_matches_reference_golden():
+    meta, d, _ = load_case("i2v_24x32")                       # BASELINE config 4
+    model, _ = build(meta, meta["seed_w"], share=True)
+    out = call(model, meta, d)
+    rel, mx = metrics("i2v_24x32 (benchmark shape) vs reference golden", out, d["ref"])
+    assert rel < E2E_REL_L2 and mx < E2E_MAX_ABS
+    _MODELS.clear()
+
+
+def test_new_prompt_is_not_served_from_a_stale_cache():
+    """The reference engines build fresh y tensors per caption (inference_text2video_entrance.py:170,240); after sample A's
+    tensors die, CPython and the caching allocator hand the SAME id() / address to sample B's tensors.  The
+    step-invariant caches must not answer B with A's context (ADVICE r1 high, VERDICT r1 weak #5)."""
+    import gc
+    meta, d, _ = load_case("t2v_small_t981_cam")
+    model, _ = build(meta, meta["seed_w"])
+    cold, _ = build(meta, meta["seed_w"])
+    x, t = d["x"].cuda(), d["t"].cuda()
+    g = torch.Generator().manual_seed(21)
+    prompts = [torch.randn(d["y"].shape, generator=g) for _ in range(6)]
+    uncond = torch.randn(d["y"].shape, generator=g).cuda()
+    seen = set()
+    for i, p in enumerate(prompts):
+        y = p.cuda()                                               # fresh tensor per prompt, freed at the end of the iteration
+        seen.add((id(y), y.data_ptr()))
+        kw_c = dict(y=y, camera_data=d["cam"], fps=d["fps"].cuda())
+        kw_u = dict(y=uncond, camera_data=d["cam"], fps=d["fps"].cuda())
+        out = model(x, t, **kw_c)
+        yo, _ = model.forward_cfg_pair(x, t, kw_c, kw_u)
+        cold.invalidate_engine()                                   # a model that has never seen another prompt
+        want = cold(x, t, y=p.cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
+        assert torch.equal(out, want), f"prompt {i}: forward() answered from a stale conditioning cache"
+        assert metrics(f"prompt {i} cfg pair vs cold model", yo, want)[0] < SELF_REL_L2
+        del y, kw_c, kw_u, out, yo
+        gc.collect()
 
 
 # Two fp16 evaluations of the same function (different batch => different tiling / split-K => different fp32 summation
@@ -90,19 +178,20 @@ def test_graph_replay_and_cfg_pair_match_oracle_and_eager():
     assert metrics("cfg pair cond vs oracle", yo, ref_c)[0] < E2E_REL_L2
     assert metrics("cfg pair uncond vs oracle", uo, ref_u)[0] < E2E_REL_L2
     assert metrics("cfg pair cond vs eager B=1", yo, eager)[0] < SELF_REL_L2
-    # graphs: same kernels in the same order.  Not bit-identical run to run: GroupNorm statistics are reduced with
-    # atomics (fp32 in smem, fp64 in global), so a last-bit difference in a mean can flip fp16 roundings downstream and
-    # two runs sit at the same noise floor apart as two differently-tiled evaluations (measured 2.3e-3).
+    # graphs: same kernels in the same order, and every reduction on the path has a fixed order (GroupNorm: per-CTA slots
+    # summed in CTA order; LayerNorm: per-tile slots merged in slot order; no floating-point atomics), so eager runs,
+    # graph capture and graph replays are bit-identical.
+    assert torch.equal(call(model, meta, d), eager)
     model.enable_cuda_graphs(True)
     g1 = call(model, meta, d)
     g2 = call(model, meta, d)                     # replay
-    assert metrics("graph capture vs eager", g1, eager)[0] < SELF_REL_L2
+    assert torch.equal(g1, eager) and torch.equal(g2, eager)
     assert metrics("graph replay vs oracle", g2, ref_c)[0] < E2E_REL_L2
     x2 = d["x"].cuda() * 0.5
     e3 = model(x2, d["t"].cuda(), **kw_c)
     model.enable_cuda_graphs(False)
     e4 = model(x2, d["t"].cuda(), **kw_c)
-    assert metrics("graph replay (new input) vs eager", e3, e4)[0] < SELF_REL_L2
+    assert torch.equal(e3, e4)
     assert model.graph_launches() > 100
 
 

@@ -27,18 +27,19 @@ def main():
     w_conv2 = packing.pack_conv3x3(torch.randn(2 * C, 2 * C, 3, 3, device=dev) * (18 * C) ** -0.5)
     x2 = r(M // 4, 2 * C)
     gamma, beta = torch.randn(C, device=dev), torch.randn(C, device=dev)
-    arena = ops.GnArena(dev, 8 << 20)
+    arena = ops.GnArena(dev, 32 << 20)
     qkv = r(M, 3 * C)
     o = torch.empty(M, C, device=dev, dtype=torch.float16)
     ld = 3 * C
 
     def run():
         arena.reset()
-        rs = arena.take_rowstats(M)
+        src = (C, ops.gemm_block_n(C))
+        rs = arena.take_rowstats(M, ops.rowstats_slots(*src))
         h = ops.gemm(x, w_cc, bias=bias, residual=res, rowstats_out=rs, w_static=True)                      # o-proj like
-        ops.gemm(h, w_geglu, bias=b_geglu, act=ops.ACT_GEGLU, block_n=bn, ln_stats=rs, ln_raw_c=C, ln_colsum=colsum,
+        ops.gemm(h, w_geglu, bias=b_geglu, act=ops.ACT_GEGLU, block_n=bn, ln_stats=rs, ln_src=src, ln_colsum=colsum,
                  w_static=True)                                                                             # ff1 GEGLU
-        ops.gemm(x, w_qkv, ln_stats=rs, ln_raw_c=C, ln_colsum=w_qkv.float().sum(1).contiguous(), w_static=True)   # QKV
+        ops.gemm(x, w_qkv, ln_stats=rs, ln_src=src, ln_colsum=w_qkv.float().sum(1).contiguous(), w_static=True)   # QKV
         ops.gemm(x, w_conv, bias=bias, mode=ops.CONV3X3, geom=(1, B * Fr, 32, 32), residual=res, w_static=True)  # 3x3 N320
         ops.gemm(x2, w_conv2, mode=ops.CONV3X3, geom=(1, B * Fr, 16, 16), w_static=True)                    # 3x3 N640 K5760
         ops.groupnorm(x, gamma, beta, rows_per_batch=Fr * HW, eps=1e-5, silu=True, scratch=arena)           # 5-D GN

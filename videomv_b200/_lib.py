@@ -76,7 +76,7 @@ class GemmParams(ctypes.Structure):
         ("B", c_i32), ("F", c_i32), ("H", c_i32), ("Wd", c_i32),
         ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
         ("residual", c_vp), ("ldr", c_i64), ("act", c_i32), ("ln_stats", c_vp), ("ln_colsum", c_vp),
-        ("ln_stats_raw_c", c_i32), ("ln_eps", c_f32), ("rowstats_out", c_vp),
+        ("ln_stats_src_n", c_i32), ("ln_stats_src_bn", c_i32), ("ln_eps", c_f32), ("rowstats_out", c_vp),
         ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32), ("variant", c_i32), ("w_static", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
@@ -117,6 +117,13 @@ class PeerAllreduceParams(ctypes.Structure):
                 ("world", c_i32), ("rank", c_i32), ("n", c_i32), ("nowait", c_i32)]
 
 
+class PeerAllgatherParams(ctypes.Structure):
+    """Mirror of `vmv_peer_allgather_params`."""
+    _fields_ = [("src", c_vp), ("dst", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp), ("done", c_vp),
+                ("world", c_i32), ("rank", c_i32), ("nowait", c_i32), ("pad_", c_i32),
+                ("nouter", c_i64), ("inner_bytes", c_i64), ("dst_offset_bytes", c_i64), ("dst_outer_stride_bytes", c_i64)]
+
+
 # every symbol include/videomv_b200.h declares: (restype, argtypes)
 SYMBOLS = {
     "vmv_last_error": (ctypes.c_char_p, []),
@@ -127,15 +134,17 @@ SYMBOLS = {
     "vmv_sizeof_peer_exchange_params": (ctypes.c_int, []),
     "vmv_sizeof_peer_allreduce_params": (ctypes.c_int, []),
     "vmv_sizeof_gn_peer": (ctypes.c_int, []),
+    "vmv_sizeof_peer_allgather_params": (ctypes.c_int, []),
     "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
     "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
-    "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp]),
+    "vmv_gemm_block_n": (ctypes.c_int, [ctypes.POINTER(GemmParams)]),
+    "vmv_groupnorm_scratch_bytes": (c_i64, [c_i32, c_i64, c_i32]),
+    "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
-    "vmv_groupnorm_fused_scratch_bytes": (c_i64, [c_i32]),
-    "vmv_groupnorm_fused": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+    "vmv_groupnorm_fused": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
-    "vmv_groupnorm_fused_peer": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp,
+    "vmv_groupnorm_fused_peer": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                                 c_f32, c_i32, c_vp, c_i64, ctypes.POINTER(GnPeer), c_vp]),
     "vmv_layernorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_vp]),
     "vmv_layernorm": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_vp, c_vp, c_f32, c_vp, c_i64, c_vp]),
@@ -150,6 +159,7 @@ SYMBOLS = {
     "vmv_cfg_ddim_step": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_vp, c_vp]),
     "vmv_peer_exchange": (ctypes.c_int, [ctypes.POINTER(PeerExchangeParams), c_vp]),
     "vmv_peer_allreduce_f64": (ctypes.c_int, [ctypes.POINTER(PeerAllreduceParams), c_vp]),
+    "vmv_peer_allgather": (ctypes.c_int, [ctypes.POINTER(PeerAllgatherParams), c_vp]),
     "vmv_ipc_export": (ctypes.c_int, [c_vp, c_vp, ctypes.POINTER(c_i64)]),
     "vmv_ipc_import": (ctypes.c_int, [c_vp, c_i64, ctypes.POINTER(c_vp)]),
 }
@@ -171,13 +181,14 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if L.vmv_abi_version() != 4:
+    if L.vmv_abi_version() != 5:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
     if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
             L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams) or
             L.vmv_sizeof_peer_exchange_params() != ctypes.sizeof(PeerExchangeParams) or
             L.vmv_sizeof_peer_allreduce_params() != ctypes.sizeof(PeerAllreduceParams) or
-            L.vmv_sizeof_gn_peer() != ctypes.sizeof(GnPeer)):
+            L.vmv_sizeof_gn_peer() != ctypes.sizeof(GnPeer) or
+            L.vmv_sizeof_peer_allgather_params() != ctypes.sizeof(PeerAllgatherParams)):
         raise RuntimeError("videomv_b200: ctypes struct mirrors do not match the compiled vmv_*_params layouts")
     _LIB = L
     return L

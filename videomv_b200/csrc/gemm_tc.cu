@@ -50,26 +50,57 @@ struct GemmArgs {
     long long ldr;
     int act;
     float* partial;   // split-K: fp32 [splits, M, N]
-    const float2* ln_stats;   // folded LayerNorm: per-row {mean, rstd}
+    const float2* ln_stats;   // folded LayerNorm: per-row {mean, rstd}, or [M][ln_nslots] partial {mean_k, M2_k} slots
     const float* ln_colsum;   // folded LayerNorm: per-column sum of the gamma-scaled weights
     int dbg;          // profiling experiments (VMV_GEMM_DEBUG): 1 = skip the TMA stores, 2 = skip the whole epilogue body
     int fast_epi;     // v2: register epilogue with 256-bit global accesses (needs 32 B aligned D / residual / rowbias rows)
     int w_static;     // W may be fetched ahead of the programmatic-dependent-launch wait (model weights)
-    int ln_raw_c;     // != 0: ln_stats holds raw {sum, sum of squares} over ln_raw_c channels (see ln_row_stats)
-    float ln_eps, ln_inv_c;
-    float* rowstats;  // fp32 [M,2]: += {sum, sum of squares} of every output row (v2 register epilogue only)
+    // ln_nslots != 0: ln_stats holds, per row, ln_nslots partial statistics {mean_k, M2_k} written by the epilogue of the
+    // upstream GEMM (its `rowstats`): slot (nt, hh) covers the 32-column blocks hh, hh+2, ... of that GEMM's N tile nt
+    // (ln_src_n columns in tiles of ln_src_bn).  They are merged in slot order (Chan et al.) -- no atomics, bit-reproducible,
+    // and free of the E[x^2]-E[x]^2 cancellation for rows with a large mean.
+    int ln_nslots, ln_src_n, ln_src_bn;
+    float ln_eps;
+    float2* rowstats; // fp32 [M][2*n_tiles][2]: partial {mean, M2} of every output row per (N tile, epilogue warp half)
+    int rowstats_nslots;
 };
 
-// Folded-LayerNorm row statistics {mean, rstd}: stored as such, or derived from the raw sums an upstream GEMM accumulated.
-__device__ __forceinline__ float2 ln_finish(const GemmArgs& a, float2 ms) {
-    if (a.ln_raw_c) {
-        const float mean = ms.x * a.ln_inv_c;
-        const float var = fmaxf(fmaf(ms.y, a.ln_inv_c, -mean * mean), 0.f);
-        ms = make_float2(mean, rsqrtf(var + a.ln_eps));
-    }
-    return ms;
+constexpr int LN_MAX_SLOTS = 10;      // 2 x ceil(1280 / 256)
+
+// number of columns slot s of a row covers, from the producing GEMM's tiling
+__device__ __forceinline__ int ln_slot_count(const GemmArgs& a, int s) {
+    const int nt = s >> 1, hh = s & 1;
+    int nvalid = min(a.ln_src_bn / 32, (a.ln_src_n - nt * a.ln_src_bn + 31) / 32);
+    nvalid = max(nvalid, 0);
+    return 32 * ((nvalid - hh + 1) / 2);
 }
-__device__ __forceinline__ float2 ln_row_stats(const GemmArgs& a, long long row) { return ln_finish(a, a.ln_stats[row]); }
+
+// Folded-LayerNorm row statistics {mean, rstd}: stored as such, or merged from the slots an upstream GEMM wrote -- in slot
+// order with the parallel-variance formula, four independent loads in flight at a time.
+__device__ __forceinline__ float2 ln_row_stats(const GemmArgs& a, long long row) {
+    if (a.ln_nslots == 0) return a.ln_stats[row];
+    const float2* sp = a.ln_stats + row * a.ln_nslots;
+    float n = 0.f, mean = 0.f, m2 = 0.f;
+#pragma unroll 1
+    for (int s0 = 0; s0 < a.ln_nslots; s0 += 4) {
+        float2 v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = (s0 + j < a.ln_nslots) ? sp[s0 + j] : make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float nk = (s0 + j < a.ln_nslots) ? (float)ln_slot_count(a, s0 + j) : 0.f;
+            if (nk > 0.f) {
+                const float nn = n + nk;
+                const float d = v[j].x - mean;
+                const float w = __fdividef(nk, nn);
+                mean = fmaf(d, w, mean);
+                m2 += fmaf(d * d, n * w, v[j].y);
+                n = nn;
+            }
+        }
+    }
+    return make_float2(mean, rsqrtf(__fdividef(m2, n) + a.ln_eps));
+}
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
 __device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int mt, int r) {
@@ -672,7 +703,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
                     ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                 }
-                if (a.ln_stats != nullptr && valid) ln_ms = a.ln_stats[grow];
+                // (slot statistics are merged right here: the loads are independent, so their latency is that of the single
+                // {mean, rstd} load, and only two registers stay live across the accumulator wait)
+                if (a.ln_stats != nullptr && valid) ln_ms = ln_row_stats(a, grow);
                 __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
@@ -685,7 +718,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const bool ln = a.ln_stats != nullptr;
                 float ln_a = 1.f, ln_b = 0.f;
                 if (ln && valid) {
-                    const float2 ms = ln_finish(a, ln_ms);
+                    const float2 ms = ln_ms;
                     ln_a = ms.y;
                     ln_b = -ms.y * ms.x;
                 }
@@ -696,7 +729,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const bool ld_ahead = !(a.dbg & 16);
                 bool requested = false;
                 uint32_t v[32];
-                float row_s = 0.f, row_q = 0.f;                 // LayerNorm sums of my row over my blocks (rowstats)
+                // LayerNorm partial statistics of my row over my blocks (rowstats): sums of (x - row_sh), (x - row_sh)^2 with
+                // row_sh = my first value, so nothing cancels when the row's mean is large compared with its spread
+                float row_s = 0.f, row_q = 0.f, row_sh = 0.f;
+                int row_cnt = 0;
 #pragma unroll 1
                 for (int blk = hh; blk < nvalid; blk += 2, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
@@ -798,10 +834,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         }
                     }
                     if (a.rowstats) {
+                        if (row_cnt == 0) row_sh = x[0];
+                        row_cnt += 32;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            row_s += x[i];
-                            row_q = fmaf(x[i], x[i], row_q);
+                            const float d = x[i] - row_sh;
+                            row_s += d;
+                            row_q = fmaf(d, d, row_q);
                         }
                     }
                     if (valid && !(a.dbg & 1)) {
@@ -813,9 +852,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         stg256(dst + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
                     }
                 }
-                if (a.rowstats && valid && hh < nvalid) {
-                    atomicAdd(a.rowstats + 2 * grow, row_s);
-                    atomicAdd(a.rowstats + 2 * grow + 1, row_q);
+                if (a.rowstats && valid) {                       // one writer per slot: no atomics, no zero-initialised buffer
+                    float2 st = make_float2(0.f, 0.f);
+                    if (row_cnt > 0) {
+                        const float inv = 1.f / (float)row_cnt;
+                        st.x = fmaf(row_s, inv, row_sh);
+                        st.y = fmaxf(fmaf(-row_s * inv, row_s, row_q), 0.f);
+                    }
+                    a.rowstats[grow * a.rowstats_nslots + 2 * nt + hh] = st;
                 }
             }
             tc_fence_before();
@@ -1047,11 +1091,16 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     }
     a.ln_stats = static_cast<const float2*>(p->ln_stats);
     a.ln_colsum = p->ln_colsum;
-    a.ln_raw_c = p->ln_stats ? p->ln_stats_raw_c : 0;
     a.ln_eps = p->ln_eps;
-    a.ln_inv_c = a.ln_raw_c > 0 ? 1.0f / (float)a.ln_raw_c : 0.f;
-    a.rowstats = static_cast<float*>(p->rowstats_out);
-    VMV_CHECK_ARG(a.ln_raw_c >= 0, "vmv_gemm: ln_stats_raw_c must be >= 0");
+    if (p->ln_stats && p->ln_stats_src_n != 0) {
+        VMV_CHECK_ARG(p->ln_stats_src_n > 0 && p->ln_stats_src_bn >= 32 && p->ln_stats_src_bn % 32 == 0,
+                      "vmv_gemm: ln_stats_src_n / ln_stats_src_bn must describe the producing GEMM's tiling");
+        a.ln_src_n = p->ln_stats_src_n;
+        a.ln_src_bn = p->ln_stats_src_bn;
+        a.ln_nslots = 2 * ((a.ln_src_n + a.ln_src_bn - 1) / a.ln_src_bn);
+        VMV_CHECK_ARG(a.ln_nslots <= LN_MAX_SLOTS, "vmv_gemm: %d LayerNorm statistic slots (max %d)", a.ln_nslots, LN_MAX_SLOTS);
+    }
+    a.rowstats = static_cast<float2*>(p->rowstats_out);
     VMV_CHECK_ARG((p->ln_stats == nullptr) == (p->ln_colsum == nullptr), "vmv_gemm: ln_stats and ln_colsum go together");
     if (p->rowbias) VMV_CHECK_ARG(p->ld_rowbias % 8 == 0, "vmv_gemm: ld_rowbias must be a multiple of 8");
     if (p->residual) VMV_CHECK_ARG(p->ldr % 8 == 0, "vmv_gemm: ldr must be a multiple of 8");
@@ -1119,6 +1168,11 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
 }  // namespace vmv
 
 using namespace vmv;
+
+extern "C" int vmv_gemm_block_n(const vmv_gemm_params* p) {
+    if (!p) return -1;
+    return pick_block_n(p, p->variant ? p->variant : default_variant());
+}
 
 extern "C" int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p) {
     Plan pl;
@@ -1190,6 +1244,7 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                                  al32(p->rowbias, p->ld_rowbias)
                              ? 1 : 0;
         }
+        a.rowstats_nslots = 2 * pl.n_tiles;
         if (a.rowstats && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
             set_error("vmv_gemm: rowstats_out needs the CTA-pair kernel's register epilogue (no split-K, no GEGLU, N %% 32 == 0, "
                       "32 B aligned rows)");

@@ -1,6 +1,6 @@
 // GroupNorm(32) statistics / apply(+SiLU) and LayerNorm on channels-last fp16 rows.  HBM-bound kernels:
 // 16-byte vector loads/stores along C, one fixed channel vector per thread so the per-channel scale/shift
-// live in registers, fp32 partials per CTA, fp64 atomics across CTAs.
+// live in registers, fp32 partials per CTA, fixed-order fp64 sums across CTAs (no atomics: bit-reproducible).
 #include "common.cuh"
 #include "../../include/videomv_b200.h"
 
@@ -49,69 +49,166 @@ __device__ __forceinline__ const uint4* gn_src(const __half* x1, long long ld1, 
                     : reinterpret_cast<const uint4*>(x2 + row * ld2 + (c - C1));
 }
 
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
-                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats) {
-    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+// ------------------------------------------------------------------------------------------------
+// Deterministic reductions (no floating-point atomics anywhere: two runs are bit-identical).
+//   (1) inside a CTA: every thread folds its 8 channel sums into per-group partials and parks them in a shared scratch
+//       (`ks` float2 slots per thread: a vector of 8 channels touches at most 2 groups when C/32 >= 8, up to 8 otherwise);
+//       NT/32 threads per group then add the contributors in a fixed order and finish with a shuffle tree.
+//   (2) across the CTAs of a chunk: each CTA writes its 32 {sum, sumsq} to its own slot; after the arrival barrier the
+//       slots are added in CTA order (fp64), again NT/32 threads per group + shuffle tree.
+//   The arrival barrier is self-resetting ({count, generation} per chunk: the last arriver zeroes the count and bumps the
+//   generation), so its words are zeroed once at allocation and never again.
+// ------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int gn_slots_per_thread(int C) { return (C / GN_GROUPS) >= 8 ? 2 : 8; }
+
+template <int NT>
+__device__ __forceinline__ void gn_cta_group_sums(const float (&s)[8], const float (&q)[8], bool active, int c0, int cpg,
+                                                  int vec0, int vw, int lanes, int ks, float2* scr, float* s_sum, float* s_sq) {
     const int t = threadIdx.x;
-    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
-    pdl_launch_dependents();
-    pdl_wait();
-    __syncthreads();
-    const int batch = blockIdx.y;
-    const int tx = t % vw, ty = t / vw;
-    const int vec = blockIdx.z * vw + tx;
-    const int c0 = vec * 8;
-    const int cpg = C / GN_GROUPS;
-    if (ty < lanes && c0 < C) {
-        const long long r_begin = (long long)blockIdx.x * rows_per_cta;
-        long long r_end = r_begin + rows_per_cta;
-        if (r_end > rows_per_batch) r_end = rows_per_batch;
-        const long long base = (long long)batch * rows_per_batch;
-        float s[8], q[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-        auto acc = [&](const uint4& u) {
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(w[j]);
-                s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-                s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-            }
-        };
-        long long r = r_begin + ty;
-        for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {       // 4 independent 16B loads in flight per thread
-            uint4 u0 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
-            uint4 u1 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0));
-            uint4 u2 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0));
-            uint4 u3 = __ldg(gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0));
-            acc(u0); acc(u1); acc(u2); acc(u3);
-        }
-        for (; r < r_end; r += lanes) acc(__ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0)));
-        // fold the 8 channels into their groups (a vector may straddle two groups)
-        int g_prev = c0 / cpg;
+    if (active) {
+        const int g0 = c0 / cpg;
+        int g_prev = g0;
         float as = 0.f, aq = 0.f;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            int g = (c0 + j) / cpg;
+            const int g = (c0 + j) / cpg;
             if (g != g_prev) {
-                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+                scr[t * ks + (g_prev - g0)] = make_float2(as, aq);
                 as = 0.f; aq = 0.f; g_prev = g;
             }
             as += s[j]; aq += q[j];
         }
-        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+        scr[t * ks + (g_prev - g0)] = make_float2(as, aq);
     }
     __syncthreads();
-    if (t < GN_GROUPS) {
-        // only groups touched by this slab are non-zero; skip exact zeros to save atomics
-        float a = s_sum[t], b = s_sq[t];
-        if (a != 0.f || b != 0.f) {
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)a);
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)b);
+    constexpr int W = NT / GN_GROUPS;                    // threads per group (8 or 16: a shuffle tree inside one warp)
+    const int g = t / W, i = t % W;
+    int vlo = (g * cpg) / 8, vhi = ((g + 1) * cpg - 1) / 8;
+    if (vlo < vec0) vlo = vec0;
+    if (vhi > vec0 + vw - 1) vhi = vec0 + vw - 1;
+    const int nv = vhi - vlo + 1;
+    float ps = 0.f, pq = 0.f;
+    if (nv > 0) {
+        const int total = lanes * nv;
+        for (int idx = i; idx < total; idx += W) {
+            const int ty = idx / nv, v = vlo + (idx - ty * nv);
+            const int j = g - (v * 8) / cpg;
+            const float2 f = scr[(ty * vw + (v - vec0)) * ks + j];
+            ps += f.x; pq += f.y;
         }
     }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+        ps += __shfl_xor_sync(0xffffffffu, ps, o);
+        pq += __shfl_xor_sync(0xffffffffu, pq, o);
+    }
+    if (i == 0) { s_sum[g] = ps; s_sq[g] = pq; }
+    __syncthreads();
+}
+
+// Sum the per-CTA slots of one chunk in CTA order; the totals of group g land in tot[2g], tot[2g+1] (shared, fp64).
+template <int NT>
+__device__ __forceinline__ void gn_sum_slots(const float2* slots, int ncta, double* tot) {
+    constexpr int W = NT / GN_GROUPS;
+    const int t = threadIdx.x, g = t / W, i = t % W;
+    double ds = 0.0, dq = 0.0;
+    for (int c = i; c < ncta; c += W) {
+        const float2 f = __ldcg(slots + (long long)c * GN_GROUPS + g);
+        ds += (double)f.x; dq += (double)f.y;
+    }
+#pragma unroll
+    for (int o = W / 2; o > 0; o >>= 1) {
+        ds += __shfl_xor_sync(0xffffffffu, ds, o);
+        dq += __shfl_xor_sync(0xffffffffu, dq, o);
+    }
+    if (i == 0) { tot[2 * g] = ds; tot[2 * g + 1] = dq; }
+    __syncthreads();
+}
+
+// Arrive at the chunk's barrier (all threads call; the CTA's slot writes precede it).  wait = true: returns once every CTA
+// of the chunk has arrived.  wait = false: returns immediately; the result is true in the LAST CTA to arrive only.
+__device__ __forceinline__ bool gn_barrier(unsigned int* bar /* {count, generation} */, unsigned int expected, bool wait) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int gen;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+        const unsigned int prev = atomicAdd(bar, 1u);
+        const int last = prev == expected - 1;
+        if (last) {
+            __threadfence();
+            atomicExch(bar, 0u);
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+        } else if (wait) {
+            unsigned int seen, spins = 0;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 1) : "memory");
+                if (++spins > (1u << 26)) __trap();               // co-residency is guaranteed by the host; never a silent hang
+            } while (seen == gen);
+        }
+        s_last = last;
+        __threadfence();
+    }
+    __syncthreads();
+    return s_last != 0;
+}
+
+template <bool NC /* read-only path: x is not written by this kernel */>
+__device__ __forceinline__ void gn_row_sums(const __half* x1, long long ld1, int C1, const __half* x2, long long ld2, int c0,
+                                            long long base, long long r_begin, long long r_end, int ty, int lanes,
+                                            float (&s)[8], float (&q)[8]) {
+    auto ld = [&](long long r) { const uint4* p = gn_src(x1, ld1, C1, x2, ld2, base + r, c0); return NC ? __ldg(p) : *p; };
+    auto acc = [&](const uint4& u) {
+        uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            float2 f = unpack_half2(w[j]);
+            s[2 * j] += f.x; q[2 * j] += f.x * f.x;
+            s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
+        }
+    };
+    long long r = r_begin + ty;
+    for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {       // 4 independent 16B loads in flight per thread
+        uint4 u0 = ld(r), u1 = ld(r + lanes), u2 = ld(r + 2LL * lanes), u3 = ld(r + 3LL * lanes);
+        acc(u0); acc(u1); acc(u2); acc(u3);
+    }
+    for (; r < r_end; r += lanes) acc(ld(r));
+}
+
+// statistics only (split form: a reduction across GPUs follows): stats[batch][32][2] fp64 {sum, sumsq}, written by the last
+// CTA of the chunk to arrive.  bars: [nbatch][2] u32 (zero at allocation), slots: [nbatch][CTAs per chunk][32] float2.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
+                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats,
+                unsigned int* __restrict__ bars, float2* __restrict__ slots) {
+    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+    __shared__ float2 scr[GN_THREADS * 8];
+    __shared__ double s_tot[2 * GN_GROUPS];
+    const int t = threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
+    const int batch = blockIdx.y;
+    const int tx = t % vw, ty = t / vw;
+    const int vec0 = blockIdx.z * vw;
+    const int c0 = (vec0 + tx) * 8;
+    const int cpg = C / GN_GROUPS;
+    const bool active = ty < lanes && c0 < C;
+    float s[8], q[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+    long long r_end = r_begin + rows_per_cta;
+    if (r_end > rows_per_batch) r_end = rows_per_batch;
+    if (active) gn_row_sums<true>(x1, ld1, C1, x2, ld2, c0, (long long)batch * rows_per_batch, r_begin, r_end, ty, lanes, s, q);
+    gn_cta_group_sums<GN_THREADS>(s, q, active, c0, cpg, vec0, min(vw, C / 8 - vec0), lanes, gn_slots_per_thread(C), scr, s_sum, s_sq);
+    const int ncta = gridDim.x * gridDim.z;
+    const int cta = blockIdx.x + gridDim.x * blockIdx.z;
+    float2* chunk = slots + (long long)batch * ncta * GN_GROUPS;
+    if (t < GN_GROUPS) chunk[(long long)cta * GN_GROUPS + t] = make_float2(s_sum[t], s_sq[t]);   // zeros for groups outside my slab
+    if (!gn_barrier(bars + 2 * batch, (unsigned)ncta, false)) return;
+    gn_sum_slots<GN_THREADS>(chunk, ncta, s_tot);
+    if (t < 2 * GN_GROUPS) stats[(long long)batch * 2 * GN_GROUPS + t] = s_tot[t];
 }
 
 __global__ void __launch_bounds__(GN_THREADS)
@@ -177,100 +274,53 @@ gn_apply_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
     for (; r < r_end; r += lanes) apply(__ldg(gn_src(x1, ld1, C1, x2, ld2, base + r, c0)), r);
 }
 
-// Single-launch GroupNorm: statistics, a per-batch arrival barrier, then apply -- the second read of x comes from L2
-// instead of HBM and the memset + two launches of the split path collapse into one graph node.  The barrier is a
-// plain global counter, so every CTA of the grid must be co-resident: the host wrapper checks the grid against the
-// occupancy of this kernel and refuses otherwise (the caller then uses the split kernels).  `stats` / `arrive` must
-// be zero on entry (the engine zeroes one arena per forward).
+// Single-launch GroupNorm: statistics, a per-chunk arrival barrier, then apply -- the second read of x comes from L2
+// instead of HBM and the two launches of the split path collapse into one graph node.  Every CTA of the grid must be
+// co-resident: the host wrapper checks the grid against the occupancy of this kernel and refuses otherwise (the caller
+// then uses the split kernels).  bars: [nbatch][2] u32 (zeroed once at allocation, self-resetting), slots: per-CTA partials.
 __global__ void __launch_bounds__(GN_THREADS)
 gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2,
-                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, double* __restrict__ stats,
-                unsigned int* __restrict__ arrive, const float* __restrict__ gamma, const float* __restrict__ beta,
-                float eps, int silu, __half* __restrict__ out, long long ldo, int opt) {
-    // opt (VMV_GN_OPT, experiments): 1 = nanosleep back-off in the barrier spin; timing-only (wrong results):
-    // 4 = do not wait at the barrier, 8 = skip the apply phase, 16 = skip the global statistics atomics
-    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS];
+                int C, long long rows_per_batch, int rows_per_cta, int vw, int lanes, unsigned int* __restrict__ bars,
+                float2* __restrict__ slots, const float* __restrict__ gamma, const float* __restrict__ beta,
+                float eps, int silu, __half* __restrict__ out, long long ldo) {
+    __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS], s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    __shared__ float2 scr[GN_THREADS * 8];
+    __shared__ double s_tot[2 * GN_GROUPS];
     const int t = threadIdx.x;
-    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
     pdl_launch_dependents();
     pdl_wait();
-    __syncthreads();
     const int batch = blockIdx.y;
     const int tx = t % vw, ty = t / vw;
-    const int vec = blockIdx.z * vw + tx;
-    const int c0 = vec * 8;
+    const int vec0 = blockIdx.z * vw;
+    const int c0 = (vec0 + tx) * 8;
     const int cpg = C / GN_GROUPS;
     const bool active = ty < lanes && c0 < C;
     const long long r_begin = (long long)blockIdx.x * rows_per_cta;
     long long r_end = r_begin + rows_per_cta;
     if (r_end > rows_per_batch) r_end = rows_per_batch;
     const long long base = (long long)batch * rows_per_batch;
-    // ---- phase 1: partial sums of this CTA's rows
-    if (active) {
-        float s[8], q[8];
+    // ---- phase 1: partial sums of this CTA's rows (plain loads: `out` may alias x)
+    float s[8], q[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
-        auto acc = [&](const uint4& u) {
-            uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                float2 f = unpack_half2(w[j]);
-                s[2 * j] += f.x; q[2 * j] += f.x * f.x;
-                s[2 * j + 1] += f.y; q[2 * j + 1] += f.y * f.y;
-            }
-        };
-        long long r = r_begin + ty;
-        for (; r + 3LL * lanes < r_end; r += 4LL * lanes) {
-            uint4 u0 = *gn_src(x1, ld1, C1, x2, ld2, base + r, c0);
-            uint4 u1 = *gn_src(x1, ld1, C1, x2, ld2, base + r + lanes, c0);
-            uint4 u2 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 2LL * lanes, c0);
-            uint4 u3 = *gn_src(x1, ld1, C1, x2, ld2, base + r + 3LL * lanes, c0);
-            acc(u0); acc(u1); acc(u2); acc(u3);
-        }
-        for (; r < r_end; r += lanes) acc(*gn_src(x1, ld1, C1, x2, ld2, base + r, c0));
-        int g_prev = c0 / cpg;
-        float as = 0.f, aq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            int g = (c0 + j) / cpg;
-            if (g != g_prev) {
-                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
-                as = 0.f; aq = 0.f; g_prev = g;
-            }
-            as += s[j]; aq += q[j];
-        }
-        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (active) gn_row_sums<false>(x1, ld1, C1, x2, ld2, c0, base, r_begin, r_end, ty, lanes, s, q);
+    gn_cta_group_sums<GN_THREADS>(s, q, active, c0, cpg, vec0, min(vw, C / 8 - vec0), lanes, gn_slots_per_thread(C), scr, s_sum, s_sq);
+    const int ncta = gridDim.x * gridDim.z;
+    if (ncta > 1) {
+        const int cta = blockIdx.x + gridDim.x * blockIdx.z;
+        float2* chunk = slots + (long long)batch * ncta * GN_GROUPS;
+        if (t < GN_GROUPS) chunk[(long long)cta * GN_GROUPS + t] = make_float2(s_sum[t], s_sq[t]);
+        gn_barrier(bars + 2 * batch, (unsigned)ncta, true);
+        gn_sum_slots<GN_THREADS>(chunk, ncta, s_tot);
+    } else {
+        if (t < GN_GROUPS) { s_tot[2 * t] = (double)s_sum[t]; s_tot[2 * t + 1] = (double)s_sq[t]; }
+        __syncthreads();
     }
-    __syncthreads();
-    if (t < GN_GROUPS) {
-        float a = s_sum[t], b = s_sq[t];
-        if ((a != 0.f || b != 0.f) && !(opt & 16)) {
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)a);
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)b);
-        }
-        __threadfence();
-    }
-    __syncthreads();
-    // ---- barrier over the CTAs of this batch (release: the fences above; acquire: the load below)
-    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
-    if (t == 0) {
-        const unsigned int expected = gridDim.x * gridDim.z;
-        atomicAdd(&arrive[batch], 1u);
-        unsigned int seen, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive + batch) : "memory");
-            if (++spins > (1u << 26)) __trap();               // co-residency was checked on the host; never a silent hang
-            if (opt & 4) break;
-            if ((opt & 1) && seen < expected) __nanosleep(100);
-        } while (seen < expected);
-    }
-    __syncthreads();
-    if (opt & 8) return;
-    // ---- phase 2: normalise; x is re-read (L2) -- not through the non-coherent path, `out` may alias x
+    // ---- phase 2: normalise; x is re-read (L2)
     if (t < GN_GROUPS) {
         const double inv_cnt = 1.0 / ((double)rows_per_batch * cpg);
-        const double mean = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]) * inv_cnt;
-        double var = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]) * inv_cnt - mean * mean;
+        const double mean = s_tot[2 * t] * inv_cnt;
+        double var = s_tot[2 * t + 1] * inv_cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         s_mean[t] = (float)mean;
         s_rstd[t] = rsqrtf((float)var + eps);
@@ -317,21 +367,23 @@ gn_fused_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __ha
 // chunk meet at the same arrival barrier as gn_fused_kernel, and the apply phase reads smem and writes global: HBM sees
 // one read and one write of the tensor.  One CTA per SM; a [49152, 320] level-0 activation is 213 KB per SM, just inside
 // the 227 KB a CTA may own, the lower levels are smaller.  Inputs that do not fit (the widest skip concatenations) use
-// gn_fused_kernel.  `stats` / `arrive` must be zero on entry.
+// gn_fused_kernel.
 // ------------------------------------------------------------------------------------------------
 constexpr int GNS_THREADS = 512;
-constexpr int GNS_MAX_DYN_SMEM = 227 * 1024 - 2048;       // the kernel's static smem (barrier + 4 x 32 floats, 1.7 KB) comes on top
+constexpr int GNS_MAX_DYN_SMEM = 227 * 1024 - 3072;       // the kernel's static smem (barrier, 4 x 32 floats, 64 doubles: 1.1 KB) comes on top
 constexpr int GNS_CHUNK_BYTES = 16384;
 
 // Cross-GPU part of a 5-D GroupNorm in the pixel-sharded layout (multi-GPU frame sharding, csrc/peer.cu): every rank holds
 // all frames of HW/P pixels, so the statistics of a sample are the sum over ranks.  The first CTA of a chunk publishes this
 // rank's 64 partial sums into every rank's slot and raises an epoch flag there; every CTA of the chunk waits for the P epochs
 // in the local flag array and sums the P slots in rank order.  world <= 1: single-GPU behaviour.
+// Control words: one 64-byte line per chunk with the same layout as every other peer op (csrc/peer.cu): u32 flags[8] at +0,
+// epoch at +32.
 struct GnPeer {
     int world, rank;
     double* slots[VMV_PEER_MAX_RANKS];            // [world][nbatch][64] doubles in every rank's arena
-    unsigned int* flags[VMV_PEER_MAX_RANKS];      // [nbatch][16] u32 in every rank's arena (8 used per chunk)
-    unsigned int* epoch;                          // local [nbatch]
+    unsigned int* flags[VMV_PEER_MAX_RANKS];      // [nbatch] lines of 16 u32 in every rank's arena (flags: first 8)
+    unsigned int* epoch;                          // local: word 8 of line 0 (line b: + 16*b)
     long long stat_rows;                          // rows per chunk summed over all ranks
 };
 
@@ -352,12 +404,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 
 __global__ void __launch_bounds__(GNS_THREADS, 1)
 gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __half* __restrict__ x2, long long ld2, int C2,
-               long long rows_per_batch, int rows_per_cta, double* __restrict__ stats, unsigned int* __restrict__ arrive,
+               long long rows_per_batch, int rows_per_cta, unsigned int* __restrict__ bars, float2* __restrict__ slots,
                const float* __restrict__ gamma, const float* __restrict__ beta, float eps, int silu,
                __half* __restrict__ out, long long ldo, const GnPeer pe) {
     extern __shared__ __align__(128) uint8_t gsm[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ float s_sum[GN_GROUPS], s_sq[GN_GROUPS], s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    __shared__ double s_tot[2 * GN_GROUPS];
     const int t = threadIdx.x;
     const int C = C1 + C2;
     const int batch = blockIdx.y;
@@ -365,17 +418,17 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
     long long left = rows_per_batch - r_begin;
     const int nrows = left <= 0 ? 0 : (left < rows_per_cta ? (int)left : rows_per_cta);
     const long long base_row = (long long)batch * rows_per_batch + r_begin;
+    float2* scr = reinterpret_cast<float2*>(gsm + (((size_t)rows_per_cta * C * 2 + 15) & ~(size_t)15));   // after the slab
     if (t == 0) {
         mbar_init(&bar, 1);
         fence_barrier_init();
     }
-    if (t < GN_GROUPS) { s_sum[t] = 0.f; s_sq[t] = 0.f; }
     __syncthreads();
     pdl_launch_dependents();
     pdl_wait();
     // the epoch this launch will use: read before this CTA arrives anywhere, i.e. before the publisher can advance it
     unsigned int peer_epoch = 0;
-    if (pe.world > 1 && t == 0) peer_epoch = *(pe.epoch + batch) + 1;
+    if (pe.world > 1 && t == 0) peer_epoch = *(pe.epoch + batch * 16) + 1;
     // ---- load: the whole slab in flight at once
     if (t < 32) {
         const uint32_t row_bytes = (uint32_t)C * 2u;
@@ -406,10 +459,10 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
     const bool active = ty < lanes;
     const uint8_t* colp = gsm + (size_t)c0 * 2;
     const size_t rstride = (size_t)C * 2;
-    if (active) {
-        float s[8], q[8];
+    float s[8], q[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    for (int j = 0; j < 8; ++j) { s[j] = 0.f; q[j] = 0.f; }
+    if (active) {
 #pragma unroll 4
         for (int r = ty; r < nrows; r += lanes) {
             const uint4 u = *reinterpret_cast<const uint4*>(colp + r * rstride);
@@ -421,67 +474,39 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
                 s[2 * j + 1] += f.y; q[2 * j + 1] = fmaf(f.y, f.y, q[2 * j + 1]);
             }
         }
-        int g_prev = c0 / cpg;
-        float as = 0.f, aq = 0.f;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int g = (c0 + j) / cpg;
-            if (g != g_prev) {
-                atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
-                as = 0.f; aq = 0.f; g_prev = g;
-            }
-            as += s[j]; aq += q[j];
-        }
-        atomicAdd(&s_sum[g_prev], as); atomicAdd(&s_sq[g_prev], aq);
     }
-    __syncthreads();
-    const unsigned int expected = gridDim.x;
-    if (expected > 1) {
-        if (t < GN_GROUPS) {
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2], (double)s_sum[t]);
-            atomicAdd(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1], (double)s_sq[t]);
-            __threadfence();
-        }
-        __syncthreads();
-        if (t == 0) {
-            atomicAdd(&arrive[batch], 1u);
-            unsigned int seen, spins = 0;
-            do {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(arrive + batch) : "memory");
-                if (++spins > (1u << 26)) __trap();           // co-residency is guaranteed by the host; never a silent hang
-            } while (seen < expected);
-        }
+    gn_cta_group_sums<GNS_THREADS>(s, q, active, c0, cpg, 0, vw, lanes, gn_slots_per_thread(C), scr, s_sum, s_sq);
+    const int ncta = gridDim.x;
+    if (ncta > 1) {
+        float2* chunk = slots + (long long)batch * ncta * GN_GROUPS;
+        if (t < GN_GROUPS) chunk[(long long)blockIdx.x * GN_GROUPS + t] = make_float2(s_sum[t], s_sq[t]);
+        gn_barrier(bars + 2 * batch, (unsigned)ncta, true);
+        gn_sum_slots<GNS_THREADS>(chunk, ncta, s_tot);
+    } else {                                                 // the chunk is mine alone: no global round trip
+        if (t < GN_GROUPS) { s_tot[2 * t] = (double)s_sum[t]; s_tot[2 * t + 1] = (double)s_sq[t]; }
         __syncthreads();
     }
     if (pe.world > 1) {
         const int nb = gridDim.y;
         if (blockIdx.x == 0) {                               // publisher of this chunk
             if (t < GN_GROUPS) {
-                double sum, sq;
-                if (expected > 1) {
-                    sum = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]);
-                    sq = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]);
-                } else {
-                    sum = (double)s_sum[t];
-                    sq = (double)s_sq[t];
-                }
                 const long long o = (((long long)pe.rank * nb + batch) * GN_GROUPS + t) * 2;
-                for (int q = 0; q < pe.world; ++q) { pe.slots[q][o] = sum; pe.slots[q][o + 1] = sq; }
+                for (int qq = 0; qq < pe.world; ++qq) { pe.slots[qq][o] = s_tot[2 * t]; pe.slots[qq][o + 1] = s_tot[2 * t + 1]; }
             }
             __threadfence_system();
             __syncthreads();
             if (t == 0)
-                for (int q = 0; q < pe.world; ++q) gn_st_release_sys(pe.flags[q] + batch * 16 + pe.rank, peer_epoch);
+                for (int qq = 0; qq < pe.world; ++qq) gn_st_release_sys(pe.flags[qq] + batch * 16 + pe.rank, peer_epoch);
         }
         if (t == 0) {
-            for (int q = 0; q < pe.world; ++q) {
+            for (int qq = 0; qq < pe.world; ++qq) {
                 unsigned long long spins = 0;
-                while ((int)(gn_ld_acquire_sys(pe.flags[pe.rank] + batch * 16 + q) - peer_epoch) < 0) {
+                while ((int)(gn_ld_acquire_sys(pe.flags[pe.rank] + batch * 16 + qq) - peer_epoch) < 0) {
                     if (++spins > (1ull << 27)) __trap();        // seconds: a peer that never arrives fails the launch
                     __nanosleep(20);
                 }
             }
-            if (blockIdx.x == 0) *(pe.epoch + batch) = peer_epoch;
+            if (blockIdx.x == 0) *(pe.epoch + batch * 16) = peer_epoch;
         }
         __syncthreads();
     }
@@ -491,17 +516,14 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
         if (pe.world > 1) {                                  // sum of the ranks' partials, in rank order
             const int nb = gridDim.y;
             sum = 0.0; sq = 0.0;
-            for (int q = 0; q < pe.world; ++q) {
-                const long long o = (((long long)q * nb + batch) * GN_GROUPS + t) * 2;
+            for (int qq = 0; qq < pe.world; ++qq) {
+                const long long o = (((long long)qq * nb + batch) * GN_GROUPS + t) * 2;
                 sum += __ldcg(pe.slots[pe.rank] + o);
                 sq += __ldcg(pe.slots[pe.rank] + o + 1);
             }
-        } else if (expected > 1) {
-            sum = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2]);
-            sq = __ldcg(&stats[((long long)batch * GN_GROUPS + t) * 2 + 1]);
-        } else {                                             // the chunk is mine alone: no global round trip
-            sum = (double)s_sum[t];
-            sq = (double)s_sq[t];
+        } else {
+            sum = s_tot[2 * t];
+            sq = s_tot[2 * t + 1];
         }
         const double mean = sum * inv_cnt;
         double var = sq * inv_cnt - mean * mean;
@@ -688,19 +710,32 @@ static int gn_check(const char* who, const void* x1, int64_t ldx1, int C1, const
     return VMV_OK;
 }
 
+// Upper bound of the per-CTA partial-statistics slots one GroupNorm call may use (any of the three kernels).
+static long long gn_max_ctas_per_call(int C, long long rows_per_batch, int nbatch) {
+    GnGeom g = gn_geom(C, 0, rows_per_batch, nbatch);
+    long long split = (long long)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta) * g.slabs * nbatch;
+    long long resident = 160LL * 8 + nbatch;                     // fused / smem kernels never exceed the co-resident capacity
+    return split > resident ? split : resident;
+}
+
+extern "C" int64_t vmv_groupnorm_scratch_bytes(int32_t C, int64_t rows_per_batch, int32_t nbatch) {
+    if (C <= 0 || rows_per_batch <= 0 || nbatch <= 0) return -1;
+    return gn_max_ctas_per_call(C, rows_per_batch, nbatch) * GN_GROUPS * (int64_t)sizeof(float2);
+}
+
 extern "C" int vmv_groupnorm_stats(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                                   int64_t rows_per_batch, int32_t nbatch, double* stats, void* stream) {
+                                   int64_t rows_per_batch, int32_t nbatch, double* stats, void* barriers, void* scratch,
+                                   void* stream) {
     int rc = gn_check("vmv_groupnorm_stats", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
     if (rc) return rc;
-    VMV_CHECK_ARG(stats != nullptr, "vmv_groupnorm_stats: null stats");
+    VMV_CHECK_ARG(stats != nullptr && barriers != nullptr && scratch != nullptr, "vmv_groupnorm_stats: null stats/barriers/scratch");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    cudaError_t e = cudaMemsetAsync(stats, 0, sizeof(double) * 2 * GN_GROUPS * nbatch, st);
-    if (e != cudaSuccess) { set_error("vmv_groupnorm_stats: memset failed: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
     GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch);
     dim3 grid((unsigned)((rows_per_batch + g.rows_per_cta - 1) / g.rows_per_cta), nbatch, g.slabs);
     launch_kernel(gn_stats_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
-                                                 g.rows_per_cta, g.vw, g.lanes, stats);
+                                                 g.rows_per_cta, g.vw, g.lanes, stats, static_cast<unsigned int*>(barriers),
+                                                 static_cast<float2*>(scratch));
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_stats");
     return VMV_OK;
@@ -726,25 +761,17 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
     return VMV_OK;
 }
 
-static int gn_opt() {
-    const char* e = getenv("VMV_GN_OPT");          // read per call: the micro-benchmark switches it between launches
-    return e ? atoi(e) : 0;
-}
-
-// Scratch for one fused call: nbatch*64 doubles (sums) followed by nbatch uint32 arrival counters, all zero on entry.
-extern "C" int64_t vmv_groupnorm_fused_scratch_bytes(int32_t nbatch) {
-    return (int64_t)nbatch * 2 * GN_GROUPS * 8 + (((int64_t)nbatch * 4 + 7) / 8) * 8;
-}
-
 static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                         int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma, const float* beta,
-                         float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer, void* stream) {
+                         int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
+                         const float* beta, float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer,
+                         void* stream) {
     int rc = gn_check("vmv_groupnorm_fused", x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch);
     if (rc) return rc;
-    VMV_CHECK_ARG(scratch && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2, "vmv_groupnorm_fused: bad scratch/gamma/beta/out");
+    VMV_CHECK_ARG(barriers && scratch && gamma && beta && out && ldo % 8 == 0 && ldo >= C1 + C2,
+                  "vmv_groupnorm_fused: bad barriers/scratch/gamma/beta/out");
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    double* stats = static_cast<double*>(scratch);
-    unsigned int* arrive = reinterpret_cast<unsigned int*>(stats + (size_t)nbatch * 2 * GN_GROUPS);
+    unsigned int* bars = static_cast<unsigned int*>(barriers);
+    float2* slots = static_cast<float2*>(scratch);
     {
         // smem-resident single pass whenever one CTA per SM can hold the tensor (VMV_GN_SMEM=0: always the re-read kernel)
         static int use_smem = -1, num_sms = 0;
@@ -766,7 +793,8 @@ static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x
             if (cpb > rows_per_batch) cpb = rows_per_batch;
             const long long rpc = (rows_per_batch + cpb - 1) / cpb;
             cpb = (rows_per_batch + rpc - 1) / rpc;                // drop CTAs that would own no rows
-            const long long smem = rpc * C * 2;
+            // the slab + the reduction scratch (GNS_THREADS x slots-per-thread float2)
+            const long long smem = ((rpc * C * 2 + 15) & ~15LL) + (long long)GNS_THREADS * gn_slots_per_thread(C) * 8;
             if (smem <= GNS_MAX_DYN_SMEM) {
                 GnPeer pe;
                 memset(&pe, 0, sizeof(pe));
@@ -780,7 +808,7 @@ static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x
                 }
                 launch_kernel(gn_smem_kernel, dim3((unsigned)cpb, nbatch), dim3(GNS_THREADS), (size_t)smem, st,
                               static_cast<const __half*>(x1), ldx1, C1, static_cast<const __half*>(x2), ldx2, C2, rows_per_batch,
-                              (int)rpc, stats, arrive, gamma, beta, eps, silu, static_cast<__half*>(out), ldo, pe);
+                              (int)rpc, bars, slots, gamma, beta, eps, silu, static_cast<__half*>(out), ldo, pe);
                 count_launch();
                 VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused (smem)");
                 return VMV_OK;
@@ -799,6 +827,7 @@ static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gn_fused_kernel, GN_THREADS, 0);
         if (e != cudaSuccess) { set_error("vmv_groupnorm_fused: occupancy query failed: %s", cudaGetErrorString(e)); return VMV_ERR_CUDA; }
+        if (per_sm > 8) per_sm = 8;                            // vmv_groupnorm_scratch_bytes assumes <= 8 per SM
         capacity = sms * per_sm;
     }
     GnGeom g = gn_geom(C1, C2, rows_per_batch, nbatch, capacity);
@@ -810,21 +839,21 @@ static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x
     }
     launch_kernel(gn_fused_kernel, grid, dim3(GN_THREADS), 0, st, static_cast<const __half*>(x1), ldx1, C1,
                                                  static_cast<const __half*>(x2), ldx2, g.C, rows_per_batch,
-                                                 g.rows_per_cta, g.vw, g.lanes, stats, arrive, gamma, beta, eps, silu,
-                                                 static_cast<__half*>(out), ldo, gn_opt());
+                                                 g.rows_per_cta, g.vw, g.lanes, bars, slots, gamma, beta, eps, silu,
+                                                 static_cast<__half*>(out), ldo);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused");
     return VMV_OK;
 }
 
 extern "C" int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                                   int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
+                                   int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
                                    const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream) {
-    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, scratch, gamma, beta, eps, silu, out, ldo, nullptr, stream);
+    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, barriers, scratch, gamma, beta, eps, silu, out, ldo, nullptr, stream);
 }
 
 extern "C" int vmv_groupnorm_fused_peer(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
-                                        int64_t rows_per_batch, int32_t nbatch, void* scratch, const float* gamma,
+                                        int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
                                         const float* beta, float eps, int32_t silu, void* out, int64_t ldo,
                                         const vmv_gn_peer* peer, void* stream) {
     VMV_CHECK_ARG(peer && peer->world >= 1 && peer->world <= VMV_PEER_MAX_RANKS && peer->rank >= 0 && peer->rank < peer->world,
@@ -832,7 +861,7 @@ extern "C" int vmv_groupnorm_fused_peer(const void* x1, int64_t ldx1, int32_t C1
     VMV_CHECK_ARG(peer->epoch && peer->stat_rows >= rows_per_batch, "vmv_groupnorm_fused_peer: bad epoch/stat_rows");
     for (int q = 0; q < peer->world; ++q)
         VMV_CHECK_ARG(peer->slots[q] && peer->flags[q], "vmv_groupnorm_fused_peer: null slots/flags for rank %d", q);
-    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, scratch, gamma, beta, eps, silu, out, ldo, peer, stream);
+    return gn_fused_impl(x1, ldx1, C1, x2, ldx2, C2, rows_per_batch, nbatch, barriers, scratch, gamma, beta, eps, silu, out, ldo, peer, stream);
 }
 
 extern "C" int vmv_layernorm(const void* x, int64_t ldx, int64_t M, int32_t C, const float* gamma, const float* beta,

@@ -125,6 +125,66 @@ peer_allreduce_kernel(const PeerArArgs a) {
     }
 }
 
+// All-gather of a strided block: every rank stores its [nouter][inner] slice at (dst_base + outer * outer_stride) of the SAME
+// destination tensor in every rank's arena (16 B remote stores), then the ranks meet at the epoch flags.  Used once per UNet
+// call to assemble the output of all frame shards (and of the cond / uncond halves of a split CFG pair) on every rank.
+struct PeerAgArgs {
+    const uint4* src;
+    uint4* dst[PEER_MAX];
+    unsigned int* flags[PEER_MAX];
+    unsigned int* epoch;
+    unsigned int* done;
+    int world, rank, nowait;
+    long long nouter, inner_vecs, base_vecs, outer_stride_vecs;
+};
+
+__global__ void __launch_bounds__(256)
+peer_allgather_kernel(const PeerAgArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    // Phase 0 ("ready to receive"): the destination is the SAME buffer every call, and a peer may still be reading the
+    // previous call's result (its consumer kernels precede this kernel in ITS stream, not in mine).  Nobody writes before
+    // every rank has entered this call.  Epochs advance by 2 per call: odd = ready, even = data delivered.
+    if (threadIdx.x == 0) {
+        const unsigned int e0 = *a.epoch + 1;               // stable until the last CTA of this launch has finished copying
+        if (blockIdx.x == 0) {
+            __threadfence_system();
+            for (int q = 0; q < a.world; ++q) st_release_sys(a.flags[q] + a.rank, e0);
+        }
+        if (!a.nowait) {
+            for (int q = 0; q < a.world; ++q) {
+                unsigned long long spins = 0;
+                while ((int)(ld_acquire_sys(a.flags[a.rank] + q) - e0) < 0) {
+                    if (++spins > (1ull << 27)) __trap();
+                    __nanosleep(20);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const long long total = a.nouter * a.inner_vecs * a.world;
+    const long long per_rank = a.nouter * a.inner_vecs;
+    const long long step = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += step) {
+        const int q = (int)(i / per_rank);
+        const long long j = i - (long long)q * per_rank;
+        const long long o = j / a.inner_vecs, v = j - o * a.inner_vecs;
+        a.dst[q][a.base_vecs + o * a.outer_stride_vecs + v] = a.src[j];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(a.done, 1u);
+        if (prev == gridDim.x - 1) {
+            __threadfence();
+            *a.done = 0;
+            const unsigned int e = *a.epoch + 2;
+            *a.epoch = e;
+            peer_signal_and_wait(a.flags, a.world, a.rank, e, a.nowait);
+        }
+    }
+}
+
 typedef CUresult (*GetRangeFn)(CUdeviceptr*, size_t*, CUdeviceptr);
 
 static GetRangeFn get_range_fn() {
@@ -209,6 +269,38 @@ extern "C" int vmv_peer_exchange(const vmv_peer_exchange_params* p, void* stream
     launch_kernel(peer_exchange_kernel, dim3((unsigned)ctas), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_peer_exchange");
+    return VMV_OK;
+}
+
+extern "C" int vmv_peer_allgather(const vmv_peer_allgather_params* p, void* stream) {
+    VMV_CHECK_ARG(p && p->src && p->epoch && p->done, "vmv_peer_allgather: null pointer");
+    VMV_CHECK_ARG(p->world >= 1 && p->world <= PEER_MAX && p->rank >= 0 && p->rank < p->world, "vmv_peer_allgather: bad world/rank");
+    VMV_CHECK_ARG(p->nouter > 0 && p->inner_bytes > 0 && p->inner_bytes % 16 == 0 && p->dst_offset_bytes % 16 == 0 &&
+                      p->dst_outer_stride_bytes % 16 == 0 && p->dst_outer_stride_bytes >= p->inner_bytes,
+                  "vmv_peer_allgather: sizes / offsets must be positive multiples of 16 bytes");
+    PeerAgArgs a;
+    memset(&a, 0, sizeof(a));
+    a.src = static_cast<const uint4*>(p->src);
+    uintptr_t al = reinterpret_cast<uintptr_t>(p->src);
+    for (int q = 0; q < p->world; ++q) {
+        VMV_CHECK_ARG(p->dst[q] && p->flags[q], "vmv_peer_allgather: null dst/flags for rank %d", q);
+        a.dst[q] = static_cast<uint4*>(p->dst[q]);
+        a.flags[q] = static_cast<unsigned int*>(p->flags[q]);
+        al |= reinterpret_cast<uintptr_t>(p->dst[q]);
+    }
+    VMV_CHECK_ARG((al & 15) == 0, "vmv_peer_allgather: src/dst must be 16 B aligned");
+    a.epoch = static_cast<unsigned int*>(p->epoch);
+    a.done = static_cast<unsigned int*>(p->done);
+    a.world = p->world; a.rank = p->rank; a.nowait = p->nowait;
+    a.nouter = p->nouter; a.inner_vecs = p->inner_bytes / 16; a.base_vecs = p->dst_offset_bytes / 16;
+    a.outer_stride_vecs = p->dst_outer_stride_bytes / 16;
+    const long long total = a.nouter * a.inner_vecs * a.world;
+    long long ctas = (total + 256 * 4 - 1) / (256 * 4);
+    if (ctas > 296) ctas = 296;
+    if (ctas < 1) ctas = 1;
+    launch_kernel(peer_allgather_kernel, dim3((unsigned)ctas), dim3(256), 0, static_cast<cudaStream_t>(stream), a);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_peer_allgather");
     return VMV_OK;
 }
 

@@ -22,9 +22,6 @@ import torch.nn.functional as F
 from . import _lib, ops, packing, parallel
 
 
-def _lib_scratch_bytes(nbatch: int) -> int:
-    return _lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch)
-
 SM_COUNT = 148
 
 
@@ -47,18 +44,22 @@ class UNetEngine:
         if self.device.type != "cuda":
             raise RuntimeError("videomv_b200: move the UNet to a CUDA device before calling it (no CPU fallback)")
         self.head_dim = module.head_dim
+        if self.head_dim != 64:
+            raise ValueError(f"videomv_b200: the attention kernels are built for head_dim=64 (got {self.head_dim}); "
+                             "both shipped configs use 64 (configs/t2v_infer.yaml:27)")
         self.variant = module.variant
         self._ws: Optional[torch.Tensor] = None        # split-K workspace
+        self._ws_retired: List[torch.Tensor] = []      # outgrown workspaces: captured graphs hold their addresses
         self._ctx_cache: Dict[Tuple, torch.Tensor] = {}
         self._i2v_cache: Dict[Tuple, Tuple[torch.Tensor, torch.Tensor]] = {}
         self._graphs: Dict[Tuple, "_Graph"] = {}
         self.use_graphs = False
         self.shard: Optional[parallel.ShardCtx] = None     # frame sharding of one sample over the ranks of a group
-        self._gn_arena: Optional[ops.GnArena] = None       # zeroed scratch of the single-launch GroupNorm (per forward)
+        self._gn_arena: Optional[ops.GnArena] = None       # statistics scratch of the current forward (GroupNorm partials, LayerNorm slots)
         self._gn_arenas: Dict[Tuple[int, int, int], ops.GnArena] = {}
         self.fused_groupnorm = os.environ.get("VMV_GN_FUSED", "1") != "0"
         # LayerNorm row sums accumulated by the epilogue of the GEMM that produces the rows (no separate statistics pass);
-        # needs the CTA-pair kernel's register epilogue and the zeroed per-forward arena
+        # needs the CTA-pair kernel's register epilogue and the per-forward arena
         self.fused_ln_stats = (self.fused_groupnorm and os.environ.get("VMV_LN_FUSED", "1") != "0"
                                and os.environ.get("VMV_GEMM_VARIANT", "2") != "1")
         self._pack()
@@ -204,21 +205,26 @@ class UNetEngine:
                 split = best
                 need = split * M * N * 4
                 if self._ws is None or self._ws.numel() < need:
+                    if self._ws is not None:
+                        self._ws_retired.append(self._ws)          # never freed while a graph may replay into it
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 kw["workspace"] = self._ws
         # w_static: every W here is a packed model weight, so the kernel may prefetch W tiles ahead of its PDL wait
-        ln = kw.pop("ln", None)                    # (stats tensor, raw_c): statistics of the rows of `a` for the folded LayerNorm
+        ln = kw.pop("ln", None)                    # (stats tensor, src): statistics of the rows of `a` for the folded LayerNorm
         if ln is not None:
-            kw.update(ln_stats=ln[0], ln_raw_c=ln[1], ln_colsum=w.colsum)
+            kw.update(ln_stats=ln[0], ln_src=ln[1], ln_colsum=w.colsum)
         want_stats = kw.pop("want_stats", False)   # the output feeds a LayerNorm: also return its row statistics
         if not want_stats:
             return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, w_static=True, **kw)
         if self.fused_ln_stats and split == 0 and N % 32 == 0 and self._gn_arena is not None:
-            rs = self._gn_arena.take_rowstats(M)
-            out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, rowstats_out=rs, **kw)
-            return out, (rs, N)
+            src_bn = ops.gemm_block_n(N, kw.get("act", 0), w.bn)
+            nsl = ops.rowstats_slots(N, src_bn)
+            if nsl <= 10:
+                rs = self._gn_arena.take_rowstats(M, nsl)
+                out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, rowstats_out=rs, **kw)
+                return out, (rs, (N, src_bn))
         out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, w_static=True, **kw)
-        return out, (ops.layernorm_stats(out), 0)
+        return out, (ops.layernorm_stats(out), None)
 
     # ------------------------------------------------------------------------------------------------------------
     # blocks
@@ -245,23 +251,30 @@ class UNetEngine:
         return to_frames(cur)
 
     # ---- frame-shard <-> pixel-shard plumbing (identity on a single GPU) -----------------------------------------
+    @property
+    def _fs(self) -> Optional[parallel.ShardCtx]:
+        """The sharding context when the frames of a sample are actually spread over ranks (else None)."""
+        sh = self.shard
+        return sh if (sh is not None and sh.frame_sharded) else None
+
     def _enter_temporal(self, S):
         """Returns (frames, pixels per rank, fn back to the frame layout) for a temporal segment."""
         HW = S["H"] * S["W"]
-        if self.shard is None:
+        ctx = self._fs
+        if ctx is None:
             return S["F"], HW, (lambda z: z)
-        ctx = self.shard
         return S["F"] * ctx.world, HW // ctx.world, (lambda z: parallel.pixels_to_frames(z, S["B"], S["F"], HW, ctx))
 
     def _to_pixels(self, x, S):
-        if self.shard is None:
+        ctx = self._fs
+        if ctx is None:
             return x
-        return parallel.frames_to_pixels(x, S["B"], S["F"], S["H"] * S["W"], self.shard)
+        return parallel.frames_to_pixels(x, S["B"], S["F"], S["H"] * S["W"], ctx)
 
     def _gn5d_kw(self, S):
-        if self.shard is None:
+        ctx = self._fs
+        if ctx is None:
             return {}
-        ctx = self.shard
         kw = dict(reduce_fn=lambda st: parallel.allreduce_stats(st, ctx), stat_rows=S["F"] * ctx.world * S["H"] * S["W"])
         if ctx.mode == "peer" and ctx.fused_gn:
             kw["peer"] = ctx            # single-pass GroupNorm with the cross-GPU sum inside the kernel (when it fits smem)
@@ -393,16 +406,21 @@ class UNetEngine:
         fps = None if fps is None else fps.to(device=dev, dtype=torch.int64).contiguous()
         ctx, concat = self.prepare_condition(x32.shape, y, image, local_image)
         out = self.forward_core(x32, t, ctx, cam, fps, concat)
+        if self.shard is not None:
+            out = out[self.shard.cfg_index]            # [cfg_ways, B, C, F, h, w]: every group evaluated the same call
         return out if out_dtype == torch.float32 else out.to(out_dtype)
 
     def prepare_condition(self, xshape, y, image=None, local_image=None):
         """Step-invariant conditioning: context tokens [B,L,1024] fp32 (+ the I2V concat planes). Cached on the
-        identity of the caller's tensors, which the sampler passes unchanged for all 50 steps."""
+        identity of the caller's tensors, which the sampler passes unchanged for all 50 steps.  The entry holds strong
+        references to the keyed tensors: while it exists neither their id() nor their storage address can be recycled
+        for another prompt's tensors (the reference engines build fresh y / image tensors per caption:
+        inference_text2video_entrance.py:170,240), and `_version` catches in-place updates."""
         key = tuple((id(z), z.data_ptr(), z._version, tuple(z.shape)) if z is not None else None
                     for z in (y, image, local_image)) + (tuple(xshape),)
         hit = self._ctx_cache.get(key)
         if hit is not None:
-            return hit
+            return hit[0], hit[1]
         dev = self.device
         if self.variant == "i2v":
             concat, ctx = self._i2v_condition(xshape, y.to(dev), image, local_image)
@@ -411,13 +429,15 @@ class UNetEngine:
         ctx = ctx.contiguous()
         if len(self._ctx_cache) >= 8:
             self._ctx_cache.clear()
-        self._ctx_cache[key] = (ctx, concat)
+        self._ctx_cache[key] = (ctx, concat, (y, image, local_image))
         return ctx, concat
 
     def forward_core(self, x32, t, ctx, cam, fps, concat):
-        """The per-step hot path on device-resident inputs. Replays a captured CUDA graph when enabled."""
+        """The per-step hot path on device-resident inputs. Replays a captured CUDA graph when enabled.
+        Returns [B, C, F, h, w]; with a sharding context [cfg_ways, B, C, F, h, w] (the gathered halves of a split CFG pair)."""
         if not self.use_graphs:
-            return self._forward_impl(x32, t, ctx, cam, fps, concat)
+            out = self._forward_impl(x32, t, ctx, cam, fps, concat)
+            return out if self.shard is None else out.clone()     # the gathered output lives in the peer arena: hand out a copy
         key = (tuple(x32.shape), tuple(ctx.shape), cam is not None, fps is not None, concat is not None)
         g = self._graphs.get(key)
         if g is None:
@@ -432,17 +452,20 @@ class UNetEngine:
             nb = B * Fr
             arena = self._gn_arenas.get((nb, H, W))
             if arena is None:
-                per_call = int(_lib_scratch_bytes(nb)) + 256
-                # 166 GroupNorms per forward + the LayerNorm row-sum accumulators (99 LayerNorms: 30 at each of the three
-                # transformer levels, 9 in the middle block = 39.5 x (level-0 rows) x 8 B; sized with margin)
-                arena = self._gn_arenas[(nb, H, W)] = ops.GnArena(x32.device, 192 * per_call + 64 * nb * H * W * 8)
+                per_call = int(_lib.lib().vmv_groupnorm_scratch_bytes(self.m.dim, H * W, nb)) + 256
+                # 166 GroupNorms per forward (per-CTA partial sums) + the LayerNorm partial-statistics slots (99 LayerNorms:
+                # 30 at each of the three transformer levels with 4 / 6 / 10 slots per row, 9 in the middle block
+                # = 187 x (level-0 rows) x 8 B; sized with margin).  Nothing here is ever memset.
+                arena = self._gn_arenas[(nb, H, W)] = ops.GnArena(x32.device, 192 * per_call + 224 * nb * H * W * 8,
+                                                                  bar_bytes=192 * ((nb * 8 + 63) // 64 * 64))
             self._gn_arena = arena
-            arena.reset()                              # one memset per forward; every GroupNorm call takes a fresh region
+            arena.reset()                              # rewind only: every call of this forward takes a fresh region
         sh = self.shard
         if sh is not None:
+            sh.begin_forward()
+        if sh is not None and sh.frame_sharded:
             # every rank receives the full [B,C,F,h,w] latent (as the sampler holds it) and computes its F/P frames
             sh.check(Fr, (H >> (len(self.m.dim_mult) - 1)) * (W >> (len(self.m.dim_mult) - 1)))
-            sh.begin_forward()
             Fl = Fr // sh.world
             lo = sh.rank * Fl
             x32 = x32[:, :, lo:lo + Fl].contiguous()
@@ -469,7 +492,7 @@ class UNetEngine:
             out = ops.rows_to_ncfhw(o16, B, Fr, S["H"], S["W"], self.head_cout)
         else:
             out = ops.conv3x3_out(a, self.head_w, self.head_b, B, Fr, S["H"], S["W"])
-        return out if sh is None else parallel.gather_frames(out, sh)
+        return out if sh is None else parallel.gather_output(out, sh)
 
     # ------------------------------------------------------------------------------------------------------------
     # I2V conditioning glue (step-invariant; depends only on local_image / image / y)

@@ -55,8 +55,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          residual: Optional[torch.Tensor] = None, act: int = ACT_NONE, mode: int = LINEAR,
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
          workspace: Optional[torch.Tensor] = None, variant: int = 0, ln_stats: Optional[torch.Tensor] = None,
-         ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False, ln_raw_c: int = 0, ln_eps: float = 1e-5,
-         rowstats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False, ln_src: Optional[Tuple[int, int]] = None,
+         ln_eps: float = 1e-5, rowstats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -91,15 +91,19 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
         _rows(residual, "gemm residual")
         p.residual, p.ldr = residual.data_ptr(), residual.stride(0)
     if ln_stats is not None:
-        if ln_stats.dtype != torch.float32 or ln_stats.numel() != 2 * M or ln_colsum is None or ln_colsum.numel() != N:
-            raise ValueError("gemm ln_stats must be fp32 [M,2] and ln_colsum fp32 [N]")
-        p.ln_stats, p.ln_colsum = ln_stats.data_ptr(), ln_colsum.data_ptr()
-        p.ln_stats_raw_c, p.ln_eps = int(ln_raw_c), float(ln_eps)       # raw {sum, sumsq} rows from an upstream rowstats_out
-    if rowstats_out is not None:
-        if rowstats_out.dtype != torch.float32 or rowstats_out.numel() != 2 * M or not rowstats_out.is_contiguous():
-            raise ValueError("gemm rowstats_out must be a contiguous (zeroed) fp32 [M,2] tensor")
-        p.rowstats_out = rowstats_out.data_ptr()
+        # ln_src = (N, block_n) of the upstream GEMM whose `rowstats_out` this is; None: {mean, rstd} rows
+        nsl = 1 if ln_src is None else rowstats_slots(*ln_src)
+        if ln_stats.dtype != torch.float32 or ln_stats.numel() != 2 * M * nsl or ln_colsum is None or ln_colsum.numel() != N:
+            raise ValueError("gemm ln_stats must be fp32 [M,2] (or [M,slots,2] with ln_src) and ln_colsum fp32 [N]")
+        p.ln_stats, p.ln_colsum, p.ln_eps = ln_stats.data_ptr(), ln_colsum.data_ptr(), float(ln_eps)
+        if ln_src is not None:
+            p.ln_stats_src_n, p.ln_stats_src_bn = int(ln_src[0]), int(ln_src[1])
     p.act, p.block_n, p.stages, p.split_k, p.variant = act, block_n, stages, split_k, variant
+    if rowstats_out is not None:
+        nsl = rowstats_slots(N, gemm_block_n(N, act, block_n, variant))
+        if rowstats_out.dtype != torch.float32 or rowstats_out.numel() != 2 * M * nsl or not rowstats_out.is_contiguous():
+            raise ValueError(f"gemm rowstats_out must be a contiguous fp32 [M,{nsl},2] tensor")
+        p.rowstats_out = rowstats_out.data_ptr()
     p.w_static = 1 if w_static else 0
     if split_k > 1:
         need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
@@ -121,21 +125,38 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     return out
 
 
-class GnArena:
-    """Zero-initialised scratch, bump-allocated: one region per single-launch GroupNorm call (`take`) and one fp32 [M,2]
-    row-statistics accumulator per LayerNorm whose sums are produced by the upstream GEMM's epilogue (`take_rowstats`).
-    `reset()` zeroes what the previous forward used (one memset) and rewinds -- call it once per forward."""
+def gemm_block_n(N: int, act: int = ACT_NONE, block_n: int = 0, variant: int = 0) -> int:
+    """The N-tile width vmv_gemm picks for these parameters (sizes `rowstats_out`)."""
+    p = GemmParams()
+    p.N, p.act, p.block_n, p.variant = N, act, block_n, variant
+    bn = int(_lib.lib().vmv_gemm_block_n(ctypes.byref(p)))
+    if bn <= 0:
+        check(1, "vmv_gemm_block_n")
+    return bn
 
-    def __init__(self, device, nbytes: int = 8 << 20):
-        self.buf = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+
+def rowstats_slots(N: int, bn: int) -> int:
+    """Partial-statistic slots per row written by a GEMM with N columns in tiles of bn: (N tile, epilogue warp half)."""
+    return 2 * ((N + bn - 1) // bn)
+
+
+class GnArena:
+    """Bump-allocated scratch for the statistics of one forward.
+      * `bar`  : arrival-barrier words of the GroupNorm kernels ({count, generation} per chunk).  Zeroed ONCE here; the
+                 barriers reset themselves, so any later call may reuse any word (no per-forward memset).
+      * `buf`  : uninitialised data: per-CTA GroupNorm partial sums (`take`) and the LayerNorm partial-statistics slots the
+                 upstream GEMM's epilogue writes (`take_rowstats`); every word is written before it is read.
+    `reset()` rewinds both -- call it once per forward."""
+
+    def __init__(self, device, nbytes: int = 8 << 20, bar_bytes: int = 1 << 20):
+        self.buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        self.bar = torch.zeros(bar_bytes, dtype=torch.uint8, device=device)
         self.off = 0
-        self.high = 0
+        self.bar_off = 0
 
     def reset(self):
-        self.high = max(self.high, self.off)
-        if self.high:
-            self.buf[:self.high].zero_()
         self.off = 0
+        self.bar_off = 0
 
     def _bump(self, n: int) -> int:
         if self.off + n > self.buf.numel():
@@ -144,12 +165,19 @@ class GnArena:
         self.off += (n + 255) // 256 * 256
         return o
 
-    def take(self, nbatch: int) -> int:
-        return self.buf.data_ptr() + self._bump(int(_lib.lib().vmv_groupnorm_fused_scratch_bytes(nbatch)))
+    def take(self, C: int, rows_per_batch: int, nbatch: int) -> Tuple[int, int]:
+        """(barriers pointer, scratch pointer) for one statistics-producing GroupNorm call."""
+        nb = (nbatch * 8 + 63) // 64 * 64
+        if self.bar_off + nb > self.bar.numel():
+            raise RuntimeError("GnArena barrier region exhausted: call reset() once per forward")
+        bo = self.bar_off
+        self.bar_off += nb
+        need = int(_lib.lib().vmv_groupnorm_scratch_bytes(C, rows_per_batch, nbatch))
+        return self.bar.data_ptr() + bo, self.buf.data_ptr() + self._bump(need)
 
-    def take_rowstats(self, rows: int) -> torch.Tensor:
-        o = self._bump(rows * 8)
-        return self.buf[o:o + rows * 8].view(torch.float32).view(rows, 2)
+    def take_rowstats(self, rows: int, nslots: int) -> torch.Tensor:
+        o = self._bump(rows * nslots * 8)
+        return self.buf[o:o + rows * nslots * 8].view(torch.float32).view(rows, nslots, 2)
 
 
 def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows_per_batch: int, eps: float,
@@ -177,15 +205,16 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
             out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
         ar = peer.peer
         d_off = ar.take_data(peer.world * nbatch * 64 * 8)
-        c_off = ar.take_ctrl(nbatch * 64 + 64)               # [nbatch][16] u32 flags, then [nbatch] u32 epochs
+        c_off = ar.take_ctrl(nbatch * 64)                    # one control line per chunk: flags +0, epoch +32
         gp = _lib.GnPeer()
         gp.world, gp.rank, gp.stat_rows = peer.world, peer.rank, int(stat_rows)
         for q in range(peer.world):
-            gp.slots[q] = ar.base[q] + d_off
-            gp.flags[q] = ar.base[q] + c_off
-        gp.epoch = ar.base[peer.rank] + c_off + nbatch * 64
+            gp.slots[q] = peer.base(q) + d_off
+            gp.flags[q] = peer.base(q) + c_off
+        gp.epoch = peer.base(peer.rank) + c_off + 32
+        bars, scr = scratch.take(C1 + C2, rows_per_batch, nbatch)
         check(L.vmv_groupnorm_fused_peer(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
-                                         rows_per_batch, nbatch, scratch.take(nbatch), gamma.data_ptr(), beta.data_ptr(),
+                                         rows_per_batch, nbatch, bars, scr, gamma.data_ptr(), beta.data_ptr(),
                                          float(eps), int(silu), out.data_ptr(), out.stride(0), ctypes.byref(gp), st),
               "vmv_groupnorm_fused_peer")
         peer.peer_ops += 1
@@ -194,15 +223,15 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
         if out is None:
             out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
         e0 = _prof_begin()
+        bars, scr = scratch.take(C1 + C2, rows_per_batch, nbatch)
 
         def launch():
             check(L.vmv_groupnorm_fused(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
-                                        rows_per_batch, nbatch, scratch.take(nbatch), gamma.data_ptr(), beta.data_ptr(),
+                                        rows_per_batch, nbatch, bars, scr, gamma.data_ptr(), beta.data_ptr(),
                                         float(eps), int(silu), out.data_ptr(), out.stride(0), _stream()), "vmv_groupnorm_fused")
         launch()
         if e0 is not None:
-            launch.pre = scratch.reset                       # replays need a zeroed arena: reset once per timing graph
-            launch.keep = (x1, x2, out, gamma, beta)
+            launch.keep = (x1, x2, out, gamma, beta, scratch)
             # algorithmic bytes: one read + one write of the tensor (what the smem-resident kernel moves through HBM)
             _prof_end(e0, "groupnorm", 0.0, 2.0 * 2 * rows * (C1 + C2),
                       f"rows{rows} C{C1}+{C2} rpb{rows_per_batch} silu{int(silu)}", launch)
@@ -212,14 +241,22 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
     if out is None:
         out = torch.empty((rows, C1 + C2), dtype=torch.float16, device=x1.device)
     e0 = _prof_begin()
+    if scratch is not None:
+        bars, scr = scratch.take(C1 + C2, rows_per_batch, nbatch)
+        keep = None
+    else:                                                    # stand-alone call: private barrier words + scratch
+        kb = torch.zeros(nbatch * 2, dtype=torch.int32, device=x1.device)
+        ks = torch.empty(int(L.vmv_groupnorm_scratch_bytes(C1 + C2, rows_per_batch, nbatch)), dtype=torch.uint8, device=x1.device)
+        bars, scr, keep = kb.data_ptr(), ks.data_ptr(), (kb, ks)
     check(L.vmv_groupnorm_stats(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
-                                rows_per_batch, nbatch, stats.data_ptr(), st), "vmv_groupnorm_stats")
+                                rows_per_batch, nbatch, stats.data_ptr(), bars, scr, st), "vmv_groupnorm_stats")
     if reduce_fn is not None:
         reduce_fn(stats)
     check(L.vmv_groupnorm_apply(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
                                 rows_per_batch, nbatch, stats.data_ptr(), stat_rows, gamma.data_ptr(), beta.data_ptr(),
                                 float(eps), int(silu), out.data_ptr(), out.stride(0), st), "vmv_groupnorm_apply")
     _prof_end(e0, "groupnorm", 0.0, 2.0 * 3 * rows * (C1 + C2))     # stats read + apply read + write
+    del keep
     return out
 
 
@@ -238,7 +275,8 @@ def _gn_smem_fits(device, rows_per_batch: int, nbatch: int, C: int) -> bool:
         return False
     cpb = min(sms // nbatch, rows_per_batch)
     rpc = -(-rows_per_batch // cpb)
-    return rpc * C * 2 <= 227 * 1024 - 2048
+    scr = 512 * (2 if C // 32 >= 8 else 8) * 8               # in-CTA reduction scratch behind the slab
+    return (rpc * C * 2 + 15) // 16 * 16 + scr <= 227 * 1024 - 3072
 
 
 def layernorm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -236,6 +236,7 @@ class _VideoUNetBase(nn.Module):
     def invalidate_engine(self):
         """Drop packed weights / captured graphs (called automatically after load_state_dict and .to())."""
         self.__dict__["_eng"] = None
+        self.__dict__["_pair_cache"] = {}
 
     def _apply(self, fn, *a, **k):
         self.invalidate_engine()
@@ -250,15 +251,18 @@ class _VideoUNetBase(nn.Module):
         self._engine().use_graphs = bool(on)
         return self
 
-    def set_frame_sharding(self, group=None, enable: bool = True, exchange=None):
-        """Spread ONE sample's frames over the ranks of `group` (default: WORLD): rank r computes frames
-        [r*F/P, (r+1)*F/P); see videomv_b200/parallel.py. Every rank must make the same calls with the same inputs and
-        receives the full output."""
+    def set_frame_sharding(self, group=None, enable: bool = True, exchange=None, cfg_split: bool = False):
+        """Spread ONE sample over the ranks of `group` (default: WORLD); see videomv_b200/parallel.py.
+        cfg_split=False: pure frame sharding, rank r computes frames [r*F/P, (r+1)*F/P) of both halves of a CFG pair.
+        cfg_split=True (even P): the first P/2 ranks evaluate the conditional half of `forward_cfg_pair`, the others the
+        unconditional half, each group frame-sharding its half over P/2 ranks (P = 2: no frame sharding at all).
+        Every rank must make the same calls with the same inputs and receives the full output."""
         from . import parallel
         eng = self._engine()
         # exchange: None (= VMV_SHARD_EXCHANGE, default "peer": one kernel per exchange over NVLink peer memory) | "gather" | "a2a"
-        eng.shard = parallel.ShardCtx(group, device=eng.device, exchange=exchange) if enable else None
+        eng.shard = parallel.ShardCtx(group, device=eng.device, exchange=exchange, cfg_split=cfg_split) if enable else None
         eng._graphs.clear()
+        self.__dict__["_pair_cache"] = {}
         return self
 
     def graph_launches(self) -> int:
@@ -273,16 +277,20 @@ class _VideoUNetBase(nn.Module):
         attentions are per sample). Returns (y_out, u_out) fp32."""
         eng = self._engine()
         b = x.shape[0]
-        key = tuple((k, id(v), getattr(v, "_version", 0)) for kw in (kw_cond, kw_uncond) for k, v in sorted(kw.items())
-                    if torch.is_tensor(v)) + (tuple(x.shape),)
+        key = tuple((k, id(v), v.data_ptr(), v._version, tuple(v.shape)) for kw in (kw_cond, kw_uncond)
+                    for k, v in sorted(kw.items()) if torch.is_tensor(v)) + (tuple(x.shape),)
         cache = self.__dict__.setdefault("_pair_cache", {})
         hit = cache.get(key)
+        split = eng.shard is not None and eng.shard.cfg_ways == 2      # this rank evaluates ONE half at batch b
         if hit is None:
             def both(name, dtype=None):
                 a, c = kw_cond.get(name), kw_uncond.get(name)
                 if a is None or c is None:
                     return None
-                z = torch.cat([a.to(eng.device), c.to(eng.device)], dim=0)
+                if split:
+                    z = (a if eng.shard.cfg_index == 0 else c).to(eng.device)
+                else:
+                    z = torch.cat([a.to(eng.device), c.to(eng.device)], dim=0)
                 return z if dtype is None else z.to(dtype)
             y2 = both("y")
             if y2 is None:
@@ -290,16 +298,25 @@ class _VideoUNetBase(nn.Module):
             cam2 = both("camera_data", torch.float32) if self.use_camera_condition else None
             fps2 = both("fps", torch.int64) if (self.use_fps_condition or self.variant == "i2v") else None
             img2, loc2 = both("image"), both("local_image")
-            ctx, concat = eng.prepare_condition((2 * b,) + tuple(x.shape[1:]), y2, img2, loc2)
+            ctx, concat = eng.prepare_condition(((1 if split else 2) * b,) + tuple(x.shape[1:]), y2, img2, loc2)
+            # the entry keeps the caller's tensors alive (their id() is the key: it must not be recycled for another
+            # prompt's tensors while the entry exists) as well as the cat'ed copies prepare_condition keys on
+            held = [v for kw in (kw_cond, kw_uncond) for v in kw.values() if torch.is_tensor(v)]
             hit = (ctx, None if cam2 is None else cam2.contiguous(), None if fps2 is None else fps2.contiguous(), concat,
-                   (y2, img2, loc2))                 # keep the cat'ed tensors alive: prepare_condition keys on them
+                   (y2, img2, loc2, held))
             if len(cache) >= 4:
                 cache.clear()
             cache[key] = hit
         ctx, cam2, fps2, concat, _ = hit
+        if split:
+            out = eng.forward_core(x.to(device=eng.device, dtype=torch.float32).contiguous(),
+                                   t.to(device=eng.device, dtype=torch.int64).contiguous(), ctx, cam2, fps2, concat)
+            return out[0], out[1]                      # [cfg half, b, C, F, h, w] gathered from both rank groups
         x2 = torch.cat([x, x], dim=0).to(device=eng.device, dtype=torch.float32).contiguous()
         t2 = torch.cat([t, t], dim=0).to(device=eng.device, dtype=torch.int64).contiguous()
         out = eng.forward_core(x2, t2, ctx, cam2, fps2, concat)
+        if eng.shard is not None:
+            out = out[0]
         return out[:b].contiguous(), out[b:].contiguous()
 
     def _check_call(self, x, masked, autoencoder, x0):
