@@ -40,6 +40,14 @@ long long vmv_launch_count(void);
  * mode VMV_GEMM_TCONV3   A = implicit 3-tap unfold along frames of x[B,F,HW,Cin], zero pad 1 on F
  *      replaces nn.Conv3d (3,1,1) (util.py:1360-1375) without the NCHW<->NCFHW rearranges.
  *
+ * mode VMV_GEMM_CONV3X3_S2  3x3 conv, STRIDE 2, zero pad 1 of x[BF,H,W,Cin] -> [BF,H/2,W/2,N]: the stride-2 windows are
+ *      read by TMA boxes with element strides {1,2,2,1} (no patch gather); replaces Downsample.op (util.py:749).
+ *      B,F,H,Wd describe the INPUT; M = BF*(H/2)*(Wd/2).
+ * mode VMV_GEMM_UPCONV3X3  nearest-x2 upsample followed by a 3x3 conv (Upsample, util.py:604-606) WITHOUT the 4x tensor:
+ *      output pixel (2y+py, 2x+px) is a 2x2 conv of the input around (y, x) with the 3x3 taps that fall on the same input
+ *      pixel pre-summed (packing.pack_upconv3x3) -- 4 phases x 4 taps x Cin, 2.25x fewer FLOPs than the 9-tap conv on the
+ *      upsampled image.  B,F,H,Wd describe the INPUT; M = BF*4*H*Wd; W is [4*N, 4*Cin] (phase-major rows, K = (ty,tx,c)).
+ *
  * W is fp16 [N, Ktot] row-major (K contiguous): Ktot = K1+K2 (linear), 9*Cin ordered (ky,kx,c),
  * or 3*Cin ordered (kt,c).  See videomv_b200/packing.py for the repack from reference layouts.
  *
@@ -48,7 +56,7 @@ long long vmv_launch_count(void);
  * GEGLU (util.py:543-550): W rows are packed per N tile as [BN/2 value rows | BN/2 gate rows];
  * output has N/2 columns: value * gelu_erf(gate).
  * ---------------------------------------------------------------------------------------------- */
-enum { VMV_GEMM_LINEAR = 0, VMV_GEMM_CONV3X3 = 1, VMV_GEMM_TCONV3 = 2 };
+enum { VMV_GEMM_LINEAR = 0, VMV_GEMM_CONV3X3 = 1, VMV_GEMM_TCONV3 = 2, VMV_GEMM_CONV3X3_S2 = 3, VMV_GEMM_UPCONV3X3 = 4 };
 enum { VMV_ACT_NONE = 0, VMV_ACT_SILU = 1, VMV_ACT_GEGLU = 2 };
 
 typedef struct vmv_gemm_params {

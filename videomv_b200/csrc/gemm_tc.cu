@@ -37,8 +37,12 @@ struct GemmArgs {
     // conv geometry (tile decode)
     int F, H, W, HW;
     int bw, bh, bf, bp;
-    int tiles_w, tiles_h;          // CONV3X3
+    int tiles_w, tiles_h;          // CONV3X3 family
     int tiles_per_sample, tiles_p; // TCONV3
+    // CONV3X3_S2: the tile geometry above is that of the OUTPUT (H/2 x W/2); TMA coordinates are 2 * (output coordinate) + tap.
+    // UPCONV3X3:  the tile geometry is that of the INPUT grid; m tiles come in 4 phases (py, px) of `mt_phase` tiles each,
+    //             output pixel (2y+py, 2x+px); 4 taps (ty, tx) at input offset (ty - 1 + py, tx - 1 + px); W rows phase*N + n.
+    int mt_phase;                  // m tiles per phase (== all m tiles when the mode has no phases)
     // epilogue
     __half* D;
     long long ldd;
@@ -103,11 +107,11 @@ __device__ __forceinline__ float2 ln_row_stats(const GemmArgs& a, long long row)
 }
 
 // Decode (m tile, row in tile) -> global output row; returns -1 when the row is padding.
-__device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int mt, int r) {
+__device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int mt, int r, int phase = 0) {
     if (a.mode == VMV_GEMM_LINEAR) {
         long long g = (long long)mt * BM + r;
         return g < a.M ? g : -1;
-    } else if (a.mode == VMV_GEMM_CONV3X3) {
+    } else if (a.mode == VMV_GEMM_CONV3X3 || a.mode == VMV_GEMM_CONV3X3_S2) {
         int tw = mt % a.tiles_w;
         int th = (mt / a.tiles_w) % a.tiles_h;
         int tf = mt / (a.tiles_w * a.tiles_h);
@@ -117,6 +121,18 @@ __device__ __forceinline__ long long tile_row_to_global(const GemmArgs& a, int m
         long long f = (long long)tf * a.bf + rf;
         long long g = (f * a.H + (th * a.bh + rh)) * a.W + (tw * a.bw + rw);
         return g < a.M ? g : -1;
+    } else if (a.mode == VMV_GEMM_UPCONV3X3) {
+        if (mt >= a.mt_phase) return -1;                   // phantom second tile of an odd pair
+        int tw = mt % a.tiles_w;
+        int th = (mt / a.tiles_w) % a.tiles_h;
+        int tf = mt / (a.tiles_w * a.tiles_h);
+        int rw = r % a.bw;
+        int rh = (r / a.bw) % a.bh;
+        int rf = r / (a.bw * a.bh);
+        long long f = (long long)tf * a.bf + rf;
+        const int y = th * a.bh + rh, x = tw * a.bw + rw;
+        long long g = (f * (2 * a.H) + (2 * y + (phase >> 1))) * (2 * a.W) + (2 * x + (phase & 1));
+        return (f < a.F && g < a.M) ? g : -1;
     } else {
         int b = mt / a.tiles_per_sample;
         int ts = mt % a.tiles_per_sample;
@@ -487,6 +503,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     const int num_clusters = gridDim.x >> 1;
     const int tiles_mn = m_pairs * n_tiles;
     const int total_tiles = tiles_mn * splits;
+    const int mp_phase = (a.mt_phase + 1) / 2;          // CTA pairs per output phase (all of them when the mode has one phase)
 
     cluster_sync_all();                                 // both CTAs resident before the pair-wide TMEM allocation
     if (warp == 0 && lane == 0) {
@@ -522,9 +539,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             int pre = 0;                                    // stages whose barrier arrival + W load were issued pre-wait
             if (a.w_static && !(a.dbg & 4) && cluster_id < total_tiles) {
                 const int split = cluster_id / tiles_mn;
-                const int nt = (cluster_id - split * tiles_mn) % n_tiles;
+                const int rem0 = cluster_id - split * tiles_mn;
+                const int nt = rem0 % n_tiles;
                 const int nt_cols = min(BN, a.N - nt * BN);
-                const int nrow = nt * BN + (int)rank * (nt_cols / 2);
+                const int nrow = ((rem0 / n_tiles) / mp_phase) * a.N + nt * BN + (int)rank * (nt_cols / 2);
                 const int kb_begin = split * a.kb_per_split;
                 const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
                 pre = min(STAGES, kb_end - kb_begin);
@@ -540,18 +558,20 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const int split = t / tiles_mn;
                 const int rem = t - split * tiles_mn;
                 const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
-                const int mt = 2 * mp + (int)rank;
+                const int phase = mp / mp_phase;                // UPCONV3X3 only (0 otherwise)
+                const int mt = 2 * (mp - phase * mp_phase) + (int)rank;
                 // the pair splits the tile's W rows; a ragged last tile (N % BN != 0) is nt_cols wide and each CTA
                 // contributes nt_cols/2 rows (its box still loads BN/2 rows; the surplus is never read by the MMA)
                 const int nt_cols = min(BN, a.N - nt * BN);
-                const int nrow = nt * BN + (int)rank * (nt_cols / 2);
+                const int nrow = phase * a.N + nt * BN + (int)rank * (nt_cols / 2);
                 int c1 = 0, c2 = 0, c3 = 0;
                 if (a.mode == VMV_GEMM_LINEAR) {
                     c1 = mt * BM;
-                } else if (a.mode == VMV_GEMM_CONV3X3) {
+                } else if (a.mode == VMV_GEMM_CONV3X3 || a.mode == VMV_GEMM_CONV3X3_S2 || a.mode == VMV_GEMM_UPCONV3X3) {
                     c1 = (mt % a.tiles_w) * a.bw;
                     c2 = ((mt / a.tiles_w) % a.tiles_h) * a.bh;
                     c3 = (mt / (a.tiles_w * a.tiles_h)) * a.bf;
+                    if (a.mode == VMV_GEMM_CONV3X3_S2) { c1 *= 2; c2 *= 2; }     // input coordinates of the stride-2 window
                 } else {
                     int ts = mt % a.tiles_per_sample;
                     c1 = (ts % a.tiles_p) * a.bp;
@@ -579,9 +599,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     if (a.mode == VMV_GEMM_LINEAR) {
                         if (kb < a.nkb1) tma_load_2d_2sm(sa, &tmA1, &full_bar[s], kb * BK, c1);
                         else tma_load_2d_2sm(sa, &tmA2, &full_bar[s], (kb - a.nkb1) * BK, c1);
-                    } else if (a.mode == VMV_GEMM_CONV3X3) {
+                    } else if (a.mode == VMV_GEMM_CONV3X3 || a.mode == VMV_GEMM_CONV3X3_S2) {
                         const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
                         const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+                        tma_load_4d_2sm(sa, &tmA1, &full_bar[s], cb * BK, c1 + dx, c2 + dy, c3);
+                    } else if (a.mode == VMV_GEMM_UPCONV3X3) {
+                        const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;      // 4 taps (ty, tx)
+                        const int dy = (tap >> 1) - 1 + (phase >> 1), dx = (tap & 1) - 1 + (phase & 1);
                         tma_load_4d_2sm(sa, &tmA1, &full_bar[s], cb * BK, c1 + dx, c2 + dy, c3);
                     } else {
                         const int tap = kb / a.cblocks, cb = kb - tap * a.cblocks;
@@ -673,10 +697,11 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
             const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
-            const int mt = 2 * mp + (int)rank;
+            const int phase = mp / mp_phase;
+            const int mt = 2 * (mp - phase * mp_phase) + (int)rank;
             const int buf = acc_it & 1;
             const uint32_t aph = (acc_it >> 1) & 1;
-            const long long grow = tile_row_to_global(a, mt, r);
+            const long long grow = tile_row_to_global(a, mt, r, phase);
             const bool valid = grow >= 0;
             const uint32_t trow = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + buf * BN;
             const int col0 = nt * out_bn;
@@ -945,13 +970,16 @@ static EncodeTiledFn get_encode_fn() {
 // fp16 tensor map, 128B swizzle, inner box = 64 elements.  dims/strides innermost first; strides in bytes
 // for dims 1..rank-1.
 static int make_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-                    const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    const cuuint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B,
+                    const cuuint32_t* elem_strides = nullptr) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
         set_error("cuTensorMapEncodeTiled not available from the driver");
         return VMV_ERR_CUDA;
     }
     cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    if (elem_strides)
+        for (int i = 0; i < rank; ++i) estr[i] = elem_strides[i];
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, rank, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1128,6 +1156,28 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
         a.nkb = 9 * a.cblocks;
         a.nkb1 = a.nkb;
         pl->m_tiles = a.tiles_w * a.tiles_h * ((NF + a.bf - 1) / a.bf);
+    } else if (p->mode == VMV_GEMM_CONV3X3_S2 || p->mode == VMV_GEMM_UPCONV3X3) {
+        // geometry arguments describe the INPUT images; tiles are laid over the output grid (stride 2: H/2 x W/2) or over the
+        // input grid (nearest-x2 upsample + conv: every input position produces the 4 output phases)
+        VMV_CHECK_ARG(p->K2 == 0, "vmv_gemm: conv modes take a single source");
+        const bool s2 = p->mode == VMV_GEMM_CONV3X3_S2;
+        const int Hin = p->H, Win = p->Wd, NF = p->B * p->F;
+        VMV_CHECK_ARG(Hin > 0 && Win > 0 && NF > 0 && (!s2 || (Hin % 2 == 0 && Win % 2 == 0)), "vmv_gemm strided / upsampling conv: bad H, W");
+        const int H = s2 ? Hin / 2 : Hin, W = s2 ? Win / 2 : Win;             // tile grid
+        VMV_CHECK_ARG((long long)NF * H * W * (s2 ? 1 : 4) == p->M, "vmv_gemm strided / upsampling conv: M does not match the output size");
+        VMV_CHECK_ARG(W >= 128 ? (W % 128 == 0) : (128 % W == 0), "vmv_gemm conv: tile-grid W=%d must divide or be a multiple of 128", W);
+        a.bw = W >= 128 ? 128 : W;
+        const int rem = 128 / a.bw;
+        VMV_CHECK_ARG(H >= rem ? (H % rem == 0) : (rem % H == 0), "vmv_gemm conv: tile-grid H=%d incompatible with 128-row tiles", H);
+        a.bh = H >= rem ? rem : H;
+        a.bf = 128 / (a.bw * a.bh);
+        a.tiles_w = W / a.bw;
+        a.tiles_h = H / a.bh;
+        a.F = NF; a.H = H; a.W = W; a.HW = H * W;
+        a.cblocks = p->K1 / BK;
+        a.nkb = (s2 ? 9 : 4) * a.cblocks;
+        a.nkb1 = a.nkb;
+        pl->m_tiles = a.tiles_w * a.tiles_h * ((NF + a.bf - 1) / a.bf);
     } else if (p->mode == VMV_GEMM_TCONV3) {
         VMV_CHECK_ARG(p->K2 == 0, "vmv_gemm: conv modes take a single source");
         const int HW = p->H * p->Wd;
@@ -1146,8 +1196,11 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
         set_error("vmv_gemm: unknown mode %d", p->mode);
         return VMV_ERR_INVALID;
     }
+    a.mt_phase = pl->m_tiles;
     pl->variant = p->variant ? p->variant : default_variant();
     VMV_CHECK_ARG(pl->variant == 1 || pl->variant == 2, "vmv_gemm: variant=%d unsupported", pl->variant);
+    if (p->mode == VMV_GEMM_CONV3X3_S2 || p->mode == VMV_GEMM_UPCONV3X3)
+        VMV_CHECK_ARG(pl->variant == 2 && p->split_k <= 1, "vmv_gemm: the strided / upsampling conv modes need the CTA-pair kernel without split-K");
     if (pl->variant == 2 && p->block_n == 64) pl->variant = 1;      // 64-wide tiles exist only in the 1-CTA kernel
     pl->bn = pick_block_n(p, pl->variant);
     VMV_CHECK_ARG(pl->bn == 64 || pl->bn == 128 || pl->bn == 160 || pl->bn == 256, "vmv_gemm: block_n=%d unsupported", pl->bn);
@@ -1191,10 +1244,12 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
 
     CUtensorMap tA1, tA2, tW;
     const long long Ktot = p->mode == VMV_GEMM_LINEAR ? (long long)p->K1 + p->K2
-                           : p->mode == VMV_GEMM_CONV3X3 ? 9LL * p->K1 : 3LL * p->K1;
+                           : (p->mode == VMV_GEMM_CONV3X3 || p->mode == VMV_GEMM_CONV3X3_S2) ? 9LL * p->K1
+                           : p->mode == VMV_GEMM_UPCONV3X3 ? 4LL * p->K1 : 3LL * p->K1;
+    const long long w_rows = p->mode == VMV_GEMM_UPCONV3X3 ? 4LL * p->N : p->N;      // one weight set per output phase
     VMV_CHECK_ARG(p->ldw >= Ktot, "vmv_gemm: ldw=%lld < Ktot=%lld", (long long)p->ldw, Ktot);
     {
-        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)p->N};
+        cuuint64_t dims[2] = {(cuuint64_t)Ktot, (cuuint64_t)w_rows};
         cuuint64_t strides[1] = {(cuuint64_t)p->ldw * 2};
         cuuint32_t box[2] = {BK, (cuuint32_t)(pl.variant == 2 ? BN / 2 : BN)};   // a CTA pair splits the W rows
         if ((rc = make_map(&tW, p->W, 2, dims, strides, box)) != VMV_OK) return rc;
@@ -1211,12 +1266,23 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
         } else {
             tA2 = tA1;
         }
-    } else if (p->mode == VMV_GEMM_CONV3X3) {
+    } else if (p->mode == VMV_GEMM_CONV3X3 || p->mode == VMV_GEMM_UPCONV3X3) {
         const cuuint64_t ld = (cuuint64_t)p->lda1 * 2;
         cuuint64_t dims[4] = {(cuuint64_t)p->K1, (cuuint64_t)a.W, (cuuint64_t)a.H, (cuuint64_t)a.F};
         cuuint64_t strides[3] = {ld, ld * a.W, ld * a.W * a.H};
         cuuint32_t box[4] = {BK, (cuuint32_t)a.bw, (cuuint32_t)a.bh, (cuuint32_t)a.bf};
         if ((rc = make_map(&tA1, p->A1, 4, dims, strides, box)) != VMV_OK) return rc;
+        tA2 = tA1;
+    } else if (p->mode == VMV_GEMM_CONV3X3_S2) {
+        // stride-2 window straight from the input image: the box spans 2*bw x 2*bh input pixels and is traversed with
+        // element strides {1, 2, 2, 1}, so bw x bh pixels land in smem -- in the (h, w) row order of the output tile
+        const cuuint64_t ld = (cuuint64_t)p->lda1 * 2;
+        const cuuint64_t Win = 2ull * a.W, Hin = 2ull * a.H;
+        cuuint64_t dims[4] = {(cuuint64_t)p->K1, Win, Hin, (cuuint64_t)a.F};
+        cuuint64_t strides[3] = {ld, ld * Win, ld * Win * Hin};
+        cuuint32_t box[4] = {BK, 2u * (cuuint32_t)a.bw, 2u * (cuuint32_t)a.bh, (cuuint32_t)a.bf};
+        cuuint32_t estr[4] = {1, 2, 2, 1};
+        if ((rc = make_map(&tA1, p->A1, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, estr)) != VMV_OK) return rc;
         tA2 = tA1;
     } else {
         const cuuint64_t ld = (cuuint64_t)p->lda1 * 2;
@@ -1236,7 +1302,7 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
     }
 
     if (pl.variant == 2) {
-        const int m_pairs = (pl.m_tiles + 1) / 2;
+        const int m_pairs = ((pl.m_tiles + 1) / 2) * (p->mode == VMV_GEMM_UPCONV3X3 ? 4 : 1);
         if (pl.splits <= 1) {
             VMV_CHECK_ARG(!(p->act == VMV_ACT_GEGLU && p->residual), "vmv_gemm: GEGLU with residual is not supported");
             auto al32 = [](const void* ptr, long long ld) { return ptr == nullptr || ((reinterpret_cast<uintptr_t>(ptr) & 31) == 0 && ld % 16 == 0); };

@@ -58,6 +58,8 @@ class UNetEngine:
         self._gn_arena: Optional[ops.GnArena] = None       # statistics scratch of the current forward (GroupNorm partials, LayerNorm slots)
         self._gn_arenas: Dict[Tuple[int, int, int], ops.GnArena] = {}
         self.fused_groupnorm = os.environ.get("VMV_GN_FUSED", "1") != "0"
+        # VMV_RESAMPLE_LEGACY=1: Downsample through an explicit patch gather, Upsample through the materialised 4x tensor (A/B)
+        self.legacy_resample = os.environ.get("VMV_RESAMPLE_LEGACY", "0") == "1"
         # LayerNorm row sums accumulated by the epilogue of the GEMM that produces the rows (no separate statistics pass);
         # needs the CTA-pair kernel's register epilogue and the per-forward arena
         self.fused_ln_stats = (self.fused_groupnorm and os.environ.get("VMV_LN_FUSED", "1") != "0"
@@ -135,8 +137,12 @@ class UNetEngine:
             return {"kind": "down", "c": mod.op.in_channels,
                     "w": _W(packing.pack_conv3x3(mod.op.weight.detach()), _f32(mod.op.bias))}
         if kind == "up":
+            if self.legacy_resample:
+                return {"kind": "up", "c": mod.conv.in_channels,
+                        "w": _W(packing.pack_conv3x3(mod.conv.weight.detach()), _f32(mod.conv.bias))}
+            # nearest x2 + 3x3 conv as four 2x2 phase convs on the original image (weights pre-summed per phase)
             return {"kind": "up", "c": mod.conv.in_channels,
-                    "w": _W(packing.pack_conv3x3(mod.conv.weight.detach()), _f32(mod.conv.bias))}
+                    "w": _W(packing.pack_upconv3x3(mod.conv.weight.detach()), _f32(mod.conv.bias))}
         if isinstance(mod, torch.nn.Conv2d):
             return {"kind": "stem", "w": _f32(mod.weight), "b": _f32(mod.bias)}
         if isinstance(mod, torch.nn.ModuleList):
@@ -184,6 +190,11 @@ class UNetEngine:
     def _gemm(self, a, w: _W, **kw):
         M = a.shape[0]
         N = w.w.shape[0]
+        mode = kw.get("mode", ops.LINEAR)
+        if mode == ops.CONV3X3_S2:
+            M //= 4                                    # output rows
+        elif mode == ops.UPCONV3X3:
+            M, N = 4 * M, N // 4
         bn = w.bn or (256 if N > 320 else (160 if N % 160 == 0 else 128))      # mirrors pick_block_n in gemm_tc.cu
         # The persistent kernel runs one CTA pair per 2 SMs (74 pairs) on 256 x bn tiles.  When the tile count is a
         # poor fit for 74 (few tiles at the 8x8 / 4x4 levels) split K so the last wave is not mostly idle.
@@ -191,7 +202,7 @@ class UNetEngine:
         nkb = w.w.shape[1] // 64
         pairs = SM_COUNT // 2
         split = 0
-        if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs:
+        if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs and mode in (ops.LINEAR, ops.CONV3X3, ops.TCONV3):
             # time(s) ~ T_full / utilisation(s) + cost of the fp32 partials (write + read back + extra launch)
             t_full = 2.0 * M * N * nkb * 64 / 0.9e15
 
@@ -351,14 +362,19 @@ class UNetEngine:
             return self._temporal(d, x, S)
         if k == "down":
             n, H, W = S["B"] * S["F"], S["H"], S["W"]
-            out = self._gemm(ops.im2col_3x3_s2(x, n, H, W), d["w"])
             S["H"], S["W"] = H // 2, W // 2
-            return out
+            if self.legacy_resample:
+                return self._gemm(ops.im2col_3x3_s2(x, n, H, W), d["w"])
+            # Downsample.op (util.py:749): stride-2 windows read by element-strided TMA boxes, no patch gather
+            return self._gemm(x, d["w"], mode=ops.CONV3X3_S2, geom=(1, n, H, W))
         if k == "up":
             n, H, W = S["B"] * S["F"], S["H"], S["W"]
-            up = ops.upsample_nearest2x(x, n, H, W)
             S["H"], S["W"] = 2 * H, 2 * W
-            return self._gemm(up, d["w"], mode=ops.CONV3X3, geom=(1, n, 2 * H, 2 * W))
+            if self.legacy_resample:
+                up = ops.upsample_nearest2x(x, n, H, W)
+                return self._gemm(up, d["w"], mode=ops.CONV3X3, geom=(1, n, 2 * H, 2 * W))
+            # Upsample (util.py:604-606) without the 4x tensor: four 2x2 phase convs, 2.25x fewer FLOPs
+            return self._gemm(x, d["w"], mode=ops.UPCONV3X3, geom=(1, n, H, W))
         if k == "stem":
             return ops.conv3x3_in(S["x_in"], d["w"], d["b"], S.get("x_in2"))
         raise RuntimeError(k)
@@ -404,14 +420,16 @@ class UNetEngine:
         t = t.to(device=dev, dtype=torch.int64).contiguous()
         cam = None if camera_data is None else camera_data.to(device=dev, dtype=torch.float32).contiguous()
         fps = None if fps is None else fps.to(device=dev, dtype=torch.int64).contiguous()
-        ctx, concat = self.prepare_condition(x32.shape, y, image, local_image)
-        out = self.forward_core(x32, t, ctx, cam, fps, concat)
+        kv, concat = self.prepare_condition(x32.shape, y, image, local_image)
+        out = self.forward_core(x32, t, kv, cam, fps, concat)
         if self.shard is not None:
             out = out[self.shard.cfg_index]            # [cfg_ways, B, C, F, h, w]: every group evaluated the same call
         return out if out_dtype == torch.float32 else out.to(out_dtype)
 
     def prepare_condition(self, xshape, y, image=None, local_image=None):
-        """Step-invariant conditioning: context tokens [B,L,1024] fp32 (+ the I2V concat planes). Cached on the
+        """Step-invariant conditioning: the K/V of every cross-attention layer for the context tokens [B,L,1024] (one GEMM
+        per SAMPLE -- the reference recomputes them per frame, per layer, per step: util.py:233-234) + the I2V concat
+        planes.  Returns ((kv_all fp16 [B*L, sum 2*C], L), concat).  Cached on the
         identity of the caller's tensors, which the sampler passes unchanged for all 50 steps.  The entry holds strong
         references to the keyed tensors: while it exists neither their id() nor their storage address can be recycled
         for another prompt's tensors (the reference engines build fresh y / image tensors per caption:
@@ -426,26 +444,27 @@ class UNetEngine:
             concat, ctx = self._i2v_condition(xshape, y.to(dev), image, local_image)
         else:
             concat, ctx = None, y.to(device=dev, dtype=torch.float32)
-        ctx = ctx.contiguous()
+        kv = self._context_kv(ctx.contiguous())
         if len(self._ctx_cache) >= 8:
             self._ctx_cache.clear()
-        self._ctx_cache[key] = (ctx, concat, (y, image, local_image))
-        return ctx, concat
+        self._ctx_cache[key] = (kv, concat, (y, image, local_image))
+        return kv, concat
 
-    def forward_core(self, x32, t, ctx, cam, fps, concat):
+    def forward_core(self, x32, t, kv, cam, fps, concat):
         """The per-step hot path on device-resident inputs. Replays a captured CUDA graph when enabled.
         Returns [B, C, F, h, w]; with a sharding context [cfg_ways, B, C, F, h, w] (the gathered halves of a split CFG pair)."""
+        kv_all, L = kv
         if not self.use_graphs:
-            out = self._forward_impl(x32, t, ctx, cam, fps, concat)
+            out = self._forward_impl(x32, t, kv_all, cam, fps, concat, L)
             return out if self.shard is None else out.clone()     # the gathered output lives in the peer arena: hand out a copy
-        key = (tuple(x32.shape), tuple(ctx.shape), cam is not None, fps is not None, concat is not None)
+        key = (tuple(x32.shape), tuple(kv_all.shape), L, cam is not None, fps is not None, concat is not None)
         g = self._graphs.get(key)
         if g is None:
-            g = _Graph(self, x32, t, ctx, cam, fps, concat)
+            g = _Graph(self, L, x32, t, kv_all, cam, fps, concat)
             self._graphs[key] = g
-        return g.run(x32, t, ctx, cam, fps, concat)
+        return g.run(x32, t, kv_all, cam, fps, concat)
 
-    def _forward_impl(self, x32, t, ctx, cam, fps, concat):
+    def _forward_impl(self, x32, t, kv_all, cam, fps, concat, L):
         B, _, Fr, H, W = x32.shape
         if self.fused_groupnorm:
             # one arena per (B*F) size class, kept alive for the CUDA graphs that captured pointers into it
@@ -476,7 +495,7 @@ class UNetEngine:
         if concat is not None:
             S["x_in2"] = concat
         S["emb_all"] = self._embeddings(t, fps, cam, B, Fr)
-        S["kv_all"], S["L"] = self._context_kv(ctx)
+        S["kv_all"], S["L"] = kv_all, L                 # step-invariant: computed once per sample in prepare_condition
         skips = []
         h = None
         for blk in self.enc:
@@ -552,28 +571,36 @@ class UNetEngine:
 class _Graph:
     """One captured CUDA graph of `_forward_impl` for a fixed set of shapes; inputs are copied into static buffers.
     Every library launch lands on the capturing stream (ops._stream), TMA descriptors are baked into the kernel
-    parameters, and all intermediates live in the graph's private memory pool."""
+    parameters, and all intermediates live in the graph's private memory pool.  Inputs that are the very same tensor as
+    at the previous replay (the per-sample conditioning: context K/V, cameras, fps, I2V planes) are not copied again."""
 
-    def __init__(self, eng: UNetEngine, *inputs):
+    def __init__(self, eng: UNetEngine, L: int, *inputs):
+        self.L = L
         self.static = [None if z is None else z.clone() for z in inputs]
+        self.last = [None] * len(inputs)            # (tensor, _version) last copied into each static buffer (strong refs)
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
         with torch.cuda.stream(side):
             for _ in range(2):                      # warm up: func attributes, workspace, allocator
-                eng._forward_impl(*self.static)
+                eng._forward_impl(*self.static, L)
         cur.wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         n0 = ops.launch_count()
         with torch.cuda.graph(self.graph):
-            self.out = eng._forward_impl(*self.static)
+            self.out = eng._forward_impl(*self.static, L)
         self.launches = ops.launch_count() - n0     # kernels per replay (bench `gpu_launches`)
 
     def run(self, *inputs):
         self.replays = getattr(self, "replays", 0) + 1
-        for dst, src in zip(self.static, inputs):
-            if dst is not None:
-                dst.copy_(src, non_blocking=True)
+        for i, (dst, src) in enumerate(zip(self.static, inputs)):
+            if dst is None:
+                continue
+            prev = self.last[i]
+            if prev is not None and prev[0] is src and prev[1] == src._version:
+                continue
+            dst.copy_(src, non_blocking=True)
+            self.last[i] = (src, src._version)
         self.graph.replay()
         return self.out.clone()

@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import AttnParams, GemmParams, check
 
-LINEAR, CONV3X3, TCONV3 = 0, 1, 2
+LINEAR, CONV3X3, TCONV3, CONV3X3_S2, UPCONV3X3 = 0, 1, 2, 3, 4
 ACT_NONE, ACT_SILU, ACT_GEGLU = 0, 1, 2
 
 # Optional per-call timing hook (bench.py roofline leg): when set to a list, every op appends
@@ -66,6 +66,10 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     _rows(w, "gemm w")
     M, K1 = a1.shape
     N = w.shape[0]
+    if mode == CONV3X3_S2:                    # geom describes the input images; the output has a quarter of the pixels
+        M //= 4
+    elif mode == UPCONV3X3:                   # 4 output pixels per input pixel; w holds one [N, 4*Cin] block per phase
+        M, N = M * 4, N // 4
     n_out = N // 2 if act == ACT_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), dtype=torch.float16, device=a1.device)
@@ -115,7 +119,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     e0 = _prof_begin()
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
     if e0 is not None:
-        ktot = w.shape[1]
+        ktot = 9 * K1 if mode == UPCONV3X3 else w.shape[1]          # algorithmic FLOPs: the 9-tap conv on the upsampled image
         keep = (a1, a2, w, out, bias, rowbias, residual, workspace, ln_stats, ln_colsum, rowstats_out)   # alive for replays
         replay = lambda p=p, keep=keep: check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
         k_in = K1 + (a2.shape[1] if a2 is not None else 0)               # activation columns actually read (conv modes: Cin)

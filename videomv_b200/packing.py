@@ -19,6 +19,28 @@ def pack_conv3x3(w: torch.Tensor) -> torch.Tensor:
     return w.permute(0, 2, 3, 1).reshape(co, 9 * ci).to(torch.float16).contiguous()
 
 
+def pack_upconv3x3(w: torch.Tensor) -> torch.Tensor:
+    """nn.Conv2d [Cout,Cin,3,3] applied AFTER a nearest x2 upsample (util.py:604-606) -> fp16 [4*Cout, 4*Cin]: one 2x2 conv per
+    output phase (py, px) on the ORIGINAL image.  Output pixel (2y+py, 2x+px), 3x3 tap k reads upsampled row 2y+py+k-1, i.e.
+    input row y + floor((py+k-1)/2): for py = 0 the taps {0 | 1,2} fall on input rows {y-1 | y}, for py = 1 the taps {0,1 | 2}
+    on {y | y+1} (same along x), so taps that share an input pixel are summed (in fp32) once here.  Row = phase*Cout + co with
+    phase = 2*py + px; K ordered (ty, tx, c) with input offset (ty - 1 + py, tx - 1 + px)."""
+    co, ci = w.shape[:2]
+    w = w.detach().float()
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}           # phase -> (taps of ty/tx = 0, taps of ty/tx = 1)
+    out = torch.empty((4, co, 2, 2, ci), dtype=torch.float32, device=w.device)
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = torch.zeros((co, ci), dtype=torch.float32, device=w.device)
+                    for ky in groups[py][ty]:
+                        for kx in groups[px][tx]:
+                            acc += w[:, :, ky, kx]
+                    out[2 * py + px, :, ty, tx] = acc
+    return out.reshape(4 * co, 4 * ci).to(torch.float16).contiguous()
+
+
 def pack_tconv3(w: torch.Tensor) -> torch.Tensor:
     """nn.Conv3d [Cout,Cin,3,1,1] -> fp16 [Cout, 3*Cin] with K ordered (kt, c)."""
     co, ci = w.shape[:2]

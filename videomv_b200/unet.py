@@ -298,23 +298,23 @@ class _VideoUNetBase(nn.Module):
             cam2 = both("camera_data", torch.float32) if self.use_camera_condition else None
             fps2 = both("fps", torch.int64) if (self.use_fps_condition or self.variant == "i2v") else None
             img2, loc2 = both("image"), both("local_image")
-            ctx, concat = eng.prepare_condition(((1 if split else 2) * b,) + tuple(x.shape[1:]), y2, img2, loc2)
+            kv, concat = eng.prepare_condition(((1 if split else 2) * b,) + tuple(x.shape[1:]), y2, img2, loc2)
             # the entry keeps the caller's tensors alive (their id() is the key: it must not be recycled for another
             # prompt's tensors while the entry exists) as well as the cat'ed copies prepare_condition keys on
             held = [v for kw in (kw_cond, kw_uncond) for v in kw.values() if torch.is_tensor(v)]
-            hit = (ctx, None if cam2 is None else cam2.contiguous(), None if fps2 is None else fps2.contiguous(), concat,
+            hit = (kv, None if cam2 is None else cam2.contiguous(), None if fps2 is None else fps2.contiguous(), concat,
                    (y2, img2, loc2, held))
             if len(cache) >= 4:
                 cache.clear()
             cache[key] = hit
-        ctx, cam2, fps2, concat, _ = hit
+        kv, cam2, fps2, concat, _ = hit
         if split:
             out = eng.forward_core(x.to(device=eng.device, dtype=torch.float32).contiguous(),
-                                   t.to(device=eng.device, dtype=torch.int64).contiguous(), ctx, cam2, fps2, concat)
+                                   t.to(device=eng.device, dtype=torch.int64).contiguous(), kv, cam2, fps2, concat)
             return out[0], out[1]                      # [cfg half, b, C, F, h, w] gathered from both rank groups
         x2 = torch.cat([x, x], dim=0).to(device=eng.device, dtype=torch.float32).contiguous()
         t2 = torch.cat([t, t], dim=0).to(device=eng.device, dtype=torch.int64).contiguous()
-        out = eng.forward_core(x2, t2, ctx, cam2, fps2, concat)
+        out = eng.forward_core(x2, t2, kv, cam2, fps2, concat)
         if eng.shard is not None:
             out = out[0]
         return out[:b].contiguous(), out[b:].contiguous()
