@@ -132,6 +132,9 @@ int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, const void* x2
 /* Single-launch form of the two calls above (single-GPU path: no reduction between statistics and apply): the rows are
  * staged in shared memory once (or re-read from L2 when they do not fit), statistics, an in-kernel arrival barrier per
  * chunk, apply.  Returns VMV_ERR_UNSUPPORTED when the grid cannot be made co-resident (never spins then). */
+/* 1 when vmv_groupnorm_fused takes the smem-resident single-pass kernel for this shape on the current device (the only form
+ * vmv_groupnorm_fused_peer supports), 0 when it re-reads the rows from L2. */
+int vmv_groupnorm_fused_fits_smem(int32_t C, int64_t rows_per_batch, int32_t nbatch);
 int vmv_groupnorm_fused(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                         int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
                         const float* beta, float eps, int32_t silu, void* out, int64_t ldo, void* stream);

@@ -1,7 +1,8 @@
-"""GroupNorm micro-benchmark on the shapes of one CFG-batched T2V 256^2 forward (B=2, 24 frames).
+"""GroupNorm micro-benchmark on the shapes of one T2V 256^2 forward (24 frames; B = 2 CFG-batched, or `B=1` as argv[2]).
 Each shape: `reps` back-to-back calls captured in a CUDA graph, over a rotating set of distinct buffers large enough
-to defeat L2 ("cold") or over one buffer ("warm"); CUDA events around graph replays.  VMV_GN_OPT selects kernel
-experiments (norm.cu).  Also prints a plain copy (read + write) of the same tensor as the bandwidth yardstick."""
+to defeat L2 ("cold") or over one buffer ("warm"); CUDA events around graph replays.  argv[1]: comma-separated values of
+VMV_GN_MIN_KB (minimum KB of rows per CTA of the smem-resident kernel, 0 = one CTA per SM whatever the size).  Also
+prints a plain copy (read + write) of the same tensor as the bandwidth yardstick."""
 import os
 import sys
 
@@ -11,18 +12,20 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from videomv_b200 import ops  # noqa: E402
 
 # (rows, C1, C2, rows_per_batch, silu, count per forward, label)
+BATCH = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+_R = 24576 * BATCH
 SHAPES = [
-    (49152, 320, 0, 24576, True, 26, "5-D 32x32 C320"),
-    (12288, 640, 0, 6144, True, 25, "5-D 16x16 C640"),
-    (3072, 1280, 0, 1536, True, 25, "5-D 8x8 C1280"),
-    (768, 1280, 0, 384, True, 29, "5-D 4x4 C1280"),
-    (49152, 320, 0, 1024, True, 12, "4-D 32x32 C320"),
-    (49152, 640, 320, 1024, True, 2, "4-D 32x32 C640+320"),
-    (12288, 640, 0, 256, True, 11, "4-D 16x16 C640"),
-    (12288, 1280, 640, 256, True, 1, "4-D 16x16 C1280+640"),
-    (3072, 1280, 0, 64, True, 12, "4-D 8x8 C1280"),
-    (3072, 1280, 1280, 64, True, 2, "4-D 8x8 C1280+1280"),
-    (768, 1280, 0, 16, True, 12, "4-D 4x4 C1280"),
+    (_R, 320, 0, 24576, True, 26, "5-D 32x32 C320"),
+    (_R // 4, 640, 0, 6144, True, 25, "5-D 16x16 C640"),
+    (_R // 16, 1280, 0, 1536, True, 25, "5-D 8x8 C1280"),
+    (_R // 64, 1280, 0, 384, True, 29, "5-D 4x4 C1280"),
+    (_R, 320, 0, 1024, True, 12, "4-D 32x32 C320"),
+    (_R, 640, 320, 1024, True, 2, "4-D 32x32 C640+320"),
+    (_R // 4, 640, 0, 256, True, 11, "4-D 16x16 C640"),
+    (_R // 4, 1280, 640, 256, True, 1, "4-D 16x16 C1280+640"),
+    (_R // 16, 1280, 0, 64, True, 12, "4-D 8x8 C1280"),
+    (_R // 16, 1280, 1280, 64, True, 2, "4-D 8x8 C1280+1280"),
+    (_R // 64, 1280, 0, 16, True, 12, "4-D 4x4 C1280"),
 ]
 
 
@@ -52,7 +55,7 @@ def main():
     opts = [int(x) for x in (sys.argv[1].split(",") if len(sys.argv) > 1 else ["0"])]
     dev = "cuda"
     arena = ops.GnArena(dev, 64 << 20)
-    print(f"| shape | n | MB in | copy cold us | " + " | ".join(f"opt{o} cold / warm us" for o in opts) + " |")
+    print(f"B={BATCH} | shape | n | MB in | copy cold us | " + " | ".join(f"min_kb {o} cold / warm us" for o in opts) + " |")
     tot = {o: [0.0, 0.0] for o in opts}
     for rows, C1, C2, rpb, silu, cnt, label in SHAPES:
         C = C1 + C2
@@ -70,7 +73,7 @@ def main():
         t_copy = time_graph(copy, reps)
         cells = []
         for o in opts:
-            os.environ["VMV_GN_OPT"] = str(o)
+            os.environ["VMV_GN_MIN_KB"] = str(o)
 
             def cold(i):
                 if i == 0:
@@ -89,7 +92,7 @@ def main():
             cells.append(f"{tc:.1f} / {tw:.1f}")
         print(f"| {label} | {cnt} | {mb:.1f} | {t_copy:.1f} | " + " | ".join(cells) + " |", flush=True)
         del xs, x2s, outs
-    print("per-forward totals (ms): " + "; ".join(f"opt{o}: cold {v[0] / 1e3:.3f} warm {v[1] / 1e3:.3f}" for o, v in tot.items()))
+    print("per-forward totals (ms): " + "; ".join(f"min_kb {o}: cold {v[0] / 1e3:.3f} warm {v[1] / 1e3:.3f}" for o, v in tot.items()))
 
 
 if __name__ == "__main__":

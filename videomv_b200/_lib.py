@@ -142,6 +142,7 @@ SYMBOLS = {
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
+    "vmv_groupnorm_fused_fits_smem": (ctypes.c_int, [c_i32, c_i64, c_i32]),
     "vmv_groupnorm_fused": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,
                                            c_f32, c_i32, c_vp, c_i64, c_vp]),
     "vmv_groupnorm_fused_peer": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp,

@@ -1200,7 +1200,9 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     pl->variant = p->variant ? p->variant : default_variant();
     VMV_CHECK_ARG(pl->variant == 1 || pl->variant == 2, "vmv_gemm: variant=%d unsupported", pl->variant);
     if (p->mode == VMV_GEMM_CONV3X3_S2 || p->mode == VMV_GEMM_UPCONV3X3)
-        VMV_CHECK_ARG(pl->variant == 2 && p->split_k <= 1, "vmv_gemm: the strided / upsampling conv modes need the CTA-pair kernel without split-K");
+        VMV_CHECK_ARG(pl->variant == 2, "vmv_gemm: the strided / upsampling conv modes need the CTA-pair kernel");
+    if (p->mode == VMV_GEMM_UPCONV3X3)
+        VMV_CHECK_ARG(p->split_k <= 1, "vmv_gemm: the upsampling conv mode does not take split-K");
     if (pl->variant == 2 && p->block_n == 64) pl->variant = 1;      // 64-wide tiles exist only in the 1-CTA kernel
     pl->bn = pick_block_n(p, pl->variant);
     VMV_CHECK_ARG(pl->bn == 64 || pl->bn == 128 || pl->bn == 160 || pl->bn == 256, "vmv_gemm: block_n=%d unsupported", pl->bn);

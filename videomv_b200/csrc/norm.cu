@@ -761,6 +761,48 @@ extern "C" int vmv_groupnorm_apply(const void* x1, int64_t ldx1, int32_t C1, con
     return VMV_OK;
 }
 
+// Launch plan of the smem-resident single-pass kernel: CTAs per chunk, rows per CTA, dynamic smem.  One CTA per SM at most
+// (all CTAs of the grid co-resident for the arrival barrier); small chunks use FEWER CTAs than SMs -- at least
+// `min_kb` KB of rows each (VMV_GN_MIN_KB, default 32; profiles/r2_gn_bench.md) -- because below that the kernel is bound by the arrival barrier
+// and the slot sum, whose cost grows with the number of CTAs of the chunk, not by moving the rows.
+struct GnSmemPlan { long long cpb, rpc, smem; };
+
+static bool gn_smem_plan(int C, long long rows_per_batch, int nbatch, GnSmemPlan* pl) {
+    static int use_smem = -1, num_sms = 0, min_kb = 32;
+    if (use_smem < 0) {
+        const char* e = getenv("VMV_GN_SMEM");            // VMV_GN_SMEM=0: always the re-read kernel
+        use_smem = (e && e[0] == '0') ? 0 : 1;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+        if (num_sms <= 0) num_sms = 148;
+    }
+    {
+        const char* e = getenv("VMV_GN_MIN_KB");          // read per call: the micro-benchmark sweeps it
+        min_kb = e ? atoi(e) : 32;
+    }
+    if (!use_smem || C > 8 * GNS_THREADS || nbatch > num_sms) return false;
+    long long cpb = num_sms / nbatch;                      // CTAs per chunk; all CTAs co-resident at one per SM
+    if (cpb > rows_per_batch) cpb = rows_per_batch;
+    if (min_kb > 0) {
+        long long by_bytes = rows_per_batch * C * 2 / ((long long)min_kb * 1024);
+        if (by_bytes < 1) by_bytes = 1;
+        if (cpb > by_bytes) cpb = by_bytes;
+    }
+    const long long rpc = (rows_per_batch + cpb - 1) / cpb;
+    cpb = (rows_per_batch + rpc - 1) / rpc;                // drop CTAs that would own no rows
+    // the slab + the reduction scratch (GNS_THREADS x slots-per-thread float2)
+    const long long smem = ((rpc * C * 2 + 15) & ~15LL) + (long long)GNS_THREADS * gn_slots_per_thread(C) * 8;
+    if (smem > GNS_MAX_DYN_SMEM) return false;
+    pl->cpb = cpb; pl->rpc = rpc; pl->smem = smem;
+    return true;
+}
+
+extern "C" int vmv_groupnorm_fused_fits_smem(int32_t C, int64_t rows_per_batch, int32_t nbatch) {
+    GnSmemPlan pl;
+    return (C > 0 && rows_per_batch > 0 && nbatch > 0 && gn_smem_plan(C, rows_per_batch, nbatch, &pl)) ? 1 : 0;
+}
+
 static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x2, int64_t ldx2, int32_t C2,
                          int64_t rows_per_batch, int32_t nbatch, void* barriers, void* scratch, const float* gamma,
                          const float* beta, float eps, int32_t silu, void* out, int64_t ldo, const vmv_gn_peer* peer,
@@ -773,46 +815,32 @@ static int gn_fused_impl(const void* x1, int64_t ldx1, int32_t C1, const void* x
     unsigned int* bars = static_cast<unsigned int*>(barriers);
     float2* slots = static_cast<float2*>(scratch);
     {
-        // smem-resident single pass whenever one CTA per SM can hold the tensor (VMV_GN_SMEM=0: always the re-read kernel)
-        static int use_smem = -1, num_sms = 0;
-        if (use_smem < 0) {
-            const char* e = getenv("VMV_GN_SMEM");
-            use_smem = (e && e[0] == '0') ? 0 : 1;
-            int dev = 0;
-            cudaGetDevice(&dev);
-            cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-            if (use_smem) {
-                cudaError_t e2 = cudaFuncSetAttribute(gn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNS_MAX_DYN_SMEM);
-                if (e2 != cudaSuccess) { set_error("vmv_groupnorm_fused: smem attribute: %s", cudaGetErrorString(e2)); return VMV_ERR_CUDA; }
-            }
-        }
         const int C = C1 + C2;
         const bool al16 = ((reinterpret_cast<uintptr_t>(x1) | reinterpret_cast<uintptr_t>(x2) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
-        if (use_smem && al16 && C <= 8 * GNS_THREADS && nbatch <= num_sms) {
-            long long cpb = num_sms / nbatch;                      // CTAs per chunk; all CTAs co-resident at one per SM
-            if (cpb > rows_per_batch) cpb = rows_per_batch;
-            const long long rpc = (rows_per_batch + cpb - 1) / cpb;
-            cpb = (rows_per_batch + rpc - 1) / rpc;                // drop CTAs that would own no rows
-            // the slab + the reduction scratch (GNS_THREADS x slots-per-thread float2)
-            const long long smem = ((rpc * C * 2 + 15) & ~15LL) + (long long)GNS_THREADS * gn_slots_per_thread(C) * 8;
-            if (smem <= GNS_MAX_DYN_SMEM) {
-                GnPeer pe;
-                memset(&pe, 0, sizeof(pe));
-                if (peer != nullptr && peer->world > 1) {
-                    pe.world = peer->world; pe.rank = peer->rank; pe.stat_rows = peer->stat_rows;
-                    pe.epoch = static_cast<unsigned int*>(peer->epoch);
-                    for (int q = 0; q < peer->world; ++q) {
-                        pe.slots[q] = peer->slots[q];
-                        pe.flags[q] = static_cast<unsigned int*>(peer->flags[q]);
-                    }
-                }
-                launch_kernel(gn_smem_kernel, dim3((unsigned)cpb, nbatch), dim3(GNS_THREADS), (size_t)smem, st,
-                              static_cast<const __half*>(x1), ldx1, C1, static_cast<const __half*>(x2), ldx2, C2, rows_per_batch,
-                              (int)rpc, bars, slots, gamma, beta, eps, silu, static_cast<__half*>(out), ldo, pe);
-                count_launch();
-                VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused (smem)");
-                return VMV_OK;
+        GnSmemPlan sp;
+        if (al16 && gn_smem_plan(C, rows_per_batch, nbatch, &sp)) {
+            static bool attr_set = false;
+            if (!attr_set) {
+                cudaError_t e2 = cudaFuncSetAttribute(gn_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GNS_MAX_DYN_SMEM);
+                if (e2 != cudaSuccess) { set_error("vmv_groupnorm_fused: smem attribute: %s", cudaGetErrorString(e2)); return VMV_ERR_CUDA; }
+                attr_set = true;
             }
+            GnPeer pe;
+            memset(&pe, 0, sizeof(pe));
+            if (peer != nullptr && peer->world > 1) {
+                pe.world = peer->world; pe.rank = peer->rank; pe.stat_rows = peer->stat_rows;
+                pe.epoch = static_cast<unsigned int*>(peer->epoch);
+                for (int q = 0; q < peer->world; ++q) {
+                    pe.slots[q] = peer->slots[q];
+                    pe.flags[q] = static_cast<unsigned int*>(peer->flags[q]);
+                }
+            }
+            launch_kernel(gn_smem_kernel, dim3((unsigned)sp.cpb, nbatch), dim3(GNS_THREADS), (size_t)sp.smem, st,
+                          static_cast<const __half*>(x1), ldx1, C1, static_cast<const __half*>(x2), ldx2, C2, rows_per_batch,
+                          (int)sp.rpc, bars, slots, gamma, beta, eps, silu, static_cast<__half*>(out), ldo, pe);
+            count_launch();
+            VMV_CUDA_LAUNCH_CHECK("vmv_groupnorm_fused (smem)");
+            return VMV_OK;
         }
     }
     if (peer != nullptr && peer->world > 1) {

@@ -202,7 +202,7 @@ class UNetEngine:
         nkb = w.w.shape[1] // 64
         pairs = SM_COUNT // 2
         split = 0
-        if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs and mode in (ops.LINEAR, ops.CONV3X3, ops.TCONV3):
+        if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs and mode != ops.UPCONV3X3:
             # time(s) ~ T_full / utilisation(s) + cost of the fp32 partials (write + read back + extra launch)
             t_full = 2.0 * M * N * nkb * 64 / 0.9e15
 

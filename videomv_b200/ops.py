@@ -217,10 +217,18 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
             gp.flags[q] = peer.base(q) + c_off
         gp.epoch = peer.base(peer.rank) + c_off + 32
         bars, scr = scratch.take(C1 + C2, rows_per_batch, nbatch)
-        check(L.vmv_groupnorm_fused_peer(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
-                                         rows_per_batch, nbatch, bars, scr, gamma.data_ptr(), beta.data_ptr(),
-                                         float(eps), int(silu), out.data_ptr(), out.stride(0), ctypes.byref(gp), st),
-              "vmv_groupnorm_fused_peer")
+        e0 = _prof_begin()
+
+        def launch_peer():
+            check(L.vmv_groupnorm_fused_peer(x1.data_ptr(), x1.stride(0), C1, _p(x2), 0 if x2 is None else x2.stride(0), C2,
+                                             rows_per_batch, nbatch, bars, scr, gamma.data_ptr(), beta.data_ptr(),
+                                             float(eps), int(silu), out.data_ptr(), out.stride(0), ctypes.byref(gp), _stream()),
+                  "vmv_groupnorm_fused_peer")
+        launch_peer()
+        if e0 is not None:
+            launch_peer.keep = (x1, x2, out, gamma, beta, scratch, gp)
+            _prof_end(e0, "groupnorm_peer", 0.0, 2.0 * 2 * rows * (C1 + C2),
+                      f"rows{rows} C{C1}+{C2} rpb{rows_per_batch} silu{int(silu)} P{peer.world}", launch_peer)
         peer.peer_ops += 1
         return out
     if scratch is not None and reduce_fn is None:
@@ -264,23 +272,10 @@ def groupnorm(x1: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, rows
     return out
 
 
-_SM_COUNT = {}
-
-
 def _gn_smem_fits(device, rows_per_batch: int, nbatch: int, C: int) -> bool:
-    """Mirror of the dispatch in vmv_groupnorm_fused (norm.cu): does the smem-resident single-pass kernel take this shape?"""
-    import os
-    if os.environ.get("VMV_GN_SMEM", "1") == "0" or C > 4096 or nbatch > 16:
-        return False
-    sms = _SM_COUNT.get(device)
-    if sms is None:
-        sms = _SM_COUNT[device] = torch.cuda.get_device_properties(device).multi_processor_count
-    if nbatch > sms:
-        return False
-    cpb = min(sms // nbatch, rows_per_batch)
-    rpc = -(-rows_per_batch // cpb)
-    scr = 512 * (2 if C // 32 >= 8 else 8) * 8               # in-CTA reduction scratch behind the slab
-    return (rpc * C * 2 + 15) // 16 * 16 + scr <= 227 * 1024 - 3072
+    """Does vmv_groupnorm_fused take the smem-resident single-pass kernel for this shape (asked of the library itself)?"""
+    with torch.cuda.device(device):
+        return bool(_lib.lib().vmv_groupnorm_fused_fits_smem(C, rows_per_batch, nbatch))
 
 
 def layernorm_stats(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:

@@ -205,7 +205,11 @@ def _peer_exchange(x: torch.Tensor, B: int, Fl: int, HW: int, ctx: ShardCtx, dir
     p.done = ctx.base(ctx.rank) + c_off + 36
     p.world, p.rank, p.direction = P, ctx.rank, direction
     p.B, p.Fl, p.HWl, p.C = B, Fl, HWl, C
+    e0 = ops._prof_begin()
     _lib.check(_lib.lib().vmv_peer_exchange(ctypes.byref(p), ops._stream()), "vmv_peer_exchange")
+    if e0 is not None:                                 # tools/sharded_breakdown.py: every rank replays the same launches in lockstep
+        replay = lambda p=p, keep=x: _lib.check(_lib.lib().vmv_peer_exchange(ctypes.byref(p), ops._stream()), "vmv_peer_exchange")
+        ops._prof_end(e0, "peer_exchange", 0.0, 2.0 * nbytes, f"dir{direction} B{B} Fl{Fl} HWl{HWl} C{C} P{P}", replay)
     ctx.peer_ops += 1
     return ar.buf[d_off:d_off + nbytes].view(torch.float16).view(x.shape[0], C)
 
@@ -305,7 +309,11 @@ def gather_output(out: torch.Tensor, ctx: ShardCtx) -> torch.Tensor:
         p.nouter, p.inner_bytes = B * C, Fl * h * w * es
         p.dst_offset_bytes = (ctx.cfg_index * B * C * F + ctx.rank * Fl) * h * w * es
         p.dst_outer_stride_bytes = F * h * w * es
+        e0 = ops._prof_begin()
         _lib.check(_lib.lib().vmv_peer_allgather(ctypes.byref(p), ops._stream()), "vmv_peer_allgather")
+        if e0 is not None:
+            replay = lambda p=p, keep=out: _lib.check(_lib.lib().vmv_peer_allgather(ctypes.byref(p), ops._stream()), "vmv_peer_allgather")
+            ops._prof_end(e0, "peer_gather", 0.0, 2.0 * out.numel() * es, f"out {tuple(out.shape)} over {Wa} ranks", replay)
         ctx.peer_ops += 1
         return ar.buf[d_off:d_off + nbytes].view(out.dtype).view(Wc, B, C, F, h, w)
     g = _gather(out, ctx, all_ranks=True)                                      # [Wc*P, B, C, Fl, h, w]
