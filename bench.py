@@ -369,7 +369,7 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
         if sharded:
             par = (f"{sh.describe()}: ONE sample on {world} GPUs" + (", cond / uncond halves of the CFG pair on two rank groups" if sh.cfg_ways > 1 else "")
                    + (f", 24 frames sharded {sh.world}-way inside a group (layout exchange at the temporal segments + GroupNorm-statistic all-reduce)" if sh.world > 1 else "")
-                   + f"; {sh.peer_ops} peer-memory kernels + {sh.collectives} NCCL collectives per UNet call")
+                   + f"; {sh.fused_ops} layout exchanges inside GEMM epilogues + {sh.peer_ops} peer-memory kernels + {sh.collectives} NCCL collectives per UNet call")
         else:
             par = f"replicas x{world} (one sample per GPU, no collective)" if world > 1 else "single GPU"
         return dict(mode=mode, sharded=sharded, ms=ms, ms_e2e=ms_e2e, clk=clk, nsamp=nsamp, steps=steps, parallelism=par,

@@ -59,6 +59,25 @@ long long vmv_launch_count(void);
 enum { VMV_GEMM_LINEAR = 0, VMV_GEMM_CONV3X3 = 1, VMV_GEMM_TCONV3 = 2, VMV_GEMM_CONV3X3_S2 = 3, VMV_GEMM_UPCONV3X3 = 4 };
 enum { VMV_ACT_NONE = 0, VMV_ACT_SILU = 1, VMV_ACT_GEGLU = 2 };
 
+#ifndef VMV_PEER_MAX_RANKS
+#define VMV_PEER_MAX_RANKS 8
+#endif
+/* Multi-GPU sharding: vmv_peer_exchange (below) fused into this GEMM's epilogue.  The output rows are NOT written to D but
+ * straight into the tensors of the OTHER sharding layout in every rank's arena -- compute and collective as one kernel, tile by
+ * tile: the destination (rank q, row) of an output row is a pure function of its index
+ *   direction 0 (frame shard -> pixel shard): row (b, f, pixel)  -> rank q = pixel / HWl, row ((b*world + rank)*Fl + f)*HWl + pixel % HWl
+ *   direction 1 (pixel shard -> frame shard): row (b, fg, pl)    -> rank q = fg / Fl,      row ((b*Fl + fg % Fl)*world + rank)*HWl + pl
+ * -- and the kernel ends with the epoch-flag rendezvous of vmv_peer_exchange (same control-line layout), so when it completes
+ * this rank's whole destination tensor is in its memory.  dst[q] have leading dimension ldd.  CTA-pair kernel, register
+ * epilogue, no split-K (else VMV_ERR_UNSUPPORTED). */
+typedef struct vmv_gemm_scatter {
+    int32_t world, rank, direction, nowait;
+    int32_t B, Fl, HWl, pad_;
+    void* dst[VMV_PEER_MAX_RANKS];
+    void* flags[VMV_PEER_MAX_RANKS];
+    void* epoch; void* done;
+} vmv_gemm_scatter;
+
 typedef struct vmv_gemm_params {
     int32_t mode;
     int32_t M, N;               /* output rows / GEMM columns (GEGLU writes N/2 columns) */
@@ -88,6 +107,7 @@ typedef struct vmv_gemm_params {
      * One writer per slot (no atomics, no initialisation needed, bit-reproducible).  CTA-pair kernel without split-K /
      * GEGLU only (else VMV_ERR_UNSUPPORTED). */
     void* rowstats_out;
+    const vmv_gemm_scatter* scatter;   /* NULL = plain output to D */
     /* tuning (0 = auto) */
     int32_t block_n;            /* 64 (variant 1 only), 128, 160 or 256 */
     int32_t stages;             /* smem pipeline depth */
@@ -289,6 +309,7 @@ int vmv_ipc_import(const void* handle64, int64_t offset, void** out);
 
 /* sizeof() of the parameter structs as compiled, so a foreign-language binding can verify its mirrors. */
 int vmv_sizeof_gemm_params(void);
+int vmv_sizeof_gemm_scatter(void);
 int vmv_sizeof_attn_params(void);
 int vmv_sizeof_peer_exchange_params(void);
 int vmv_sizeof_peer_allreduce_params(void);

@@ -61,7 +61,7 @@ def main():
         relp = max(((oc - ref_c).norm() / ref_c.norm()).item(), ((ou - ref_u).norm() / ref_u.norm()).item())
         sh = model._engine().shard
         print(f"[sharded] rank {rank}/{world} [{item}: {sh.describe()}]: rel_l2 vs single-GPU {rel:.3e} (forward) {relp:.3e} (CFG pair), "
-              f"{sh.peer_ops} peer-memory kernels + {sh.collectives} NCCL collectives per forward", flush=True)
+              f"{sh.fused_ops} exchanges fused into GEMM epilogues + {sh.peer_ops} peer-memory kernels + {sh.collectives} NCCL collectives per forward", flush=True)
         ok *= 1 if (rel < 6e-3 and relp < 6e-3) else 0
         outs[item] = out
         # graphs with the captured exchanges

@@ -50,7 +50,7 @@ def test_library_exports_every_declared_symbol():
     L = ctypes.CDLL(_lib.LIBPATH)
     for sym in declared:
         assert hasattr(L, sym), sym
-    assert _lib.lib().vmv_abi_version() == 5
+    assert _lib.lib().vmv_abi_version() == 6
     assert ctypes.sizeof(_lib.GemmParams) == _lib.lib().vmv_sizeof_gemm_params()
     assert ctypes.sizeof(_lib.AttnParams) == _lib.lib().vmv_sizeof_attn_params()
     assert ctypes.sizeof(_lib.PeerExchangeParams) == _lib.lib().vmv_sizeof_peer_exchange_params()

@@ -89,6 +89,58 @@ def test_world1_with_real_wait_and_allreduce():
         assert torch.equal(res[r], want), r
 
 
+@pytest.mark.parametrize("P,B,F,HW,C,K,mode", [(2, 2, 24, 256, 320, 320, "linear"), (4, 1, 24, 64, 1280, 1280, "linear"),
+                                                (2, 1, 8, 256, 128, 64, "conv"), (4, 2, 8, 64, 128, 128, "tconv"), (8, 1, 24, 16, 1280, 640, "linear")])
+def test_gemm_scatter_simulated_ranks(P, B, F, HW, C, K, mode):
+    """vmv_gemm with `scatter`: the layout exchange inside the GEMM epilogue.  Every simulated rank runs its GEMM on its rows
+    of the source layout and the epilogue stores them straight into all ranks' destination-layout tensors; the result must
+    equal GEMM followed by the stand-alone exchange.  direction 0 (frames -> pixels) for linear / conv, 1 for the temporal conv."""
+    from videomv_b200 import _lib, ops, packing
+    Fl, HWl = F // P, HW // P
+    g = torch.Generator(device="cuda").manual_seed(3)
+    direction = 1 if mode == "tconv" else 0
+    if mode == "conv":
+        H = W = int(HW ** 0.5)
+        w = packing.pack_conv3x3(torch.randn(C, K, 3, 3, generator=g, device="cuda") * (9 * K) ** -0.5)
+    elif mode == "tconv":
+        w = packing.pack_tconv3(torch.randn(C, K, 3, 1, 1, generator=g, device="cuda") * (3 * K) ** -0.5)
+    else:
+        w = (torch.randn(C, K, generator=g, device="cuda") * K ** -0.5).half()
+    bias = torch.randn(C, generator=g, device="cuda")
+    rows = B * Fl * HW                                                   # == B * F * HWl
+    xs = [torch.randn(rows, K, generator=g, device="cuda").half() for _ in range(P)]
+    res = [torch.randn(rows, C, generator=g, device="cuda").half() for _ in range(P)]
+    dsts = [torch.zeros(rows, C, dtype=torch.float16, device="cuda") for _ in range(P)]
+    flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(P)]
+    plain = []
+    for r in range(P):
+        kw = dict(bias=bias, residual=res[r])
+        if mode == "conv":
+            kw.update(mode=ops.CONV3X3, geom=(1, B * Fl, H, W))
+        elif mode == "tconv":
+            kw.update(mode=ops.TCONV3, geom=(B, F, HWl, 1))
+        plain.append(ops.gemm(xs[r], w, **kw))
+        sc = _lib.GemmScatter()
+        sc.world, sc.rank, sc.direction, sc.nowait = P, r, direction, 1
+        sc.B, sc.Fl, sc.HWl = B, Fl, HWl
+        for q in range(P):
+            sc.dst[q] = dsts[q].data_ptr()
+            sc.flags[q] = flags[q].data_ptr()
+        sc.epoch = flags[r].data_ptr() + 32
+        sc.done = flags[r].data_ptr() + 36
+        ops.gemm(xs[r], w, out=dsts[r], scatter=sc, **kw)
+    torch.cuda.synchronize()
+    if direction == 0:       # source [B, Fl, P(q), HWl, C] on rank r -> dst_q [B, P(r), Fl, HWl, C]
+        full = torch.stack([pl.reshape(B, Fl, P, HWl, C) for pl in plain], 0)            # [r, B, Fl, q, HWl, C]
+        want = [full[:, :, :, q].permute(1, 0, 2, 3, 4).reshape(rows, C) for q in range(P)]
+    else:                    # source [B, P(q), Fl, HWl, C] on rank r -> dst_q [B, Fl, P(r), HWl, C]
+        full = torch.stack([pl.reshape(B, P, Fl, HWl, C) for pl in plain], 0)            # [r, B, q, Fl, HWl, C]
+        want = [full[:, :, q].permute(1, 2, 0, 3, 4).reshape(rows, C) for q in range(P)]
+    for q in range(P):
+        assert torch.equal(dsts[q], want[q].contiguous()), f"rank {q}"
+        assert flags[q][:P].tolist() == [1] * P and flags[q][8].item() == 1 and flags[q][9].item() == 0
+
+
 def test_allgather_simulated_ranks():
     """vmv_peer_allgather: the output all-gather of a sharded UNet call (frame shards x CFG halves), ranks simulated one after
     the other (nowait).  Every rank's buffer ends up holding [cfg half][B, C, F, h, w]; epochs advance by 2 per call."""

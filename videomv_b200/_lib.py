@@ -67,6 +67,16 @@ def build(force: bool = False, verbose: bool = False) -> str:
 c_i32, c_i64, c_f32, c_vp = ctypes.c_int32, ctypes.c_int64, ctypes.c_float, ctypes.c_void_p
 
 
+PEER_MAX = 8
+
+
+class GemmScatter(ctypes.Structure):
+    """Mirror of `vmv_gemm_scatter`."""
+    _fields_ = [("world", c_i32), ("rank", c_i32), ("direction", c_i32), ("nowait", c_i32),
+                ("B", c_i32), ("Fl", c_i32), ("HWl", c_i32), ("pad_", c_i32),
+                ("dst", c_vp * PEER_MAX), ("flags", c_vp * PEER_MAX), ("epoch", c_vp), ("done", c_vp)]
+
+
 class GemmParams(ctypes.Structure):
     """Mirror of `vmv_gemm_params` (include/videomv_b200.h)."""
     _fields_ = [
@@ -77,6 +87,7 @@ class GemmParams(ctypes.Structure):
         ("bias", c_vp), ("rowbias", c_vp), ("ld_rowbias", c_i64), ("rows_per_group", c_i32),
         ("residual", c_vp), ("ldr", c_i64), ("act", c_i32), ("ln_stats", c_vp), ("ln_colsum", c_vp),
         ("ln_stats_src_n", c_i32), ("ln_stats_src_bn", c_i32), ("ln_eps", c_f32), ("rowstats_out", c_vp),
+        ("scatter", ctypes.POINTER(GemmScatter)),
         ("block_n", c_i32), ("stages", c_i32), ("split_k", c_i32), ("variant", c_i32), ("w_static", c_i32),
         ("workspace", c_vp), ("workspace_bytes", c_i64),
     ]
@@ -130,6 +141,7 @@ SYMBOLS = {
     "vmv_abi_version": (ctypes.c_int, []),
     "vmv_launch_count": (ctypes.c_longlong, []),
     "vmv_sizeof_gemm_params": (ctypes.c_int, []),
+    "vmv_sizeof_gemm_scatter": (ctypes.c_int, []),
     "vmv_sizeof_attn_params": (ctypes.c_int, []),
     "vmv_sizeof_peer_exchange_params": (ctypes.c_int, []),
     "vmv_sizeof_peer_allreduce_params": (ctypes.c_int, []),
@@ -182,9 +194,10 @@ def lib() -> ctypes.CDLL:
         fn = getattr(L, name)           # AttributeError if the .so does not export a declared symbol
         fn.restype = res
         fn.argtypes = args
-    if L.vmv_abi_version() != 5:
+    if L.vmv_abi_version() != 6:
         raise RuntimeError("videomv_b200: ABI version mismatch between _lib.py and the built library")
     if (L.vmv_sizeof_gemm_params() != ctypes.sizeof(GemmParams) or
+            L.vmv_sizeof_gemm_scatter() != ctypes.sizeof(GemmScatter) or
             L.vmv_sizeof_attn_params() != ctypes.sizeof(AttnParams) or
             L.vmv_sizeof_peer_exchange_params() != ctypes.sizeof(PeerExchangeParams) or
             L.vmv_sizeof_peer_allreduce_params() != ctypes.sizeof(PeerAllreduceParams) or

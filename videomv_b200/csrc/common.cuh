@@ -374,4 +374,36 @@ __device__ __forceinline__ void stg256(void* p, const uint32_t (&v)[8]) {
 template <int N>
 __device__ __forceinline__ void bulk_wait_group() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory"); }
 
+
+// ------------------------------------------------------------------------------------------------
+// Epoch-flag rendezvous over peer memory (multi-GPU sharding: csrc/peer.cu, the peer GroupNorm in csrc/norm.cu).
+// flags[q] = rank q's flag line (8 x u32, one word per publishing rank); publish = "my data for epoch e is in your
+// memory", wait = "everyone's data for epoch e is in mine".  Release pattern: ONE system-scope fence by the publishing
+// thread (cumulative over the writes of the threads it has synchronised with at a CTA barrier or through an atomic, like
+// cooperative-groups grid.sync), then relaxed flag stores; acquire pattern: relaxed polls, then one fence.
+// A rank that never arrives traps (the launch fails) instead of hanging the GPU.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_relaxed_sys_u32(unsigned int* p, unsigned int v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned int ld_relaxed_sys_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void peer_publish(unsigned int* const* flags, int world, int rank, unsigned int e, int stride_words = 0) {
+    __threadfence_system();
+    for (int q = 0; q < world; ++q) st_relaxed_sys_u32(flags[q] + stride_words + rank, e);
+}
+__device__ __forceinline__ void peer_wait_all(unsigned int* const* flags, int world, int rank, unsigned int e, int stride_words = 0) {
+    for (int q = 0; q < world; ++q) {
+        unsigned long long spins = 0;
+        while ((int)(ld_relaxed_sys_u32(flags[rank] + stride_words + q) - e) < 0) {
+            if (++spins > (1ull << 27)) __trap();                // seconds: a peer that never arrives fails the launch
+            __nanosleep(20);
+        }
+    }
+    __threadfence_system();
+}
+
 }  // namespace vmv

@@ -67,7 +67,36 @@ struct GemmArgs {
     float ln_eps;
     float2* rowstats; // fp32 [M][2*n_tiles][2]: partial {mean, M2} of every output row per (N tile, epilogue warp half)
     int rowstats_nslots;
+    // multi-GPU: output rows go to the peers' tensors of the other sharding layout + epoch-flag rendezvous at the end (csrc/peer.cu)
+    int sc_world, sc_rank, sc_dir, sc_nowait;
+    int sc_B, sc_Fl, sc_HWl;
+    __half* sc_dst[VMV_PEER_MAX_RANKS];
+    unsigned int* sc_flags[VMV_PEER_MAX_RANKS];
+    unsigned int* sc_epoch;
+    unsigned int* sc_done;
 };
+
+// destination of output row `grow` when the epilogue scatters into the other sharding layout
+__device__ __forceinline__ __half* scatter_row(const GemmArgs& a, long long grow) {
+    const int P = a.sc_world;
+    const long long HWl = a.sc_HWl;
+    int q;
+    long long row;
+    if (a.sc_dir == 0) {                               // rows (b, f, pixel), pixel < P*HWl
+        const long long HW = HWl * P;
+        const long long bf = grow / HW, pix = grow - bf * HW;
+        const long long b = bf / a.sc_Fl, f = bf - b * a.sc_Fl;
+        q = (int)(pix / HWl);
+        row = ((b * P + a.sc_rank) * a.sc_Fl + f) * HWl + (pix - (long long)q * HWl);
+    } else {                                           // rows (b, fg, pl), fg < P*Fl
+        const long long F = (long long)a.sc_Fl * P;
+        const long long bf = grow / HWl, pl = grow - bf * HWl;
+        const long long b = bf / F, fg = bf - b * F;
+        q = (int)(fg / a.sc_Fl);
+        row = ((b * a.sc_Fl + (fg - (long long)q * a.sc_Fl)) * P + a.sc_rank) * HWl + pl;
+    }
+    return a.sc_dst[q] + row * a.ldd;
+}
 
 constexpr int LN_MAX_SLOTS = 10;      // 2 x ceil(1280 / 256)
 
@@ -708,6 +737,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             int nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
             if (nvalid < 0) nvalid = 0;
             const __half* resrow = (a.residual && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
+            __half* drow = nullptr;                              // my output row (possibly in a peer's memory)
+            if (valid) drow = a.sc_world ? scatter_row(a, grow) : a.D + grow * a.ldd;
             uint32_t rcur[16];
             float2 ln_ms = make_float2(0.f, 1.f);
             if (a.fast_epi) {
@@ -872,7 +903,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
-                        __half* dst = a.D + grow * a.ldd + col0 + c;
+                        __half* dst = drow + col0 + c;
                         stg256(dst, *reinterpret_cast<uint32_t(*)[8]>(&o[0]));
                         stg256(dst + 16, *reinterpret_cast<uint32_t(*)[8]>(&o[8]));
                     }
@@ -896,6 +927,23 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         }
     }
 
+    if (a.sc_world) {
+        // fused layout exchange: every CTA's remote stores are performed (system scope), the last CTA of this rank publishes
+        // the epoch in every peer's flag line and waits for the peers' epochs -- same protocol as peer_exchange_kernel
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(a.sc_done, 1u);
+            if (prev == gridDim.x - 1) {
+                __threadfence();
+                *a.sc_done = 0;
+                const unsigned int e = *a.sc_epoch + 1;
+                *a.sc_epoch = e;
+                peer_publish(a.sc_flags, a.sc_world, a.sc_rank, e);
+                if (!a.sc_nowait) peer_wait_all(a.sc_flags, a.sc_world, a.sc_rank, e);
+            }
+        }
+    }
     tc_fence_before();
     cluster_sync_all();
     if (warp == 1) tmem_dealloc_2sm<TCOLS>(tmem_base);
@@ -1094,7 +1142,7 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
     memset(&a, 0, sizeof(a));
     VMV_CHECK_ARG(p->M > 0 && p->N > 0, "vmv_gemm: M, N must be positive (M=%d N=%d)", p->M, p->N);
     VMV_CHECK_ARG(p->N % 16 == 0, "vmv_gemm: N=%d must be a multiple of 16", p->N);
-    VMV_CHECK_ARG(p->A1 && p->W && p->D, "vmv_gemm: null A1/W/D");
+    VMV_CHECK_ARG(p->A1 && p->W && (p->D || p->scatter), "vmv_gemm: null A1/W/D");
     VMV_CHECK_ARG(p->K1 > 0 && p->K1 % BK == 0 && p->K2 % BK == 0,
                   "vmv_gemm: K1=%d, K2=%d must be multiples of %d", p->K1, p->K2, BK);
     VMV_CHECK_ARG(p->lda1 % 8 == 0 && p->ldw % 8 == 0 && p->ldd % 8 == 0, "vmv_gemm: leading dims must be multiples of 8");
@@ -1129,6 +1177,23 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
         VMV_CHECK_ARG(a.ln_nslots <= LN_MAX_SLOTS, "vmv_gemm: %d LayerNorm statistic slots (max %d)", a.ln_nslots, LN_MAX_SLOTS);
     }
     a.rowstats = static_cast<float2*>(p->rowstats_out);
+    if (p->scatter != nullptr) {
+        const vmv_gemm_scatter* sc = p->scatter;
+        VMV_CHECK_ARG(sc->world >= 1 && sc->world <= VMV_PEER_MAX_RANKS && sc->rank >= 0 && sc->rank < sc->world, "vmv_gemm scatter: bad world/rank");
+        VMV_CHECK_ARG(sc->direction == 0 || sc->direction == 1, "vmv_gemm scatter: direction must be 0 or 1");
+        VMV_CHECK_ARG(sc->B > 0 && sc->Fl > 0 && sc->HWl > 0 && (long long)sc->B * sc->Fl * sc->HWl * sc->world == p->M,
+                      "vmv_gemm scatter: B*Fl*HWl*world must equal M");
+        VMV_CHECK_ARG(sc->epoch && sc->done && p->ldd % 16 == 0, "vmv_gemm scatter: null epoch/done, or ldd not a multiple of 16");
+        a.sc_world = sc->world; a.sc_rank = sc->rank; a.sc_dir = sc->direction; a.sc_nowait = sc->nowait;
+        a.sc_B = sc->B; a.sc_Fl = sc->Fl; a.sc_HWl = sc->HWl;
+        for (int q = 0; q < sc->world; ++q) {
+            VMV_CHECK_ARG(sc->dst[q] && sc->flags[q] && (reinterpret_cast<uintptr_t>(sc->dst[q]) & 31) == 0, "vmv_gemm scatter: bad dst/flags for rank %d", q);
+            a.sc_dst[q] = static_cast<__half*>(sc->dst[q]);
+            a.sc_flags[q] = static_cast<unsigned int*>(sc->flags[q]);
+        }
+        a.sc_epoch = static_cast<unsigned int*>(sc->epoch);
+        a.sc_done = static_cast<unsigned int*>(sc->done);
+    }
     VMV_CHECK_ARG((p->ln_stats == nullptr) == (p->ln_colsum == nullptr), "vmv_gemm: ln_stats and ln_colsum go together");
     if (p->rowbias) VMV_CHECK_ARG(p->ld_rowbias % 8 == 0, "vmv_gemm: ld_rowbias must be a multiple of 8");
     if (p->residual) VMV_CHECK_ARG(p->ldr % 8 == 0, "vmv_gemm: ldr must be a multiple of 8");
@@ -1313,6 +1378,10 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                              ? 1 : 0;
         }
         a.rowstats_nslots = 2 * pl.n_tiles;
+        if (a.sc_world && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
+            set_error("vmv_gemm: scatter needs the CTA-pair kernel's register epilogue (no split-K, no GEGLU, N %% 32 == 0, 32 B aligned rows)");
+            return VMV_ERR_UNSUPPORTED;
+        }
         if (a.rowstats && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
             set_error("vmv_gemm: rowstats_out needs the CTA-pair kernel's register epilogue (no split-K, no GEGLU, N %% 32 == 0, "
                       "32 B aligned rows)");
@@ -1322,8 +1391,8 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
         else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
         else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
-        if (a.rowstats) {
-            set_error("vmv_gemm: rowstats_out is not available in the one-tile-per-CTA kernel (variant 1)");
+        if (a.rowstats || a.sc_world) {
+            set_error("vmv_gemm: rowstats_out / scatter are not available in the one-tile-per-CTA kernel (variant 1)");
             return VMV_ERR_UNSUPPORTED;
         }
         dim3 grid(pl.n_tiles, pl.m_tiles, pl.splits);

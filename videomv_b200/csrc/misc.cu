@@ -270,12 +270,13 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
 using namespace vmv;
 
 extern "C" const char* vmv_last_error(void) { return g_err; }
-extern "C" int vmv_abi_version(void) { return 5; }
+extern "C" int vmv_abi_version(void) { return 6; }
 extern "C" long long vmv_launch_count(void) { return g_launches.load(); }
 extern "C" int vmv_sizeof_gemm_params(void) { return (int)sizeof(vmv_gemm_params); }
 extern "C" int vmv_sizeof_attn_params(void) { return (int)sizeof(vmv_attn_params); }
 extern "C" int vmv_sizeof_peer_exchange_params(void) { return (int)sizeof(vmv_peer_exchange_params); }
 extern "C" int vmv_sizeof_peer_allreduce_params(void) { return (int)sizeof(vmv_peer_allreduce_params); }
+extern "C" int vmv_sizeof_gemm_scatter(void) { return (int)sizeof(vmv_gemm_scatter); }
 extern "C" int vmv_sizeof_gn_peer(void) { return (int)sizeof(vmv_gn_peer); }
 extern "C" int vmv_sizeof_peer_allgather_params(void) { return (int)sizeof(vmv_peer_allgather_params); }
 

@@ -387,15 +387,6 @@ struct GnPeer {
     long long stat_rows;                          // rows per chunk summed over all ranks
 };
 
-__device__ __forceinline__ void gn_st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int gn_ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -493,19 +484,11 @@ gn_smem_kernel(const __half* __restrict__ x1, long long ld1, int C1, const __hal
                 const long long o = (((long long)pe.rank * nb + batch) * GN_GROUPS + t) * 2;
                 for (int qq = 0; qq < pe.world; ++qq) { pe.slots[qq][o] = s_tot[2 * t]; pe.slots[qq][o + 1] = s_tot[2 * t + 1]; }
             }
-            __threadfence_system();
             __syncthreads();
-            if (t == 0)
-                for (int qq = 0; qq < pe.world; ++qq) gn_st_release_sys(pe.flags[qq] + batch * 16 + pe.rank, peer_epoch);
+            if (t == 0) peer_publish(pe.flags, pe.world, pe.rank, peer_epoch, batch * 16);
         }
         if (t == 0) {
-            for (int qq = 0; qq < pe.world; ++qq) {
-                unsigned long long spins = 0;
-                while ((int)(gn_ld_acquire_sys(pe.flags[pe.rank] + batch * 16 + qq) - peer_epoch) < 0) {
-                    if (++spins > (1ull << 27)) __trap();        // seconds: a peer that never arrives fails the launch
-                    __nanosleep(20);
-                }
-            }
+            peer_wait_all(pe.flags, pe.world, pe.rank, peer_epoch, batch * 16);
             if (blockIdx.x == 0) *(pe.epoch + batch * 16) = peer_epoch;
         }
         __syncthreads();

@@ -34,28 +34,10 @@ struct PeerExArgs {
     long long chunk_vecs;          // HWl * C / 8
 };
 
-__device__ __forceinline__ void st_release_sys(unsigned int* p, unsigned int v) {
-    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ unsigned int ld_acquire_sys(const unsigned int* p) {
-    unsigned int v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
-}
-
 // Publish `e` in slot `rank` of every rank's flag array, then wait until every rank's epoch has reached `e` in mine.
-// A rank that never arrives traps (the launch fails) instead of hanging the GPU.
 __device__ __forceinline__ void peer_signal_and_wait(unsigned int* const* flags, int world, int rank, unsigned int e, int nowait) {
-    __threadfence_system();
-    for (int q = 0; q < world; ++q) st_release_sys(flags[q] + rank, e);
-    if (nowait) return;
-    for (int q = 0; q < world; ++q) {
-        unsigned long long spins = 0;
-        while ((int)(ld_acquire_sys(flags[rank] + q) - e) < 0) {
-            if (++spins > (1ull << 27)) __trap();                // seconds: a peer that never arrives fails the launch
-            __nanosleep(20);
-        }
-    }
+    peer_publish(flags, world, rank, e);
+    if (!nowait) peer_wait_all(flags, world, rank, e);
 }
 
 __global__ void __launch_bounds__(256)
@@ -80,9 +62,9 @@ peer_exchange_kernel(const PeerExArgs a) {
         }
         a.dst[q][doff + v] = a.src[so + v];
     }
-    __threadfence_system();                // my remote stores are performed before this CTA counts as arrived
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();            // the CTA's remote stores are performed before it counts as arrived (cumulative over the barrier)
         const unsigned int prev = atomicAdd(a.done, 1u);
         if (prev == gridDim.x - 1) {       // last CTA of this rank: everything this rank had to send is on its way
             __threadfence();
@@ -110,7 +92,6 @@ peer_allreduce_kernel(const PeerArArgs a) {
         const double v = a.data[i];
         for (int q = 0; q < a.world; ++q) a.slots[q][(long long)a.rank * a.n + i] = v;
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
         const unsigned int e = *a.epoch + 1;
@@ -147,19 +128,8 @@ peer_allgather_kernel(const PeerAgArgs a) {
     // every rank has entered this call.  Epochs advance by 2 per call: odd = ready, even = data delivered.
     if (threadIdx.x == 0) {
         const unsigned int e0 = *a.epoch + 1;               // stable until the last CTA of this launch has finished copying
-        if (blockIdx.x == 0) {
-            __threadfence_system();
-            for (int q = 0; q < a.world; ++q) st_release_sys(a.flags[q] + a.rank, e0);
-        }
-        if (!a.nowait) {
-            for (int q = 0; q < a.world; ++q) {
-                unsigned long long spins = 0;
-                while ((int)(ld_acquire_sys(a.flags[a.rank] + q) - e0) < 0) {
-                    if (++spins > (1ull << 27)) __trap();
-                    __nanosleep(20);
-                }
-            }
-        }
+        if (blockIdx.x == 0) peer_publish(a.flags, a.world, a.rank, e0);
+        if (!a.nowait) peer_wait_all(a.flags, a.world, a.rank, e0);
     }
     __syncthreads();
     const long long total = a.nouter * a.inner_vecs * a.world;
@@ -171,9 +141,9 @@ peer_allgather_kernel(const PeerAgArgs a) {
         const long long o = j / a.inner_vecs, v = j - o * a.inner_vecs;
         a.dst[q][a.base_vecs + o * a.outer_stride_vecs + v] = a.src[j];
     }
-    __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
+        __threadfence_system();
         const unsigned int prev = atomicAdd(a.done, 1u);
         if (prev == gridDim.x - 1) {
             __threadfence();

@@ -202,6 +202,25 @@ class UNetEngine:
         nkb = w.w.shape[1] // 64
         pairs = SM_COUNT // 2
         split = 0
+        # to_layout = (direction, S): this GEMM's output feeds a layout exchange of the frame-sharded multi-GPU mode
+        # (0: frames -> pixels before a temporal segment, 1: pixels -> frames after it).  With peer memory the exchange
+        # happens INSIDE the epilogue (rows stored straight into the peers' tensors + flag rendezvous at the kernel's end).
+        to_layout = kw.pop("to_layout", None)
+        fs = self._fs if to_layout is not None else None
+        if fs is not None:
+            direction, S_ = to_layout
+            B_, Fl_, HW_ = S_["B"], S_["F"], S_["H"] * S_["W"]
+            if (fs.mode == "peer" and fs.fused_exchange and kw.get("act", 0) != ops.ACT_GEGLU and N % 32 == 0
+                    and not kw.get("want_stats", False)):
+                sc, dst = parallel.make_scatter(M, N, B_, Fl_, HW_, fs, direction)
+                ln = kw.pop("ln", None)
+                if ln is not None:
+                    kw.update(ln_stats=ln[0], ln_src=ln[1], ln_colsum=w.colsum)
+                return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, out=dst, scatter=sc, **kw)
+            out = self._gemm(a, w, **kw)
+            if direction == 0:
+                return parallel.frames_to_pixels(out, B_, Fl_, HW_, fs)
+            return parallel.pixels_to_frames(out, B_, Fl_, HW_, fs)
         if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs and mode != ops.UPCONV3X3:
             # time(s) ~ T_full / utilisation(s) + cost of the fp32 partials (write + read back + extra launch)
             t_full = 2.0 * M * N * nkb * 64 / 0.9e15
@@ -251,15 +270,16 @@ class UNetEngine:
             res = self._gemm(x, d["skip"], a2=skip)
         else:
             res = x
-        h2 = self._gemm(a1, d["c2"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), residual=res)
-        # temporal tail (util.py:1381-1392) on the pixel-sharded layout when the sample is spread over ranks
-        Ff, HWt, to_frames = self._enter_temporal(S)
-        h2t = self._to_pixels(h2, S)
+        # temporal tail (util.py:1381-1392) on the pixel-sharded layout when the sample is spread over ranks: conv2's
+        # epilogue delivers its rows in that layout, the last temporal conv's epilogue brings them back
+        h2t = self._gemm(a1, d["c2"], mode=ops.CONV3X3, geom=(1, B * Fr, H, W), residual=res, to_layout=(0, S))
+        Ff, HWt = self._temporal_geom(S)
         cur = h2t
         for i, (gn, wt) in enumerate(d["t"]):
             a = ops.groupnorm(cur, *gn, rows_per_batch=Ff * HWt, eps=1e-5, silu=True, scratch=self._gn_arena, **self._gn5d_kw(S))
-            cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Ff, HWt, 1), residual=h2t if i == 3 else None)
-        return to_frames(cur)
+            cur = self._gemm(a, wt, mode=ops.TCONV3, geom=(B, Ff, HWt, 1), residual=h2t if i == 3 else None,
+                             to_layout=(1, S) if i == 3 else None)
+        return cur
 
     # ---- frame-shard <-> pixel-shard plumbing (identity on a single GPU) -----------------------------------------
     @property
@@ -268,19 +288,13 @@ class UNetEngine:
         sh = self.shard
         return sh if (sh is not None and sh.frame_sharded) else None
 
-    def _enter_temporal(self, S):
-        """Returns (frames, pixels per rank, fn back to the frame layout) for a temporal segment."""
+    def _temporal_geom(self, S):
+        """(frames, pixels per rank) of a temporal segment: all frames of HW/P pixels when the sample is frame-sharded."""
         HW = S["H"] * S["W"]
         ctx = self._fs
         if ctx is None:
-            return S["F"], HW, (lambda z: z)
-        return S["F"] * ctx.world, HW // ctx.world, (lambda z: parallel.pixels_to_frames(z, S["B"], S["F"], HW, ctx))
-
-    def _to_pixels(self, x, S):
-        ctx = self._fs
-        if ctx is None:
-            return x
-        return parallel.frames_to_pixels(x, S["B"], S["F"], S["H"] * S["W"], ctx)
+            return S["F"], HW
+        return S["F"] * ctx.world, HW // ctx.world
 
     def _gn5d_kw(self, S):
         ctx = self._fs
@@ -328,7 +342,7 @@ class UNetEngine:
         g = self._gemm(h, tb["ff1"], act=ops.ACT_GEGLU, ln=hst)
         return self._gemm(g, tb["ff2"], residual=h)
 
-    def _spatial(self, d, x, S):
+    def _spatial(self, d, x, S, to_pixels=False):
         HW = S["H"] * S["W"]
         a = ops.groupnorm(x, *d["gn"], rows_per_batch=HW, eps=1e-6, silu=False, scratch=self._gn_arena)
         h, hst = self._gemm(a, d["pin"], want_stats=True)
@@ -337,29 +351,36 @@ class UNetEngine:
         off = d["kv_off"]
         kv = (kvall[:, off:off + C], kvall[:, off + C:off + 2 * C], S["L"], kvall.stride(0))
         h = self._tblock(d["tb"], h, hst, S, d["heads"], temporal=False, kv=kv)
-        return self._gemm(h, d["pout"], residual=x)
+        # a TemporalTransformer follows: proj_out's epilogue hands the rows over in the pixel-sharded layout
+        return self._gemm(h, d["pout"], residual=x, to_layout=(0, S) if to_pixels else None)
 
-    def _temporal(self, d, x, S):
-        Ff, HWt, to_frames = self._enter_temporal(S)
-        xt = self._to_pixels(x, S)
+    def _temporal(self, d, xt, S):
+        """`xt` is already in the temporal layout (== the frame layout on one GPU)."""
+        Ff, HWt = self._temporal_geom(S)
         a = ops.groupnorm(xt, *d["gn"], rows_per_batch=Ff * HWt, eps=1e-6, silu=False, scratch=self._gn_arena, **self._gn5d_kw(S))
         h, hst = self._gemm(a, d["pin"], want_stats=True)
         h = self._tblock(d["tb"], h, hst, S, d["heads"], temporal=True, Fr=Ff, HW=HWt)
-        return to_frames(self._gemm(h, d["pout"], residual=xt))
+        return self._gemm(h, d["pout"], residual=xt, to_layout=(1, S))
 
     def _run_block(self, d, x, skip, S):
         k = d["kind"]
         if k == "list":
-            for it in d["items"]:
-                x = self._run_block(it, x, skip, S)
+            items = d["items"]
+            for i, it in enumerate(items):
+                if it["kind"] == "spatial":
+                    x = self._spatial(it, x, S, to_pixels=i + 1 < len(items) and items[i + 1]["kind"] == "temporal")
+                elif it["kind"] == "temporal":
+                    if i == 0 or items[i - 1]["kind"] != "spatial":
+                        fs = self._fs
+                        if fs is not None:
+                            x = parallel.frames_to_pixels(x, S["B"], S["F"], S["H"] * S["W"], fs)
+                    x = self._temporal(it, x, S)
+                else:
+                    x = self._run_block(it, x, skip, S)
                 skip = None
             return x
         if k == "res":
             return self._res(d, x, skip, S)
-        if k == "spatial":
-            return self._spatial(d, x, S)
-        if k == "temporal":
-            return self._temporal(d, x, S)
         if k == "down":
             n, H, W = S["B"] * S["F"], S["H"], S["W"]
             S["H"], S["W"] = H // 2, W // 2
@@ -501,8 +522,7 @@ class UNetEngine:
         for blk in self.enc:
             h = self._run_block(blk, h, None, S)
             skips.append(h)
-        for blk in self.mid:
-            h = self._run_block(blk, h, None, S)
+        h = self._run_block({"kind": "list", "items": self.mid}, h, None, S)
         for blk in self.dec:
             h = self._run_block(blk, h, skips.pop(), S)
         a = ops.groupnorm(h, *self.head_gn, rows_per_batch=S["H"] * S["W"], eps=1e-5, silu=True, scratch=self._gn_arena)

@@ -56,7 +56,7 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
          geom: Optional[Tuple[int, int, int, int]] = None, block_n: int = 0, stages: int = 0, split_k: int = 0,
          workspace: Optional[torch.Tensor] = None, variant: int = 0, ln_stats: Optional[torch.Tensor] = None,
          ln_colsum: Optional[torch.Tensor] = None, w_static: bool = False, ln_src: Optional[Tuple[int, int]] = None,
-         ln_eps: float = 1e-5, rowstats_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         ln_eps: float = 1e-5, rowstats_out: Optional[torch.Tensor] = None, scatter=None) -> torch.Tensor:
     """D = epilogue(A (*) W^T).  See `vmv_gemm` in include/videomv_b200.h.
 
     a1 [M,K1] (linear) or the channels-last activation [B*F*H*W, Cin] (conv modes, geom=(B,F,H,W));
@@ -109,6 +109,8 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
             raise ValueError(f"gemm rowstats_out must be a contiguous fp32 [M,{nsl},2] tensor")
         p.rowstats_out = rowstats_out.data_ptr()
     p.w_static = 1 if w_static else 0
+    if scatter is not None:                     # _lib.GemmScatter: rows go to the peers' tensors of the other sharding layout; `out` = mine
+        p.scatter = ctypes.pointer(scatter)
     if split_k > 1:
         need = _lib.lib().vmv_gemm_workspace_bytes(ctypes.byref(p))
         if need < 0:
@@ -120,12 +122,12 @@ def gemm(a1: torch.Tensor, w: torch.Tensor, *, a2: Optional[torch.Tensor] = None
     check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
     if e0 is not None:
         ktot = 9 * K1 if mode == UPCONV3X3 else w.shape[1]          # algorithmic FLOPs: the 9-tap conv on the upsampled image
-        keep = (a1, a2, w, out, bias, rowbias, residual, workspace, ln_stats, ln_colsum, rowstats_out)   # alive for replays
+        keep = (a1, a2, w, out, bias, rowbias, residual, workspace, ln_stats, ln_colsum, rowstats_out, scatter)   # alive for replays
         replay = lambda p=p, keep=keep: check(_lib.lib().vmv_gemm(ctypes.byref(p), _stream()), "vmv_gemm")
         k_in = K1 + (a2.shape[1] if a2 is not None else 0)               # activation columns actually read (conv modes: Cin)
         _prof_end(e0, "gemm_tc", 2.0 * M * N * ktot, 2.0 * (M * k_in + N * ktot + M * n_out * (2 if residual is not None else 1)),
                   f"mode{mode} M{M} N{N} K{ktot} act{act} res{int(residual is not None)} rb{int(rowbias is not None)} "
-                  f"split{split_k}", replay)
+                  f"split{split_k}" + ("" if scatter is None else f" scatter{scatter.direction}P{scatter.world}"), replay)
     return out
 
 

@@ -133,7 +133,8 @@ class ShardCtx:
         self.rank = self.rank_all % self.world
         self.members = [self.cfg_index * self.world + i for i in range(self.world)]
         self.collectives = 0          # NCCL / gloo collectives issued per forward (reported by bench.py)
-        self.peer_ops = 0             # peer-memory exchange / all-reduce kernels issued per forward
+        self.peer_ops = 0             # peer-memory exchange / all-reduce / peer-GroupNorm / gather kernels issued per forward
+        self.fused_ops = 0            # layout exchanges done inside a GEMM epilogue (no kernel of their own)
         mode = exchange or EXCHANGE or ("peer" if (device is not None and torch.device(device).type == "cuda") else "gather")
         if mode not in ("peer", "gather", "a2a"):
             raise ValueError(f"VMV_SHARD_EXCHANGE={mode!r}: expected peer, gather or a2a")
@@ -141,6 +142,9 @@ class ShardCtx:
         # 5-D GroupNorm in the pixel layout: "1" = one smem-resident kernel with the cross-GPU statistics sum inside
         # (vmv_groupnorm_fused_peer); "0" = statistics kernel + peer all-reduce kernel + apply kernel
         self.fused_gn = os.environ.get("VMV_SHARD_FUSED_GN", "1") != "0"
+        # layout exchanges: "1" = inside the epilogue of the GEMM that produces the exchanged tensor (vmv_gemm scatter);
+        # "0" = one vmv_peer_exchange kernel per exchange
+        self.fused_exchange = os.environ.get("VMV_SHARD_FUSED_EXCHANGE", "1") != "0"
         self.peer: Optional[PeerArena] = None
         self.group = group            # the frame group (torch.distributed modes)
         if mode == "peer":
@@ -163,6 +167,7 @@ class ShardCtx:
     def begin_forward(self):
         self.collectives = 0
         self.peer_ops = 0
+        self.fused_ops = 0
         if self.peer is not None:
             self.peer.begin_forward()
 
@@ -212,6 +217,29 @@ def _peer_exchange(x: torch.Tensor, B: int, Fl: int, HW: int, ctx: ShardCtx, dir
         ops._prof_end(e0, "peer_exchange", 0.0, 2.0 * nbytes, f"dir{direction} B{B} Fl{Fl} HWl{HWl} C{C} P{P}", replay)
     ctx.peer_ops += 1
     return ar.buf[d_off:d_off + nbytes].view(torch.float16).view(x.shape[0], C)
+
+
+def make_scatter(rows: int, C: int, B: int, Fl: int, HW: int, ctx: ShardCtx, direction: int):
+    """For a GEMM whose output [rows, C] should land in the OTHER layout (direction 0: frames -> pixels, 1: pixels -> frames):
+    allocate the destination tensor at the same arena offset on every rank + a control line and return
+    (vmv_gemm_scatter struct, this rank's destination tensor).  The exchange then happens inside the GEMM's epilogue
+    (`ops.gemm(..., out=dst, scatter=struct)`): no exchange kernel, no extra pass over the tensor."""
+    from . import _lib
+    ar = ctx.peer
+    P = ctx.world
+    nbytes = rows * C * 2
+    d_off = ar.take_data(nbytes)
+    c_off = ar.take_ctrl(64)
+    sc = _lib.GemmScatter()
+    sc.world, sc.rank, sc.direction = P, ctx.rank, direction
+    sc.B, sc.Fl, sc.HWl = B, Fl, HW // P
+    for q in range(P):
+        sc.dst[q] = ctx.base(q) + d_off
+        sc.flags[q] = ctx.base(q) + c_off
+    sc.epoch = ctx.base(ctx.rank) + c_off + 32
+    sc.done = ctx.base(ctx.rank) + c_off + 36
+    ctx.fused_ops += 1
+    return sc, ar.buf[d_off:d_off + nbytes].view(torch.float16).view(rows, C)
 
 
 def frames_to_pixels(x: torch.Tensor, B: int, Fl: int, HW: int, ctx: ShardCtx) -> torch.Tensor:
