@@ -447,10 +447,10 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                     f.write(f"| {desc} | {n} | {us:.1f} | {n * us / 1e3:.3f} | {100 * n * us / (dev_ms * 1e3):.1f}% | {fl / us / 1e6:.0f} |\n")
                 f.write(f"gemm total {dev_ms:.3f} ms per B=2 forward ({len(rows)} distinct shapes)\n")
         achieved = g[1] / (dev_ms * 1e-3) / 1e12
-        # DRAM traffic of the same kernel family from the committed ncu capture of one forward (profiles/r1_traffic.json,
+        # DRAM traffic of the same kernel family from the committed ncu capture of one forward (profiles/r2_traffic.json,
         # made by tools/summarize_traffic.py): bytes per launch, like `achieved` is FLOPs per launch / time per launch
         traffic, alg_bytes = None, sum(r_[2] for r_ in prof if r_[0] == "gemm_tc")
-        tj = os.path.join(ROOT, "profiles", "r1_traffic.json")
+        tj = os.path.join(ROOT, "profiles", "r2_traffic.json")
         if os.path.isfile(tj):
             try:
                 tr = json.load(open(tj)).get("gemm_tc2_kernel")

@@ -89,9 +89,11 @@ def test_world1_with_real_wait_and_allreduce():
         assert torch.equal(res[r], want), r
 
 
-@pytest.mark.parametrize("P,B,F,HW,C,K,mode", [(2, 2, 24, 256, 320, 320, "linear"), (4, 1, 24, 64, 1280, 1280, "linear"),
-                                                (2, 1, 8, 256, 128, 64, "conv"), (4, 2, 8, 64, 128, 128, "tconv"), (8, 1, 24, 16, 1280, 640, "linear")])
-def test_gemm_scatter_simulated_ranks(P, B, F, HW, C, K, mode):
+@pytest.mark.parametrize("P,B,F,HW,C,K,mode,split", [
+    (2, 2, 24, 256, 320, 320, "linear", 0), (4, 1, 24, 64, 1280, 1280, "linear", 0), (2, 1, 8, 256, 128, 64, "conv", 0),
+    (4, 2, 8, 64, 128, 128, "tconv", 0), (8, 1, 24, 16, 1280, 640, "linear", 0),
+    (2, 1, 24, 16, 1280, 2560, "linear", 4), (2, 1, 8, 16, 256, 512, "tconv", 3), (4, 1, 4, 64, 128, 256, "conv", 4)])
+def test_gemm_scatter_simulated_ranks(P, B, F, HW, C, K, mode, split):
     """vmv_gemm with `scatter`: the layout exchange inside the GEMM epilogue.  Every simulated rank runs its GEMM on its rows
     of the source layout and the epilogue stores them straight into all ranks' destination-layout tensors; the result must
     equal GEMM followed by the stand-alone exchange.  direction 0 (frames -> pixels) for linear / conv, 1 for the temporal conv."""
@@ -114,7 +116,7 @@ def test_gemm_scatter_simulated_ranks(P, B, F, HW, C, K, mode):
     flags = [torch.zeros(16, dtype=torch.int32, device="cuda") for _ in range(P)]
     plain = []
     for r in range(P):
-        kw = dict(bias=bias, residual=res[r])
+        kw = dict(bias=bias, residual=res[r], split_k=split)         # split-K: the finish kernel scatters
         if mode == "conv":
             kw.update(mode=ops.CONV3X3, geom=(1, B * Fl, H, W))
         elif mode == "tconv":

@@ -66,6 +66,10 @@ def main():
             acc += ms
             print(f"| {f} | {sum(r[1] for r in rows)} launches | {ms:.3f} ms |")
         print(f"| sum of families | | {acc:.3f} ms |\n| whole call, graph replay (all ranks in lockstep) | {model.graph_launches()} kernels | {total:.3f} ms |")
+        print("\ngemm_tc launches that feed a layout exchange (res1 + mode 1 conv2 / mode 0 proj_out -> pixels; mode 2 / mode 0 -> frames):")
+        for desc, n, fl, us, by in sorted(out["gemm_tc"], key=lambda r: r[0]):
+            if "scatter" in desc or (" res1 " in desc and ("mode1" in desc or "mode2" in desc or "mode0" in desc) and "act0" in desc):
+                print(f"| {desc} | {n} | {us:.1f} us | {n * us / 1e3:.3f} ms |")
         for f in ("peer_exchange", "groupnorm_peer", "peer_gather"):
             print(f"\n{f}:")
             for desc, n, fl, us, by in sorted(out[f], key=lambda r: -r[1] * r[3]):

@@ -949,50 +949,68 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     if (warp == 1) tmem_dealloc_2sm<TCOLS>(tmem_base);
 }
 
-// Reduce split-K partials and apply the (non-GEGLU) epilogue.  One thread per 8 output columns.
+// Reduce split-K partials and apply the (non-GEGLU) epilogue.  One thread per 8 output columns.  With `scatter` the rows go
+// to the peers' tensors of the other sharding layout (coalesced 16 B stores) and the kernel ends with the flag rendezvous.
 __global__ void splitk_finish_kernel(const float* __restrict__ partial, int splits, int M, int N, GemmArgs a) {
     pdl_launch_dependents();
     pdl_wait();
     const int nvec = N / 8;
     long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (long long)M * nvec) return;
-    const long long row = idx / nvec;
-    const int n = (int)(idx % nvec) * 8;
-    float x[8];
+    if (idx < (long long)M * nvec) {
+        const long long row = idx / nvec;
+        const int n = (int)(idx % nvec) * 8;
+        float x[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) x[j] = 0.f;
-    for (int s = 0; s < splits; ++s) {
-        const float4* p = reinterpret_cast<const float4*>(partial + ((long long)s * M + row) * N + n);
-        float4 u = p[0], w = p[1];
-        x[0] += u.x; x[1] += u.y; x[2] += u.z; x[3] += u.w;
-        x[4] += w.x; x[5] += w.y; x[6] += w.z; x[7] += w.w;
-    }
-    if (a.ln_stats) {
-        const float2 ms = ln_row_stats(a, row);
+        for (int j = 0; j < 8; ++j) x[j] = 0.f;
+        for (int s = 0; s < splits; ++s) {
+            const float4* p = reinterpret_cast<const float4*>(partial + ((long long)s * M + row) * N + n);
+            float4 u = p[0], w = p[1];
+            x[0] += u.x; x[1] += u.y; x[2] += u.z; x[3] += u.w;
+            x[4] += w.x; x[5] += w.y; x[6] += w.z; x[7] += w.w;
+        }
+        if (a.ln_stats) {
+            const float2 ms = ln_row_stats(a, row);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = ms.y * (x[j] - ms.x * a.ln_colsum[n + j]);
-    }
-    if (a.bias) {
+            for (int j = 0; j < 8; ++j) x[j] = ms.y * (x[j] - ms.x * a.ln_colsum[n + j]);
+        }
+        if (a.bias) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] += a.bias[n + j];
-    }
-    if (a.rowbias) {
-        const __half* rb = a.rowbias + (row / a.rows_per_group) * a.ld_rowbias + n;
+            for (int j = 0; j < 8; ++j) x[j] += a.bias[n + j];
+        }
+        if (a.rowbias) {
+            const __half* rb = a.rowbias + (row / a.rows_per_group) * a.ld_rowbias + n;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] += __half2float(rb[j]);
-    }
-    if (a.act == VMV_ACT_SILU) {
+            for (int j = 0; j < 8; ++j) x[j] += __half2float(rb[j]);
+        }
+        if (a.act == VMV_ACT_SILU) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
-    }
-    if (a.residual) {
-        const __half* rp = a.residual + row * a.ldr + n;
+            for (int j = 0; j < 8; ++j) x[j] = silu_f(x[j]);
+        }
+        if (a.residual) {
+            const __half* rp = a.residual + row * a.ldr + n;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) x[j] += __half2float(rp[j]);
+            for (int j = 0; j < 8; ++j) x[j] += __half2float(rp[j]);
+        }
+        uint4 o = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
+                             pack_half2(x[6], x[7]));
+        __half* drow = a.sc_world ? scatter_row(a, row) : a.D + row * a.ldd;
+        *reinterpret_cast<uint4*>(drow + n) = o;
     }
-    uint4 o = make_uint4(pack_half2(x[0], x[1]), pack_half2(x[2], x[3]), pack_half2(x[4], x[5]),
-                         pack_half2(x[6], x[7]));
-    *reinterpret_cast<uint4*>(a.D + row * a.ldd + n) = o;
+    if (a.sc_world) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(a.sc_done, 1u);
+            if (prev == gridDim.x - 1) {
+                __threadfence();
+                *a.sc_done = 0;
+                const unsigned int e = *a.sc_epoch + 1;
+                *a.sc_epoch = e;
+                peer_publish(a.sc_flags, a.sc_world, a.sc_rank, e);
+                if (!a.sc_nowait) peer_wait_all(a.sc_flags, a.sc_world, a.sc_rank, e);
+            }
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1378,8 +1396,8 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                              ? 1 : 0;
         }
         a.rowstats_nslots = 2 * pl.n_tiles;
-        if (a.sc_world && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
-            set_error("vmv_gemm: scatter needs the CTA-pair kernel's register epilogue (no split-K, no GEGLU, N %% 32 == 0, 32 B aligned rows)");
+        if (a.sc_world && pl.splits <= 1 && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
+            set_error("vmv_gemm: scatter needs the CTA-pair kernel's register epilogue (no GEGLU, N %% 32 == 0, 32 B aligned rows) or split-K");
             return VMV_ERR_UNSUPPORTED;
         }
         if (a.rowstats && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
@@ -1387,9 +1405,11 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                       "32 B aligned rows)");
             return VMV_ERR_UNSUPPORTED;
         }
-        if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
-        else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, a, m_pairs, pl.n_tiles, pl.splits, st);
+        GemmArgs ak = a;
+        if (pl.splits > 1) ak.sc_world = 0;             // split-K: the finish kernel scatters (and runs the rendezvous), not this one
+        if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
+        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
+        else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
     } else {
         if (a.rowstats || a.sc_world) {
             set_error("vmv_gemm: rowstats_out / scatter are not available in the one-tile-per-CTA kernel (variant 1)");

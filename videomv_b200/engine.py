@@ -202,25 +202,6 @@ class UNetEngine:
         nkb = w.w.shape[1] // 64
         pairs = SM_COUNT // 2
         split = 0
-        # to_layout = (direction, S): this GEMM's output feeds a layout exchange of the frame-sharded multi-GPU mode
-        # (0: frames -> pixels before a temporal segment, 1: pixels -> frames after it).  With peer memory the exchange
-        # happens INSIDE the epilogue (rows stored straight into the peers' tensors + flag rendezvous at the kernel's end).
-        to_layout = kw.pop("to_layout", None)
-        fs = self._fs if to_layout is not None else None
-        if fs is not None:
-            direction, S_ = to_layout
-            B_, Fl_, HW_ = S_["B"], S_["F"], S_["H"] * S_["W"]
-            if (fs.mode == "peer" and fs.fused_exchange and kw.get("act", 0) != ops.ACT_GEGLU and N % 32 == 0
-                    and not kw.get("want_stats", False)):
-                sc, dst = parallel.make_scatter(M, N, B_, Fl_, HW_, fs, direction)
-                ln = kw.pop("ln", None)
-                if ln is not None:
-                    kw.update(ln_stats=ln[0], ln_src=ln[1], ln_colsum=w.colsum)
-                return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, out=dst, scatter=sc, **kw)
-            out = self._gemm(a, w, **kw)
-            if direction == 0:
-                return parallel.frames_to_pixels(out, B_, Fl_, HW_, fs)
-            return parallel.pixels_to_frames(out, B_, Fl_, HW_, fs)
         if kw.get("act", 0) != ops.ACT_GEGLU and nkb >= 32 and tiles < 4 * pairs and mode != ops.UPCONV3X3:
             # time(s) ~ T_full / utilisation(s) + cost of the fp32 partials (write + read back + extra launch)
             t_full = 2.0 * M * N * nkb * 64 / 0.9e15
@@ -239,6 +220,26 @@ class UNetEngine:
                         self._ws_retired.append(self._ws)          # never freed while a graph may replay into it
                     self._ws = torch.empty(need, dtype=torch.uint8, device=self.device)
                 kw["workspace"] = self._ws
+        # to_layout = (direction, S): this GEMM's output feeds a layout exchange of the frame-sharded multi-GPU mode
+        # (0: frames -> pixels before a temporal segment, 1: pixels -> frames after it).  With peer memory the exchange
+        # happens INSIDE the kernel that produces the rows (the GEMM's register epilogue, or the split-K finish kernel):
+        # they are stored straight into the peers' tensors and the kernel ends with the flag rendezvous.
+        to_layout = kw.pop("to_layout", None)
+        fs = self._fs if to_layout is not None else None
+        if fs is not None:
+            direction, S_ = to_layout
+            B_, Fl_, HW_ = S_["B"], S_["F"], S_["H"] * S_["W"]
+            if (fs.mode == "peer" and fs.fused_exchange and kw.get("act", 0) != ops.ACT_GEGLU and N % 32 == 0
+                    and not kw.get("want_stats", False)):
+                sc, dst = parallel.make_scatter(M, N, B_, Fl_, HW_, fs, direction)
+                ln = kw.pop("ln", None)
+                if ln is not None:
+                    kw.update(ln_stats=ln[0], ln_src=ln[1], ln_colsum=w.colsum)
+                return ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=split, w_static=True, out=dst, scatter=sc, **kw)
+            out = self._gemm(a, w, **kw)
+            if direction == 0:
+                return parallel.frames_to_pixels(out, B_, Fl_, HW_, fs)
+            return parallel.pixels_to_frames(out, B_, Fl_, HW_, fs)
         # w_static: every W here is a packed model weight, so the kernel may prefetch W tiles ahead of its PDL wait
         ln = kw.pop("ln", None)                    # (stats tensor, src): statistics of the rows of `a` for the folded LayerNorm
         if ln is not None:
