@@ -232,6 +232,9 @@ int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, int32_t W, i
  * unet_t2v.py:368 when the head conv runs on the tensor cores (vmv_gemm CONV3X3 with Cout zero-padded to 16 columns) */
 int vmv_rows_to_ncfhw(const void* x, int64_t ldx, int32_t B, int32_t F, int32_t H, int32_t W, int32_t Cout, float* out,
                       void* stream);
+/* out[m, :] = softmax(scale * x[m, :]) over fp16 rows (fp32 maths), scale > 0: the softmax of the single-head, d = C
+ * attention of the VAE decoder's middle block (autoencoder.py:419-441), whose QK^T and PV are plain vmv_gemm calls. */
+int vmv_softmax_rows(const void* x, int64_t ldx, int64_t M, int32_t N, float scale, void* out, int64_t ldo, void* stream);
 /* sinusoidal_embedding util.py:177-189: t int64 [B] -> out fp16 [B, dim] = [cos | sin] */
 int vmv_sinusoidal_embedding(const int64_t* t, int32_t B, int32_t dim, void* out, void* stream);
 /* e[b*F+f, :] = silu( t_emb[b,:] (+ t_emb2[b,:]) (+ cam_emb[b*F+f,:]) )   (unet_t2v.py:326-335 + the nn.SiLU

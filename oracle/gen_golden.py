@@ -118,8 +118,36 @@ def make_ddim_case():
                         eps=out["eps"], v=out["v"])
 
 
+def make_vae_case(name, n, hw, seed_w, seed_z):
+    """Pin oracle/vae_oracle.py against the reference AutoencoderKL.decode (imported unmodified) and store the fixture."""
+    from oracle import vae_oracle
+    VAE = ref_import.load_reference_vae()
+    torch.manual_seed(0)
+    model = VAE(**ref_import.VAE_KWARGS).eval()
+    shapes = {k: list(v.shape) for k, v in model.state_dict().items()}
+    sd = synth.synth_state_dict(shapes, seed=seed_w)
+    model.load_state_dict(sd, strict=True)
+    z = torch.randn(n, 4, hw, hw, generator=torch.Generator().manual_seed(seed_z)) * 5.0     # latents / scale_factor: std ~ 5
+    t0 = time.time()
+    with torch.no_grad():
+        ref = model.decode(z)
+    t_ref = time.time() - t0
+    out = vae_oracle.vae_decode(sd, z)
+    err = (out - ref).abs().max().item()
+    print(f"[{name}] ref {t_ref:.1f}s  max|oracle-ref|={err:.3e}  max|ref|={ref.abs().max().item():.3f} std={ref.std().item():.3f}", flush=True)
+    assert err <= 2e-5 * max(1.0, ref.abs().max().item()), f"oracle does not match the reference on {name}"
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), z=z.numpy(), ref=ref.numpy().astype(np.float32),
+                        weight_checksum=np.float64(_weight_checksum(sd)))
+    with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
+        json.dump(dict(kind="vae", kwargs=ref_import.VAE_KWARGS, n=n, hw=hw, seed_w=seed_w, seed_z=seed_z,
+                       oracle_vs_ref_maxabs=err, shapes=shapes), f)
+
+
 def main():
     which = sys.argv[1:] or ["small", "full"]
+    if "vae" in which:
+        make_vae_case("vae_small", n=2, hw=8, seed_w=21, seed_z=22)          # 2 x 64 x 64 images
+        make_vae_case("vae_256", n=1, hw=32, seed_w=21, seed_z=23)           # one 256 x 256 frame (BASELINE config 2's frames)
     if "ddim" in which:
         make_ddim_case()
     if "small" in which:

@@ -102,6 +102,22 @@ def load_reference():
     return _CACHE["t2v"], _CACHE["i2v"]
 
 
+def load_reference_vae():
+    """The reference's AutoencoderKL class (tools/modules/autoencoder.py), unmodified."""
+    if "vae" in _CACHE:
+        return _CACHE["vae"]
+    load_reference()                      # stubs + sys.path for utils.registry_class
+    mod = _load("tools.modules.autoencoder", "tools/modules/autoencoder.py")
+    _CACHE["vae"] = mod.AutoencoderKL
+    return _CACHE["vae"]
+
+
+# cfg.auto_encoder of tools/modules/config.py:110-127 (the SD-1.x VAE every shipped config uses)
+VAE_KWARGS = dict(ddconfig=dict(double_z=True, z_channels=4, resolution=256, in_channels=3, out_ch=3, ch=128,
+                                ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[], dropout=0.0,
+                                video_kernel_size=[3, 1, 1]), embed_dim=4)
+
+
 def load_reference_ddim():
     """The reference's DiffusionDDIM class (tools/modules/diffusions/diffusion_ddim.py), unmodified."""
     if "ddim" in _CACHE:

@@ -2,7 +2,7 @@
 
 `/root/reference` exists only in the build container.  So that `bench.py --impl reference` (CPU) and the
 `reference_cuda` leg of the native bench line (the reference's eager-PyTorch CUDA path, the thing the north star's
-">= 1.8x" is measured against) run the GENUINE reference classes on the GPU box, this copies the eight files those
+">= 1.8x" is measured against) run the GENUINE reference classes on the GPU box, this copies the nine files those
 classes need, unmodified, into the git-ignored `oracle/_ref/reference/` (same relative paths).  That directory is
 listed in .gitignore (never part of the history) but not in .gpurunignore (it travels with the snapshot, like the
 built .so).  Nothing under videomv_b200/ imports it; oracle/ref_import.py falls back to it when /root/reference is
@@ -19,7 +19,7 @@ DST = os.path.join(HERE, "_ref", "reference")
 FILES = [
     "tools/modules/unet/util.py", "tools/modules/unet/unet_t2v.py", "tools/modules/unet/unet_i2vgen.py",
     "tools/modules/diffusions/diffusion_ddim.py", "tools/modules/diffusions/schedules.py",
-    "tools/modules/diffusions/losses.py", "utils/registry.py", "utils/registry_class.py",
+    "tools/modules/diffusions/losses.py", "tools/modules/autoencoder.py", "utils/registry.py", "utils/registry_class.py",
 ]
 
 

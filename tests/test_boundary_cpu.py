@@ -32,6 +32,18 @@ def test_state_dict_matches_reference(case):
     assert list(mine) == list(ref)      # same ordering too (checkpoint tools sometimes zip by position)
 
 
+def test_vae_state_dict_matches_reference():
+    """AutoencoderKL drop-in: same keys, shapes and order as tools/modules/autoencoder.py:32."""
+    from videomv_b200 import vae
+    meta = _meta("vae_small")
+    with torch.device("meta"):
+        model = vae.AutoencoderKL(**meta["kwargs"])
+    mine = {k: list(v.shape) for k, v in model.state_dict().items()}
+    assert mine == meta["shapes"] and list(mine) == list(meta["shapes"])
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        vae.AutoencoderKL(**meta["kwargs"]).decode(torch.zeros(1, 4, 8, 8))
+
+
 def test_ctor_swallows_unknown_kwargs_and_yaml_types():
     from videomv_b200 import unet
     kw = dict(_meta("t2v_small")["kwargs"], some_future_flag=3, use_lgm_refine=True)
@@ -56,6 +68,8 @@ def test_library_exports_every_declared_symbol():
     assert ctypes.sizeof(_lib.PeerExchangeParams) == _lib.lib().vmv_sizeof_peer_exchange_params()
     assert ctypes.sizeof(_lib.PeerAllreduceParams) == _lib.lib().vmv_sizeof_peer_allreduce_params()
     assert ctypes.sizeof(_lib.GnPeer) == _lib.lib().vmv_sizeof_gn_peer()
+    assert ctypes.sizeof(_lib.GemmScatter) == _lib.lib().vmv_sizeof_gemm_scatter()
+    assert ctypes.sizeof(_lib.PeerAllgatherParams) == _lib.lib().vmv_sizeof_peer_allgather_params()
 
 
 def test_cpu_call_fails_loudly():

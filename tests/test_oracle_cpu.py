@@ -37,6 +37,19 @@ def test_oracle_matches_reference_golden(case):
     assert err <= 2e-5 * max(1.0, d["ref"].abs().max().item()), err
 
 
+@pytest.mark.parametrize("case", ["vae_small", "vae_256"])
+def test_vae_oracle_matches_reference_golden(case):
+    from oracle import vae_oracle
+    meta, d, checksum = load_case(case)
+    sd = synth.synth_state_dict(meta["shapes"], seed=meta["seed_w"])
+    got = sum(float(sd[k].double().abs().sum()) for k in sorted(sd))
+    assert abs(got - checksum) <= 1e-9 * checksum
+    out = vae_oracle.vae_decode(sd, d["z"])
+    assert out.shape == d["ref"].shape
+    err = (out - d["ref"]).abs().max().item()
+    assert err <= 2e-5 * max(1.0, d["ref"].abs().max().item()), err
+
+
 def test_oracle_is_input_dependent():
     meta, d, _ = load_case("t2v_small")
     sd = synth.synth_state_dict(meta["shapes"], seed=meta["seed_w"])

@@ -166,6 +166,7 @@ SYMBOLS = {
     "vmv_im2col_3x3_s2": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "vmv_conv3x3_in": (ctypes.c_int, [c_vp, c_i32, c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
     "vmv_conv3x3_out": (ctypes.c_int, [c_vp, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp, c_i32, c_vp, c_vp]),
+    "vmv_softmax_rows": (ctypes.c_int, [c_vp, c_i64, c_i64, c_i32, c_f32, c_vp, c_i64, c_vp]),
     "vmv_rows_to_ncfhw": (ctypes.c_int, [c_vp, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_vp, c_vp]),
     "vmv_sinusoidal_embedding": (ctypes.c_int, [c_vp, c_i32, c_i32, c_vp, c_vp]),
     "vmv_embed_combine_silu": (ctypes.c_int, [c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_vp, c_vp]),

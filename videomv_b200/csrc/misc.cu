@@ -265,6 +265,55 @@ __global__ void cfg_ddim_kernel(const float* __restrict__ xt, const float* __res
     xprev[i] = sa_prev * x0 + s1a_prev * eps;                      // :240-243 (eta = 0)
 }
 
+
+// softmax over the last dimension of fp16 rows (fp32 maths): out[m, :] = softmax(scale * x[m, :]).  One warp per row, three
+// passes over the row (max, sum of exponentials, normalised write) with 16 B accesses; the row stays in L1/L2 between them.
+// Used by the single-head d=512 attention of the VAE decoder's middle block (autoencoder.py:419-441).
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const __half* __restrict__ x, long long ldx, long long M, int N, float scale, __half* __restrict__ out, long long ldo) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= M) return;
+    const uint4* xp = reinterpret_cast<const uint4*>(x + row * ldx);
+    const int nvec = N / 8;
+    const float sl2 = scale * 1.4426950408889634f;
+    float mx = -INFINITY;
+    for (int v = lane; v < nvec; v += 32) {
+        const uint4 u = xp[v];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_half2(w[j]); mx = fmaxf(mx, fmaxf(f.x, f.y)); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // scale > 0: max of scale*x = scale*max
+    const float off = mx * sl2;
+    float sum = 0.f;
+    for (int v = lane; v < nvec; v += 32) {
+        const uint4 u = xp[v];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { const float2 f = unpack_half2(w[j]); sum += exp2f(fmaf(f.x, sl2, -off)) + exp2f(fmaf(f.y, sl2, -off)); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    uint4* op = reinterpret_cast<uint4*>(out + row * ldo);
+    for (int v = lane; v < nvec; v += 32) {
+        const uint4 u = xp[v];
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float2 f = unpack_half2(w[j]);
+            o[j] = pack_half2(exp2f(fmaf(f.x, sl2, -off)) * inv, exp2f(fmaf(f.y, sl2, -off)) * inv);
+        }
+        op[v] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
 }  // namespace vmv
 
 using namespace vmv;
@@ -337,6 +386,17 @@ extern "C" int vmv_conv3x3_out(const void* x, int32_t B, int32_t F, int32_t H, i
         static_cast<const __half*>(x), B, F, H, W, C, w, bias, out);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_conv3x3_out");
+    return VMV_OK;
+}
+
+extern "C" int vmv_softmax_rows(const void* x, int64_t ldx, int64_t M, int32_t N, float scale, void* out, int64_t ldo, void* stream) {
+    VMV_CHECK_ARG(x && out && M > 0 && N > 0 && N % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= N && ldo >= N && scale > 0.f,
+                  "vmv_softmax_rows: bad args (N, ldx, ldo multiples of 8; scale > 0)");
+    VMV_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0, "vmv_softmax_rows: x/out must be 16 B aligned");
+    launch_kernel(softmax_rows_kernel, dim3((unsigned)((M + 7) / 8)), dim3(256), 0, static_cast<cudaStream_t>(stream),
+                  static_cast<const __half*>(x), ldx, M, N, scale, static_cast<__half*>(out), ldo);
+    count_launch();
+    VMV_CUDA_LAUNCH_CHECK("vmv_softmax_rows");
     return VMV_OK;
 }
 

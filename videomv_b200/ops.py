@@ -373,6 +373,16 @@ def conv3x3_out(x: torch.Tensor, w: torch.Tensor, bias: torch.Tensor, B: int, F:
     return out
 
 
+def softmax_rows(x: torch.Tensor, scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """softmax(scale * x) over the last dim of fp16 rows."""
+    _rows(x, "softmax_rows x")
+    if out is None:
+        out = torch.empty_like(x)
+    check(_lib.lib().vmv_softmax_rows(x.data_ptr(), x.stride(0), x.shape[0], x.shape[1], float(scale), out.data_ptr(),
+                                      out.stride(0), _stream()), "vmv_softmax_rows")
+    return out
+
+
 def rows_to_ncfhw(x: torch.Tensor, B: int, F: int, H: int, W: int, cout: int) -> torch.Tensor:
     """fp16 rows [B*F*H*W, >=cout] -> fp32 [B,cout,F,H,W]."""
     _rows(x, "rows_to_ncfhw x")
