@@ -43,6 +43,12 @@ struct GemmArgs {
     // UPCONV3X3:  the tile geometry is that of the INPUT grid; m tiles come in 4 phases (py, px) of `mt_phase` tiles each,
     //             output pixel (2y+py, 2x+px); 4 taps (ty, tx) at input offset (ty - 1 + py, tx - 1 + px); W rows phase*N + n.
     int mt_phase;                  // m tiles per phase (== all m tiles when the mode has no phases)
+    // A-resident schedule (small K: all K blocks of an m tile fit the ring).  The ring depth is set to the number of K
+    // blocks, so stage s always holds K block s of the CURRENT m tile; every cluster works through a contiguous run of
+    // tiles (all N tiles of an m pair back to back) and re-loads only W for the 2nd, 3rd, ... N tile of an m pair: the A
+    // rows cross the L2 -> SM path once instead of once per N tile (the K <= 512 transformer GEMMs at the 32x32 level are
+    // bound by exactly that path).
+    int a_res;
     // epilogue
     __half* D;
     long long ldd;
@@ -533,6 +539,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
     const int tiles_mn = m_pairs * n_tiles;
     const int total_tiles = tiles_mn * splits;
     const int mp_phase = (a.mt_phase + 1) / 2;          // CTA pairs per output phase (all of them when the mode has one phase)
+    // tile schedule: round-robin over clusters, or (A-resident) one contiguous run of tiles per cluster
+    const int depth = a.a_res ? a.nkb : STAGES;         // ring depth in use
+    const int run = a.a_res ? (total_tiles + num_clusters - 1) / num_clusters : 0;
+    const int t_begin = a.a_res ? min(total_tiles, cluster_id * run) : cluster_id;
+    const int t_end = a.a_res ? min(total_tiles, (cluster_id + 1) * run) : total_tiles;
+    const int t_step = a.a_res ? 1 : num_clusters;
 
     cluster_sync_all();                                 // both CTAs resident before the pair-wide TMEM allocation
     if (warp == 0 && lane == 0) {
@@ -566,15 +578,15 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             // ------------------------------ TMA producer (both CTAs) ------------------------------
             constexpr uint32_t tx_bytes = 2u * (A_STAGE_BYTES + L::B_STAGE_BYTES);
             int pre = 0;                                    // stages whose barrier arrival + W load were issued pre-wait
-            if (a.w_static && !(a.dbg & 4) && cluster_id < total_tiles) {
-                const int split = cluster_id / tiles_mn;
-                const int rem0 = cluster_id - split * tiles_mn;
+            if (a.w_static && !(a.dbg & 4) && t_begin < t_end) {
+                const int split = t_begin / tiles_mn;
+                const int rem0 = t_begin - split * tiles_mn;
                 const int nt = rem0 % n_tiles;
                 const int nt_cols = min(BN, a.N - nt * BN);
                 const int nrow = ((rem0 / n_tiles) / mp_phase) * a.N + nt * BN + (int)rank * (nt_cols / 2);
                 const int kb_begin = split * a.kb_per_split;
                 const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
-                pre = min(STAGES, kb_end - kb_begin);
+                pre = min(depth, kb_end - kb_begin);
                 for (int i = 0; i < pre; ++i) {
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[i], tx_bytes);
                     else mbar_arrive_remote(&full_bar[i], 0);
@@ -583,10 +595,12 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             }
             pdl_wait();
             int it = 0;
-            for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+            for (int t = t_begin; t < t_end; t += t_step) {
                 const int split = t / tiles_mn;
                 const int rem = t - split * tiles_mn;
                 const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
+                // A-resident: the A rows of this m pair are already in the ring unless this is the first tile of my run or of the m pair
+                const bool load_a = !a.a_res || t == t_begin || nt == 0;
                 const int phase = mp / mp_phase;                // UPCONV3X3 only (0 otherwise)
                 const int mt = 2 * (mp - phase * mp_phase) + (int)rank;
                 // the pair splits the tile's W rows; a ragged last tile (N % BN != 0) is nt_cols wide and each CTA
@@ -610,8 +624,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 const int kb_begin = split * a.kb_per_split;
                 const int kb_end = min(a.nkb, kb_begin + a.kb_per_split);
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % depth;
+                    const uint32_t ph = (it / depth) & 1;
                     const bool prefetched = it < pre;      // first ring pass: arrival + W tile already issued
                     if (!prefetched) mbar_wait(&empty_bar[s], ph ^ 1);
                     if (a.dbg & 4) {                       // experiment: no operand traffic, barrier protocol only
@@ -620,12 +634,14 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         continue;
                     }
                     if (!prefetched) {
-                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], tx_bytes);
+                        if (rank == 0) mbar_arrive_expect_tx(&full_bar[s], load_a ? tx_bytes : 2u * L::B_STAGE_BYTES);
                         else mbar_arrive_remote(&full_bar[s], 0);
                     }
                     void* sa = smem + L::A_OFF + s * A_STAGE_BYTES;
                     void* sb = smem + L::B_OFF + s * L::B_STAGE_BYTES;
-                    if (a.mode == VMV_GEMM_LINEAR) {
+                    if (!load_a) {
+                        // stage s still holds K block kb of this m pair's A rows
+                    } else if (a.mode == VMV_GEMM_LINEAR) {
                         if (kb < a.nkb1) tma_load_2d_2sm(sa, &tmA1, &full_bar[s], kb * BK, c1);
                         else tma_load_2d_2sm(sa, &tmA2, &full_bar[s], (kb - a.nkb1) * BK, c1);
                     } else if (a.mode == VMV_GEMM_CONV3X3 || a.mode == VMV_GEMM_CONV3X3_S2) {
@@ -649,7 +665,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         if (lane == 0 && rank == 0) {
             // ------------------------------ MMA issuer (leader CTA only) ------------------------------
             int it = 0, acc_it = 0;
-            for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
+            for (int t = t_begin; t < t_end; t += t_step, ++acc_it) {
                 const int split = t / tiles_mn;
                 const int nt_mma = (t - split * tiles_mn) % n_tiles;
                 const uint32_t idesc = umma_idesc_f16_f32(2 * BM, min(BN, a.N - nt_mma * BN));   // ragged last N tile
@@ -661,8 +677,8 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 tc_fence_after();
                 const uint32_t dcol = tmem_base + buf * BN;
                 for (int kb = kb_begin; kb < kb_end; ++kb, ++it) {
-                    const int s = it % STAGES;
-                    const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % depth;
+                    const uint32_t ph = (it / depth) & 1;
                     mbar_wait(&full_bar[s], ph);
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
@@ -701,7 +717,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int per = geglu ? 64 : 32;
         float nb[4] = {0.f, 0.f, 0.f, 0.f}, nc[4] = {0.f, 0.f, 0.f, 0.f};
         auto fetch_cols = [&](int tt) {
-            if (tt >= total_tiles) return;
+            if (tt >= t_end) return;
             const int rem_ = tt % tiles_mn;
             const int nt_ = rem_ % n_tiles;
             const int col0_ = nt_ * out_bn;
@@ -720,9 +736,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 }
             }
         };
-        if (a.fast_epi) fetch_cols(cluster_id);
+        if (a.fast_epi) fetch_cols(t_begin);
         int acc_it = 0;
-        for (int t = cluster_id; t < total_tiles; t += num_clusters, ++acc_it) {
+        for (int t = t_begin; t < t_end; t += t_step, ++acc_it) {
             const int split = t / tiles_mn;
             const int rem = t - split * tiles_mn;
             const int mp = rem / n_tiles, nt = rem - mp * n_tiles;
@@ -753,7 +769,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         if (i < cnt) { sbias[i] = nb[qq]; scol[i] = nc[qq]; }
                     }
                 }
-                fetch_cols(t + num_clusters);                   // next tile's values: a whole tile of latency hiding
+                fetch_cols(t + t_step);                         // next tile's values: a whole tile of latency hiding
                 // (2) request the residual of my first block and my row's LayerNorm statistics
                 if (resrow && hh < nvalid) {
                     ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
@@ -1407,6 +1423,17 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
         }
         GemmArgs ak = a;
         if (pl.splits > 1) ak.sc_world = 0;             // split-K: the finish kernel scatters (and runs the rendezvous), not this one
+        {
+            // A-resident schedule: small K (every K block of an m tile fits the ring), several N tiles per m tile, and enough
+            // tiles that contiguous runs per cluster balance as well as round-robin does.  OFF by default (VMV_GEMM_ARES=1):
+            // measured neutral on B200 (19.70 vs 19.77 frames/s, profiles/r2_ab_ares.txt) -- the K <= 512 GEMMs are bound by
+            // the latency of the 8-warp epilogue (ncu: 26 % issue slots busy, 2.5 warps per scheduler), not by operand traffic.
+            static int ares = -1;
+            if (ares < 0) { const char* e = getenv("VMV_GEMM_ARES"); ares = (e && e[0] == '1') ? 1 : 0; }
+            const int ring = BN == 256 ? 6 : 8;
+            const long long total = (long long)m_pairs * pl.n_tiles;
+            if (ares && p->mode == VMV_GEMM_LINEAR && pl.splits <= 1 && a.nkb <= ring && pl.n_tiles >= 2 && total >= 2 * 74) ak.a_res = 1;
+        }
         if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
         else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
         else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
