@@ -98,11 +98,11 @@ typedef struct vmv_gemm_params {
      * with ln_stats[m] = {mean, rstd} (vmv_layernorm_stats) and ln_colsum[n] = sum_k W'[n,k].  NULL = off. */
     const void* ln_stats; const float* ln_colsum;
     /* ln_stats_src_n != 0: ln_stats is the `rowstats_out` of the upstream vmv_gemm that produced A (N = ln_stats_src_n,
-     * block_n = ln_stats_src_bn = vmv_gemm_block_n of that call): per row 2*ceil(N/block_n) partial {mean_k, M2_k} slots,
+     * block_n = ln_stats_src_bn = vmv_gemm_block_n of that call): per row vmv_gemm_epilogue_split()*ceil(N/block_n) partial {mean_k, M2_k} slots,
      * merged by the epilogue in slot order (parallel-variance merge) and finished with ln_eps.  0 = ln_stats is {mean, rstd}. */
     int32_t ln_stats_src_n; int32_t ln_stats_src_bn; float ln_eps;
-    /* rowstats_out != NULL: fp32 [M][2*ceil(N/block_n)][2]; the epilogue writes, per row and per (N tile, epilogue warp
-     * half), the partial LayerNorm statistics {mean_k, M2_k = sum (d - mean_k)^2} of the final (pre-rounding) output
+    /* rowstats_out != NULL: fp32 [M][vmv_gemm_epilogue_split()*ceil(N/block_n)][2]; the epilogue writes, per row and per (N tile,
+     * epilogue warp of the row's TMEM lane quarter), the partial LayerNorm statistics {mean_k, M2_k = sum (d - mean_k)^2} of the final (pre-rounding) output
      * values it holds -- the LayerNorm statistics of the tensor this GEMM produces, for the next GEMM's folded LayerNorm.
      * One writer per slot (no atomics, no initialisation needed, bit-reproducible).  CTA-pair kernel without split-K /
      * GEGLU only (else VMV_ERR_UNSUPPORTED). */
@@ -122,6 +122,8 @@ typedef struct vmv_gemm_params {
 int vmv_gemm(const vmv_gemm_params* p, void* stream);
 /* the N-tile width vmv_gemm will use for p (sizes rowstats_out; becomes the consumer's ln_stats_src_bn) */
 int vmv_gemm_block_n(const vmv_gemm_params* p);
+/* epilogue warps per TMEM lane quarter of the CTA-pair kernel = statistic slots per (row, N tile) of rowstats_out */
+int vmv_gemm_epilogue_split(void);
 /* bytes of workspace vmv_gemm needs for p (0 when split_k <= 1) */
 int64_t vmv_gemm_workspace_bytes(const vmv_gemm_params* p);
 

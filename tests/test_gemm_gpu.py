@@ -273,13 +273,15 @@ def test_dependent_launch_chain():
 
 def _merge_slots(rs, N, bn):
     """Host restatement of the consumer's slot merge: rs [M, slots, 2] of {mean_k, M2_k} -> (mean, biased variance)."""
+    from videomv_b200 import _lib
+    S = int(_lib.lib().vmv_gemm_epilogue_split())
     M, nsl, _ = rs.shape
     n = torch.zeros(M, dtype=torch.float64, device=rs.device)
     mean, m2 = torch.zeros_like(n), torch.zeros_like(n)
     for s_ in range(nsl):
-        nt, hh = s_ // 2, s_ % 2
+        nt, hh = s_ // S, s_ % S
         nvalid = max(min(bn // 32, (N - nt * bn + 31) // 32), 0)
-        nk = 32 * ((nvalid - hh + 1) // 2)
+        nk = 32 * max((nvalid - hh + S - 1) // S, 0)
         if nk <= 0:
             continue
         mk, m2k = rs[:, s_, 0].double(), rs[:, s_, 1].double()

@@ -150,6 +150,7 @@ SYMBOLS = {
     "vmv_gemm": (ctypes.c_int, [ctypes.POINTER(GemmParams), c_vp]),
     "vmv_gemm_workspace_bytes": (c_i64, [ctypes.POINTER(GemmParams)]),
     "vmv_gemm_block_n": (ctypes.c_int, [ctypes.POINTER(GemmParams)]),
+    "vmv_gemm_epilogue_split": (ctypes.c_int, []),
     "vmv_groupnorm_scratch_bytes": (c_i64, [c_i32, c_i64, c_i32]),
     "vmv_groupnorm_stats": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_vp, c_vp, c_vp]),
     "vmv_groupnorm_apply": (ctypes.c_int, [c_vp, c_i64, c_i32, c_vp, c_i64, c_i32, c_i64, c_i32, c_vp, c_i64, c_vp, c_vp,

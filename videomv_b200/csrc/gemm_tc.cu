@@ -24,6 +24,10 @@ namespace vmv {
 
 void count_launch(int n = 1);
 
+#ifndef VMV_EPI_SPLIT
+#define VMV_EPI_SPLIT 2
+#endif
+constexpr int EPI_SPLIT = VMV_EPI_SPLIT;         // epilogue warps per TMEM lane quarter: they share a quarter's rows and interleave the tile's 32-column blocks
 constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int A_STAGE_BYTES = BM * BK * 2;   // 16 KiB
@@ -104,14 +108,14 @@ __device__ __forceinline__ __half* scatter_row(const GemmArgs& a, long long grow
     return a.sc_dst[q] + row * a.ldd;
 }
 
-constexpr int LN_MAX_SLOTS = 10;      // 2 x ceil(1280 / 256)
+constexpr int LN_MAX_SLOTS = 16;      // EPI_SPLIT x ceil(1280 / 256) for EPI_SPLIT <= 3
 
 // number of columns slot s of a row covers, from the producing GEMM's tiling
 __device__ __forceinline__ int ln_slot_count(const GemmArgs& a, int s) {
-    const int nt = s >> 1, hh = s & 1;
+    const int nt = s / EPI_SPLIT, hh = s - nt * EPI_SPLIT;
     int nvalid = min(a.ln_src_bn / 32, (a.ln_src_n - nt * a.ln_src_bn + 31) / 32);
     nvalid = max(nvalid, 0);
-    return 32 * ((nvalid - hh + 1) / 2);
+    return 32 * max((nvalid - hh + EPI_SPLIT - 1) / EPI_SPLIT, 0);
 }
 
 // Folded-LayerNorm row statistics {mean, rstd}: stored as such, or merged from the slots an upstream GEMM wrote -- in slot
@@ -493,8 +497,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__
 constexpr int EPI_BLK_COLS = 32;                 // epilogue column block: 32 fp16 = 64 B rows, SWIZZLE_64B boxes
 constexpr int EPI_BLK_BYTES = 32 * 64;            // 32 rows x 64 B per warp per block
 
-constexpr int V2_THREADS = 320;                  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
-constexpr int V2_EPI_WARPS = 8;
+constexpr int V2_EPI_WARPS = 4 * EPI_SPLIT;
+constexpr int V2_THREADS = 64 + 32 * V2_EPI_WARPS;   // warp 0 TMA, warp 1 MMA, then the epilogue warps
 
 template <int BN, int STAGES, int NBLK_>
 struct SmemLayout2 {
@@ -703,7 +707,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         // Global-latency loads are taken off the accumulator critical path: bias / LayerNorm column sums are staged in
         // smem before the tile's MMAs finish, and the residual of block i+1 is requested before block i is processed.
         const int q = warp & 3;
-        const int hh = (warp - 2) >> 2;                         // 0: even blocks, 1: odd blocks
+        const int hh = (warp - 2) >> 2;                         // which of the quarter's EPI_SPLIT warps: blocks hh, hh + EPI_SPLIT, ...
         const int r = q * 32 + lane;
         float* sbias = s_epi_scr[warp - 2];
         float* scol = sbias + 128;
@@ -723,13 +727,13 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int col0_ = nt_ * out_bn;
             int nvalid_ = min(out_bn / EPI_BLK_COLS, (a.n_out - col0_ + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
             if (nvalid_ < 0) nvalid_ = 0;
-            const int cnt = ((nvalid_ - hh + 1) / 2) * per;
+            const int cnt = max((nvalid_ - hh + EPI_SPLIT - 1) / EPI_SPLIT, 0) * per;
 #pragma unroll
             for (int qq = 0; qq < 4; ++qq) {
                 const int i = lane + 32 * qq;
                 if (i < cnt) {
                     const int j = i / per, w = i - j * per;
-                    const int blk = hh + 2 * j;
+                    const int blk = hh + EPI_SPLIT * j;
                     const int n = geglu ? nt_ * BN + blk * 32 + (w & 31) + (w >= 32 ? BN / 2 : 0) : col0_ + blk * 32 + w;
                     nb[qq] = a.bias ? __ldg(a.bias + n) : 0.f;
                     nc[qq] = a.ln_colsum ? __ldg(a.ln_colsum + n) : 0.f;
@@ -762,7 +766,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 //     column (hh+2j)*32+i of the tile; GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
                 __syncwarp();                                   // previous tile's readers are done with the scratch
                 {
-                    const int cnt = ((nvalid - hh + 1) / 2) * per;
+                    const int cnt = max((nvalid - hh + EPI_SPLIT - 1) / EPI_SPLIT, 0) * per;
 #pragma unroll
                     for (int qq = 0; qq < 4; ++qq) {
                         const int i = lane + 32 * qq;
@@ -806,7 +810,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 float row_s = 0.f, row_q = 0.f, row_sh = 0.f;
                 int row_cnt = 0;
 #pragma unroll 1
-                for (int blk = hh; blk < nvalid; blk += 2, ++j) {
+                for (int blk = hh; blk < nvalid; blk += EPI_SPLIT, ++j) {
                     const int c = blk * EPI_BLK_COLS;           // column inside the tile's output range
                     float x[32];
                     if (geglu) {
@@ -875,10 +879,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
 #pragma unroll
                             for (int i = 0; i < 32; ++i) x[i] = __uint_as_float(v[i]);
                         }
-                        requested = ld_ahead && blk + 2 < nvalid;
+                        requested = ld_ahead && blk + EPI_SPLIT < nvalid;
                         if (requested) {
-                            tmem_ld_32x32b_x16(trow + c + 2 * EPI_BLK_COLS, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
-                            tmem_ld_32x32b_x16(trow + c + 2 * EPI_BLK_COLS + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
+                            tmem_ld_32x32b_x16(trow + c + EPI_SPLIT * EPI_BLK_COLS, *reinterpret_cast<uint32_t(*)[16]>(&v[0]));
+                            tmem_ld_32x32b_x16(trow + c + EPI_SPLIT * EPI_BLK_COLS + 16, *reinterpret_cast<uint32_t(*)[16]>(&v[16]));
                         }
                         if (rb) {
 #pragma unroll
@@ -900,9 +904,9 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             x[2 * i] += f.x;
                             x[2 * i + 1] += f.y;
                         }
-                        if (blk + 2 < nvalid) {                 // request the next block's residual now
-                            ldg256(resrow + (blk + 2) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
-                            ldg256(resrow + (blk + 2) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
+                        if (blk + EPI_SPLIT < nvalid) {         // request the next block's residual now
+                            ldg256(resrow + (blk + EPI_SPLIT) * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
+                            ldg256(resrow + (blk + EPI_SPLIT) * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                         }
                     }
                     if (a.rowstats) {
@@ -931,7 +935,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                         st.x = fmaf(row_s, inv, row_sh);
                         st.y = fmaxf(fmaf(-row_s * inv, row_s, row_q), 0.f);
                     }
-                    a.rowstats[grow * a.rowstats_nslots + 2 * nt + hh] = st;
+                    a.rowstats[grow * a.rowstats_nslots + EPI_SPLIT * nt + hh] = st;
                 }
             }
             tc_fence_before();
@@ -1207,7 +1211,7 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
                       "vmv_gemm: ln_stats_src_n / ln_stats_src_bn must describe the producing GEMM's tiling");
         a.ln_src_n = p->ln_stats_src_n;
         a.ln_src_bn = p->ln_stats_src_bn;
-        a.ln_nslots = 2 * ((a.ln_src_n + a.ln_src_bn - 1) / a.ln_src_bn);
+        a.ln_nslots = EPI_SPLIT * ((a.ln_src_n + a.ln_src_bn - 1) / a.ln_src_bn);
         VMV_CHECK_ARG(a.ln_nslots <= LN_MAX_SLOTS, "vmv_gemm: %d LayerNorm statistic slots (max %d)", a.ln_nslots, LN_MAX_SLOTS);
     }
     a.rowstats = static_cast<float2*>(p->rowstats_out);
@@ -1323,6 +1327,8 @@ static int make_plan(const vmv_gemm_params* p, Plan* pl) {
 
 using namespace vmv;
 
+extern "C" int vmv_gemm_epilogue_split(void) { return EPI_SPLIT; }
+
 extern "C" int vmv_gemm_block_n(const vmv_gemm_params* p) {
     if (!p) return -1;
     return pick_block_n(p, p->variant ? p->variant : default_variant());
@@ -1411,7 +1417,7 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
                                  al32(p->rowbias, p->ld_rowbias)
                              ? 1 : 0;
         }
-        a.rowstats_nslots = 2 * pl.n_tiles;
+        a.rowstats_nslots = EPI_SPLIT * pl.n_tiles;
         if (a.sc_world && pl.splits <= 1 && !(a.fast_epi && p->act != VMV_ACT_GEGLU)) {
             set_error("vmv_gemm: scatter needs the CTA-pair kernel's register epilogue (no GEGLU, N %% 32 == 0, 32 B aligned rows) or split-K");
             return VMV_ERR_UNSUPPORTED;

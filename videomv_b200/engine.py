@@ -250,7 +250,7 @@ class UNetEngine:
         if self.fused_ln_stats and split == 0 and N % 32 == 0 and self._gn_arena is not None:
             src_bn = ops.gemm_block_n(N, kw.get("act", 0), w.bn)
             nsl = ops.rowstats_slots(N, src_bn)
-            if nsl <= 10:
+            if nsl <= 16:
                 rs = self._gn_arena.take_rowstats(M, nsl)
                 out = ops.gemm(a, w.w, bias=w.b, block_n=w.bn, split_k=0, w_static=True, rowstats_out=rs, **kw)
                 return out, (rs, (N, src_bn))
@@ -497,7 +497,7 @@ class UNetEngine:
                 # 166 GroupNorms per forward (per-CTA partial sums) + the LayerNorm partial-statistics slots (99 LayerNorms:
                 # 30 at each of the three transformer levels with 4 / 6 / 10 slots per row, 9 in the middle block
                 # = 187 x (level-0 rows) x 8 B; sized with margin).  Nothing here is ever memset.
-                arena = self._gn_arenas[(nb, H, W)] = ops.GnArena(x32.device, 192 * per_call + 224 * nb * H * W * 8,
+                arena = self._gn_arenas[(nb, H, W)] = ops.GnArena(x32.device, 192 * per_call + 336 * nb * H * W * 8,
                                                                   bar_bytes=192 * ((nb * 8 + 63) // 64 * 64))
             self._gn_arena = arena
             arena.reset()                              # rewind only: every call of this forward takes a fresh region

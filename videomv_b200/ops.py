@@ -142,8 +142,8 @@ def gemm_block_n(N: int, act: int = ACT_NONE, block_n: int = 0, variant: int = 0
 
 
 def rowstats_slots(N: int, bn: int) -> int:
-    """Partial-statistic slots per row written by a GEMM with N columns in tiles of bn: (N tile, epilogue warp half)."""
-    return 2 * ((N + bn - 1) // bn)
+    """Partial-statistic slots per row written by a GEMM with N columns in tiles of bn: (N tile, epilogue warp of the quarter)."""
+    return int(_lib.lib().vmv_gemm_epilogue_split()) * ((N + bn - 1) // bn)
 
 
 class GnArena:
