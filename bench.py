@@ -497,6 +497,33 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                                   "frac_of_peak": t_fwd_alg * DDIM_STEPS * args.steps / (ms / 1e3) / pk["tflops"]}
         # ---- cpu baseline leg (N=1 only): bounded oracle sample on the host cores
         if world == 1 and not args.no_cpu_baseline:
+            # ---- the same sample through the REFERENCE's own sampler class driving this module (its two-call CFG pattern,
+            # diffusion_ddim.py:149-155, its elementwise update): the path a user of inference.py gets with only the registry
+            # swap of INTEGRATION.md section 1 and no other change
+            try:
+                from oracle import ref_import
+                if ref_import.available():
+                    RefDDIM = ref_import.load_reference_ddim()
+                    rd = RefDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.0120,
+                                 zero_terminal_snr=False), mean_type=mean_type, var_type="fixed_small", loss_type="mse")
+                    model.enable_cuda_graphs(not args.no_graphs)
+
+                    def ref_loop():
+                        noise = host["noise"].to(dev, non_blocking=True)
+                        kwargs = to_kwargs(kind, host, dev)
+                        with torch.no_grad():
+                            return rd.ddim_sample_loop(noise, model, model_kwargs=kwargs, guide_scale=gs, ddim_timesteps=DDIM_STEPS, eta=0.0).to("cpu")
+                    ref_loop()
+                    torch.cuda.synchronize()
+                    t0 = time.time()
+                    ref_loop()
+                    dt = time.time() - t0
+                    line["e2e_reference_sampler"] = {"value": FRAMES / dt, "unit": "frames/s", "samples": 1,
+                                                     "how": "the reference's unmodified DiffusionDDIM.ddim_sample_loop calling this module twice per step "
+                                                            "(B=1 graphs), host inputs, wall clock"}
+                    model.enable_cuda_graphs(False)
+            except Exception as e:  # noqa: BLE001
+                line["e2e_reference_sampler"] = {"error": repr(e)}
             # ---- the reference's own CUDA path on this GPU (bounded sample), then the CPU baseline
             try:
                 rc = reference_cuda_leg(kind, hw, dev, model.state_dict())

@@ -209,9 +209,12 @@ typedef struct vmv_attn_params {
     int64_t o_bs_outer, o_bs_inner, o_rs;
     int32_t kv_group;          /* kv outer index = bo / kv_group */
     float scale;               /* head_dim^-0.5 */
-    int32_t impl;              /* 0 auto | 1 strided mma.sync kernel (any layout) | 2 tcgen05/TMEM kernel (contiguous
-                                  batches, nq >= 128; VMV_ERR_UNSUPPORTED otherwise).  Auto picks 2 whenever the
-                                  layout allows (spatial self-attention, text cross-attention), else 1. */
+    int32_t impl;              /* 0 auto | 1 strided mma.sync kernel (any layout) | 2 tcgen05/TMEM kernel: contiguous batches
+                                  of >= 128 rows; short contiguous sequences (power-of-two length, packed 128/n per tile,
+                                  block-diagonal mask); strided sequences of <= 128 rows (temporal attention: 128/F pixels
+                                  packed per tile by a 4-D TMA box); VMV_ERR_UNSUPPORTED otherwise.  Auto picks 2 for the long
+                                  sequences (and, with VMV_ATTN_TC_PACKED=1, for the packed forms, which measure slower
+                                  than kernel 1 on B200), else 1. */
 } vmv_attn_params;
 int vmv_attention(const vmv_attn_params* p, void* stream);
 

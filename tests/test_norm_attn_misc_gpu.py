@@ -78,13 +78,14 @@ def _attn_ref(q, k, v, scale):
     return torch.einsum("bhqk,bhkd->bhqd", torch.softmax(s, -1), v.float())
 
 
-@pytest.mark.parametrize("NF,HW,heads", [(24, 1024, 5), (24, 256, 10), (24, 64, 20), (24, 16, 20), (2, 4096, 5), (3, 100, 2),
-                                         (3, 300, 2), (5, 128, 1), (2, 1000, 3)])
+@pytest.mark.parametrize("NF,HW,heads", [(24, 1024, 5), (24, 256, 10), (24, 64, 20), (24, 16, 20), (48, 64, 20), (48, 16, 20),
+                                         (3, 64, 2), (5, 16, 3), (7, 32, 1), (2, 4096, 5), (3, 100, 2), (3, 300, 2), (5, 128, 1),
+                                         (2, 1000, 3)])
 @pytest.mark.parametrize("impl", [1, 2], ids=["mma.sync", "tcgen05"])
 def test_attention_spatial_fused_qkv(NF, HW, heads, impl):
     from videomv_b200 import ops
-    if impl == 2 and HW < 128:
-        pytest.skip("tcgen05 attention needs nq >= 128")
+    if impl == 2 and HW < 128 and (HW & (HW - 1)):
+        pytest.skip("tcgen05 attention packs short sequences only when their length is a power of two")
     C = heads * 64
     qkv = _r(NF * HW, 3 * C, seed=1)
     out = torch.empty(NF * HW, C, dtype=torch.float16, device="cuda")
@@ -97,13 +98,13 @@ def test_attention_spatial_fused_qkv(NF, HW, heads, impl):
     assert_close(f"attn spatial NF{NF} HW{HW} h{heads}", out, ref, rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("B,Fr,HW,heads,L", [(1, 24, 1024, 5, 77), (2, 24, 64, 20, 77), (1, 4, 256, 10, 145), (2, 3, 256, 10, 77),
-                                              (2, 2, 4096, 5, 145)])
+@pytest.mark.parametrize("B,Fr,HW,heads,L", [(1, 24, 1024, 5, 77), (2, 24, 64, 20, 77), (2, 24, 16, 20, 77), (1, 24, 16, 20, 145),
+                                              (1, 4, 256, 10, 145), (2, 3, 256, 10, 77), (2, 2, 4096, 5, 145)])
 @pytest.mark.parametrize("impl", [1, 2], ids=["mma.sync", "tcgen05"])
 def test_attention_cross(B, Fr, HW, heads, L, impl):
     from videomv_b200 import ops
-    if impl == 2 and HW < 128:
-        pytest.skip("tcgen05 attention needs nq >= 128")
+    if impl == 2 and HW < 128 and Fr % (128 // HW):
+        pytest.skip("packed cross-attention needs the frames of a tile to share one context")
     C = heads * 64
     q = _r(B * Fr * HW, C, seed=1)
     kv = _r(B * L, 2 * C, seed=2)
@@ -117,8 +118,12 @@ def test_attention_cross(B, Fr, HW, heads, L, impl):
     assert_close(f"attn cross B{B} F{Fr} HW{HW} L{L}", out, ref, rtol=2e-3, atol=2e-3)
 
 
-@pytest.mark.parametrize("B,Fr,HW,heads", [(1, 24, 1024, 5), (2, 24, 256, 10), (2, 24, 16, 20), (1, 4, 64, 8), (1, 24, 1024, 8)])
-def test_attention_temporal(B, Fr, HW, heads):
+@pytest.mark.parametrize("B,Fr,HW,heads", [(1, 24, 1024, 5), (2, 24, 256, 10), (2, 24, 16, 20), (1, 4, 64, 8), (1, 24, 1024, 8),
+                                           (2, 24, 1024, 5), (1, 24, 7, 3), (2, 6, 33, 2), (1, 128, 5, 1), (1, 24, 512, 5)])
+@pytest.mark.parametrize("impl", [1, 2], ids=["mma.sync", "tcgen05"])
+def test_attention_temporal(B, Fr, HW, heads, impl):
+    """Temporal attention: a sequence = the F frames of one pixel (row stride HW * ld).  impl 2 = the tcgen05 kernel with
+    G = 128 // F pixels packed per tile by a 4-D TMA box and the j % G == r % G mask."""
     from videomv_b200 import ops
     C = heads * 64
     ld = 3 * C
@@ -126,7 +131,7 @@ def test_attention_temporal(B, Fr, HW, heads):
     out = torch.empty(B * Fr * HW, C, dtype=torch.float16, device="cuda")
     st = (Fr * HW * ld, ld, HW * ld)
     ops.attention(qkv, qkv[:, C:], qkv[:, 2 * C:], out, outer=B, inner=HW, heads=heads, nq=Fr, nk=Fr,
-                  q_strides=st, k_strides=st, v_strides=st, o_strides=(Fr * HW * C, C, HW * C))
+                  q_strides=st, k_strides=st, v_strides=st, o_strides=(Fr * HW * C, C, HW * C), impl=impl)
     t = qkv.reshape(B, Fr, HW, 3, heads, 64).permute(3, 0, 2, 4, 1, 5).reshape(3, B * HW, heads, Fr, 64)
     ref = _attn_ref(t[0], t[1], t[2], 0.125)                              # [B*HW, h, F, 64]
     ref = ref.reshape(B, HW, heads, Fr, 64).permute(0, 3, 1, 2, 4).reshape(B * Fr * HW, C)

@@ -235,16 +235,17 @@ extern "C" int vmv_attention(const vmv_attn_params* p, void* stream) {
     VMV_CHECK_ARG(nb <= 65535 * 1LL && p->heads <= 65535, "vmv_attention: batch %lld too large for one launch", nb);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     {
-        // tcgen05 kernel whenever the layout allows (contiguous batches of >= 128 query rows: spatial self-attention
-        // and text cross-attention), or explicitly with impl == 2.  VMV_ATTN_TC=0 keeps auto on the mma.sync kernel.
+        // tcgen05 kernel whenever the layout allows (long contiguous sequences, packed short ones, packed strided ones:
+        // every attention of the UNet), or explicitly with impl == 2.  VMV_ATTN_TC=0 keeps auto on the mma.sync kernel.
         static int auto_tc = -1;
         if (auto_tc < 0) { const char* e = getenv("VMV_ATTN_TC"); auto_tc = (e && e[0] == '0') ? 0 : 1; }
         if (p->impl == 2 || (p->impl == 0 && auto_tc)) {
             const int rc = attention_tc_try(p, st);
             if (rc != VMV_ERR_UNSUPPORTED) return rc;
             if (p->impl == 2) {
-                set_error("vmv_attention: impl=2 (tcgen05) needs contiguous batches (inner == 1, batch stride == n * row "
-                          "stride), nq >= 128 and 32 B aligned output rows");
+                set_error("vmv_attention: impl=2 (tcgen05) needs contiguous batches (inner == 1, batch stride == n * row stride) of "
+                          ">= 128 rows or of a power-of-two length that divides 128, or strided sequences of <= 128 rows "
+                          "(inner > 1, nq == nk), and 32 B aligned output rows");
                 return VMV_ERR_UNSUPPORTED;
             }
         }

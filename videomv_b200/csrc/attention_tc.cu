@@ -1,5 +1,13 @@
-// tcgen05 flash attention for the long-sequence cases (spatial self-attention 256..4096 tokens, text cross-attention):
-//   O = softmax(Q K^T * scale) V,  head_dim 64, fp16 in/out, fp32 softmax, batches contiguous in memory.
+// tcgen05 flash attention:  O = softmax(Q K^T * scale) V,  head_dim 64, fp16 in/out, fp32 softmax.
+//   mode 0  long sequences (spatial self-attention 256..4096 tokens, text cross-attention), batches contiguous in memory;
+//   mode 1  SHORT contiguous sequences (spatial / cross attention at the 8x8 and 4x4 levels: 64 or 16 tokens): 128 / n
+//           consecutive sequences are packed into one 128-row tile; self-attention masks the score tile block-diagonally,
+//           cross-attention needs no mask (the packed frames share the text K/V);
+//   mode 2  STRIDED short sequences (temporal attention: a sequence = the F frames of one pixel, frame stride = HW rows):
+//           G = 128 / F pixels are packed into one tile by a 4-D TMA box (64 d, G pixels, F frames, 1 sample); tile row
+//           r = f * G + p, so query r may attend key j iff j % G == r % G (and j < G * F).
+// The packed modes spend up to 128 / n times the minimum MMA / exp work, which is free here: these shapes are bound by the
+// HBM traffic of Q, K, V, O, and the tile now arrives in a handful of TMA boxes instead of per-thread strided loads.
 //
 // Persistent: one CTA per SM walks tiles of 128 query rows of one (batch, head); K/V are streamed in 128-key chunks
 // through a 4-stage TMA ring.  All pipeline counters run across tiles, so the next tile's Q / first K/V chunks are
@@ -20,6 +28,8 @@
 #include "../../include/videomv_b200.h"
 
 #include <mutex>
+#include <stdlib.h>
+#include <string.h>
 
 namespace vmv {
 
@@ -44,6 +54,12 @@ constexpr int AT_OCOL = 256;
 struct AttTcArgs {
     int nq, nk, kv_group;
     int nqt, heads, ntiles;                               // tile = (batch, head, 128-row block), q block fastest
+    int mode;                                             // 0 long sequences, 1 packed contiguous, 2 packed strided (see the header)
+    int G, seq_shift;                                     // mode 2: pixels per tile; mode 1: log2(tokens per sequence)
+    int self_mask;                                        // mode 1: block-diagonal mask (self-attention) or none (cross)
+    int rows_total;                                       // mode 1: outer * nq rows in the flattened row space
+    int HW;                                               // mode 2: pixels (sequences) per sample
+    long long o_bs_inner;                                 // mode 2: output stride between pixels
     float scale_log2;                                     // scale * log2(e)
     __half* o;
     long long o_bs, o_rs;                                 // elements
@@ -78,7 +94,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int nchunks = (a.nk + AT_BN - 1) / AT_BN;
+    // key chunks per tile: packed self-attention tiles hold their keys in one chunk; cross-attention streams the context
+    const int nchunks = (a.mode == 0 || (a.mode == 1 && !a.self_mask)) ? (a.nk + AT_BN - 1) / AT_BN : 1;
     const int tstep = gridDim.x;
 
     if (warp == 0 && lane == 0) {
@@ -95,6 +112,14 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<AT_TMEM_COLS>(tmem_ptr_smem);
+    if (a.mode == 2) {
+        // the packed box brings G * F < 128 rows: the rows behind it are never written by TMA.  Their keys are masked (P = 0
+        // exactly), but 0 x NaN would still poison P V, so the tail rows of every V stage are zeroed once.
+        const int first = a.G * a.nq * 128;                   // bytes
+        for (int i = first + (int)threadIdx.x * 16; i < AT_TILE; i += AT_THREADS * 16)
+            for (int st = 0; st < AT_KV; ++st) *reinterpret_cast<uint4*>(smem + AT_OFF_V + st * AT_TILE + i) = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+    }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -105,18 +130,40 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     if (warp == 0) {
         if (lane == 0) {
             int g = 0, tc = 0;                                // chunk / tile counters of this CTA
+            const uint32_t box_bytes = a.mode == 2 ? (uint32_t)(a.G * a.nq) * 128u : (uint32_t)AT_TILE;   // rows a box brings x 128 B
             for (int T = blockIdx.x; T < a.ntiles; T += tstep, ++tc) {
                 const int qt = T % a.nqt, h = (T / a.nqt) % a.heads, bo = T / (a.nqt * a.heads);
-                const int kbo = bo / a.kv_group;
                 mbar_wait(q_empty, (tc & 1) ^ 1);
-                mbar_arrive_expect_tx(q_full, AT_TILE);
-                tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + qt * AT_BM);
-                for (int j = 0; j < nchunks; ++j, ++g) {
-                    const int st = g % AT_KV;
-                    mbar_wait(&kv_empty[st], ((g / AT_KV) & 1) ^ 1);
-                    mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
-                    tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
-                    tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                mbar_arrive_expect_tx(q_full, box_bytes);
+                if (a.mode == 0) {
+                    const int kbo = bo / a.kv_group;
+                    tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, bo * a.nq + qt * AT_BM);
+                    for (int j = 0; j < nchunks; ++j, ++g) {
+                        const int st = g % AT_KV;
+                        mbar_wait(&kv_empty[st], ((g / AT_KV) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&kv_full[st], 2 * AT_TILE);
+                        tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                        tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, kbo * a.nk + j * AT_BN);
+                    }
+                } else {
+                    // packed.  mode 1: qt = 128-row block of the flattened row space (bo == 0); mode 2: qt = group of G pixels,
+                    // bo = sample
+                    int krow = qt * AT_BM;                                            // self-attention: the same rows
+                    if (a.mode == 1 && !a.self_mask) krow = ((qt * AT_BM) >> a.seq_shift) / a.kv_group * a.nk;   // the frames' shared context
+                    if (a.mode == 1) tma_load_2d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, qt * AT_BM);
+                    else tma_load_4d(smem + AT_OFF_Q, &tmQ, q_full, h * AT_D, qt * a.G, 0, bo);
+                    for (int j = 0; j < nchunks; ++j, ++g) {
+                        const int st = g % AT_KV;
+                        mbar_wait(&kv_empty[st], ((g / AT_KV) & 1) ^ 1);
+                        mbar_arrive_expect_tx(&kv_full[st], 2 * box_bytes);
+                        if (a.mode == 1) {
+                            tma_load_2d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, krow + j * AT_BN);
+                            tma_load_2d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, krow + j * AT_BN);
+                        } else {
+                            tma_load_4d(smem + AT_OFF_K + st * AT_TILE, &tmK, &kv_full[st], h * AT_D, qt * a.G, 0, bo);
+                            tma_load_4d(smem + AT_OFF_V + st * AT_TILE, &tmV, &kv_full[st], h * AT_D, qt * a.G, 0, bo);
+                        }
+                    }
                 }
             }
         }
@@ -194,7 +241,8 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             };
             for (int j = 0; j < nchunks; ++j, ++g) {
                 const int kbase = j * AT_BN + hh * 64;
-                const bool full = kbase + 64 <= a.nk;         // warp-uniform: only the last chunk can be ragged
+                // warp-uniform: only the last chunk can be ragged; the packed modes always take the masked path
+                const bool full = a.mode == 0 ? kbase + 64 <= a.nk : (a.mode == 1 && !a.self_mask && kbase + 64 <= a.nk);
                 mbar_wait(&s_full[g & 1], (g >> 1) & 1);
                 tc_fence_after();
                 uint32_t sv[64];
@@ -206,6 +254,25 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
                 if (full) {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) mx = fmaxf(mx, __uint_as_float(sv[i]));
+                } else if (a.mode == 2) {
+                    // tile row = f * G + pixel: key jj belongs to my sequence iff jj % G == r % G (and it is a loaded row)
+                    const int G = a.G, lim = a.G * a.nq;
+                    int jm = kbase % G;
+                    const int rm = r % G;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        if (jm != rm || kbase + i >= lim) sv[i] = 0xff800000u;
+                        jm = (jm + 1 == G) ? 0 : jm + 1;
+                        mx = fmaxf(mx, __uint_as_float(sv[i]));
+                    }
+                } else if (a.mode == 1 && a.self_mask) {
+                    // packed contiguous sequences of 2^seq_shift tokens: block-diagonal
+                    const int rb = r >> a.seq_shift;
+#pragma unroll
+                    for (int i = 0; i < 64; ++i) {
+                        if (((kbase + i) >> a.seq_shift) != rb) sv[i] = 0xff800000u;
+                        mx = fmaxf(mx, __uint_as_float(sv[i]));
+                    }
                 } else {
 #pragma unroll
                     for (int i = 0; i < 64; ++i) {
@@ -258,8 +325,21 @@ attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
             pair_sync();
             const float inv = 1.f / (l_run + xsum[(hh ^ 1) * 128 + r]);
             const int qrow = qt * AT_BM + r;
-            if (qrow < a.nq) {
-                __half* dst = a.o + (long long)bo * a.o_bs + (long long)qrow * a.o_rs + h * AT_D + hh * 32;
+            bool st_ok;
+            long long o_off;
+            if (a.mode == 0) {
+                st_ok = qrow < a.nq;
+                o_off = (long long)bo * a.o_bs + (long long)qrow * a.o_rs;
+            } else if (a.mode == 1) {                             // flattened row space, sequences contiguous
+                st_ok = qrow < a.rows_total;
+                o_off = (long long)qrow * a.o_rs;
+            } else {                                              // row r = frame f, pixel qt * G + p
+                const int f = r / a.G, pix = qt * a.G + (r - f * a.G);
+                st_ok = f < a.nq && pix < a.HW;
+                o_off = (long long)bo * a.o_bs + (long long)pix * a.o_bs_inner + (long long)f * a.o_rs;
+            }
+            if (st_ok) {
+                __half* dst = a.o + o_off + h * AT_D + hh * 32;
 #pragma unroll
                 for (int c = 0; c < 32; c += 16) {
                     uint32_t w[8];
@@ -282,25 +362,63 @@ static bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 // Returns VMV_OK if launched, VMV_ERR_UNSUPPORTED if the problem does not fit this kernel (caller falls back to the
 // generic strided kernel), another code on error.
 int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
-    if (p->inner != 1 || p->nq < 128) return VMV_ERR_UNSUPPORTED;
-    if (p->q_bs_outer != (int64_t)p->nq * p->q_rs || p->k_bs_outer != (int64_t)p->nk * p->k_rs ||
-        p->v_bs_outer != (int64_t)p->nk * p->v_rs)
+    // The packed forms are correct for every short-sequence attention of the UNet but measured SLOWER than the mma.sync
+    // kernel on them (temporal 24 x 24 at the 32x32 level, CFG batch: 53.5 vs 27 us; 64-token spatial: 13.9 vs ~9 us --
+    // profiles/r2_attention_packed.md): one key chunk per tile leaves the per-tile latency chain (TMA -> S -> softmax -> P ->
+    // PV -> O) unamortised, while the mma.sync kernel already streams Q/K/V/O at 3.4-4.6 TB/s.  So `impl = 0` (auto) takes
+    // them only with VMV_ATTN_TC_PACKED=1; `impl = 2` always does.
+    static int packed_auto = -1;
+    if (packed_auto < 0) { const char* e = getenv("VMV_ATTN_TC_PACKED"); packed_auto = (e && e[0] == '1') ? 1 : 0; }
+    if (p->impl == 0 && !packed_auto && !(p->inner == 1 && p->nq >= 128)) return VMV_ERR_UNSUPPORTED;
+    // ---- which form of the kernel takes this problem?
+    int mode = -1, G = 0, seq_shift = 0, self_mask = 0;
+    if (p->inner == 1 && p->nq >= 128) {
+        mode = 0;
+    } else if (p->inner == 1 && p->nq >= 8 && (p->nq & (p->nq - 1)) == 0) {
+        // short contiguous sequences: 128 / nq of them per tile
+        while ((1 << seq_shift) < p->nq) ++seq_shift;
+        G = 128 / p->nq;
+        if (p->kv_group == 1 && p->nk == p->nq) { mode = 1; self_mask = 1; }
+        else if (p->kv_group > 1 && p->kv_group % G == 0) { mode = 1; self_mask = 0; }
+        if (mode == 1 && p->o_bs_outer != (int64_t)p->nq * p->o_rs) mode = -1;       // the output rows must be contiguous too
+    } else if (p->inner > 1 && p->kv_group == 1 && p->nq == p->nk && p->nq >= 2 && p->nq <= 128) {
+        mode = 2;                                                 // strided short sequences (temporal attention)
+        G = 128 / p->nq;
+    }
+    if (mode < 0) return VMV_ERR_UNSUPPORTED;
+    if (mode != 2 && (p->q_bs_outer != (int64_t)p->nq * p->q_rs || p->k_bs_outer != (int64_t)p->nk * p->k_rs ||
+                      p->v_bs_outer != (int64_t)p->nk * p->v_rs))
         return VMV_ERR_UNSUPPORTED;                               // batches must be contiguous row blocks
     if (p->outer % p->kv_group != 0) return VMV_ERR_UNSUPPORTED;
-    if (!aligned32(p->o) || p->o_rs % 16 != 0 || p->o_bs_outer % 16 != 0) return VMV_ERR_UNSUPPORTED;
+    if (!aligned32(p->o) || p->o_rs % 16 != 0 || p->o_bs_outer % 16 != 0 || (mode == 2 && p->o_bs_inner % 16 != 0)) return VMV_ERR_UNSUPPORTED;
     if ((reinterpret_cast<uintptr_t>(p->q) | reinterpret_cast<uintptr_t>(p->k) | reinterpret_cast<uintptr_t>(p->v)) & 15)
         return VMV_ERR_UNSUPPORTED;
     CUtensorMap tq, tk, tv;
-    const unsigned box[2] = {AT_D, 128};
-    auto mk = [&](CUtensorMap* m, const void* base, long long rows, long long rs) {
-        const unsigned long long dims[2] = {(unsigned long long)p->heads * AT_D, (unsigned long long)rows};
-        const unsigned long long strides[1] = {(unsigned long long)rs * 2};
-        return make_map_generic(m, base, 2, dims, strides, box, 128);
-    };
     int rc;
-    if ((rc = mk(&tq, p->q, (long long)p->outer * p->nq, p->q_rs)) != VMV_OK) return rc;
-    if ((rc = mk(&tk, p->k, (long long)(p->outer / p->kv_group) * p->nk, p->k_rs)) != VMV_OK) return rc;
-    if ((rc = mk(&tv, p->v, (long long)(p->outer / p->kv_group) * p->nk, p->v_rs)) != VMV_OK) return rc;
+    if (mode != 2) {
+        const unsigned box[2] = {AT_D, 128};
+        auto mk = [&](CUtensorMap* m, const void* base, long long rows, long long rs) {
+            const unsigned long long dims[2] = {(unsigned long long)p->heads * AT_D, (unsigned long long)rows};
+            const unsigned long long strides[1] = {(unsigned long long)rs * 2};
+            return make_map_generic(m, base, 2, dims, strides, box, 128);
+        };
+        if ((rc = mk(&tq, p->q, (long long)p->outer * p->nq, p->q_rs)) != VMV_OK) return rc;
+        if ((rc = mk(&tk, p->k, (long long)(p->outer / p->kv_group) * p->nk, p->k_rs)) != VMV_OK) return rc;
+        if ((rc = mk(&tv, p->v, (long long)(p->outer / p->kv_group) * p->nk, p->v_rs)) != VMV_OK) return rc;
+    } else {
+        // (d, pixel, frame, sample): one box = 64 d x G pixels x all F frames of one sample; rows land as (frame, pixel)
+        const unsigned box[4] = {AT_D, (unsigned)G, (unsigned)p->nq, 1};
+        auto mk4 = [&](CUtensorMap* m, const void* base, long long bs_o, long long bs_i, long long rs) {
+            if ((bs_o * 2) % 16 || (bs_i * 2) % 16 || (rs * 2) % 16) return (int)VMV_ERR_UNSUPPORTED;
+            const unsigned long long dims[4] = {(unsigned long long)p->heads * AT_D, (unsigned long long)p->inner,
+                                                (unsigned long long)p->nq, (unsigned long long)p->outer};
+            const unsigned long long strides[3] = {(unsigned long long)bs_i * 2, (unsigned long long)rs * 2, (unsigned long long)bs_o * 2};
+            return make_map_generic(m, base, 4, dims, strides, box, 128);
+        };
+        if ((rc = mk4(&tq, p->q, p->q_bs_outer, p->q_bs_inner, p->q_rs)) != VMV_OK) return rc;
+        if ((rc = mk4(&tk, p->k, p->k_bs_outer, p->k_bs_inner, p->k_rs)) != VMV_OK) return rc;
+        if ((rc = mk4(&tv, p->v, p->v_bs_outer, p->v_bs_inner, p->v_rs)) != VMV_OK) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, AT_SMEM);
@@ -308,13 +426,26 @@ int attention_tc_try(const vmv_attn_params* p, cudaStream_t st) {
         attr_set = true;
     }
     AttTcArgs a;
+    memset(&a, 0, sizeof(a));
     a.nq = p->nq; a.nk = p->nk; a.kv_group = p->kv_group;
     a.scale_log2 = p->scale * 1.4426950408889634f;
     a.o = static_cast<__half*>(p->o);
-    a.o_bs = p->o_bs_outer; a.o_rs = p->o_rs;
-    a.nqt = (p->nq + AT_BM - 1) / AT_BM;
+    a.o_bs = p->o_bs_outer; a.o_rs = p->o_rs; a.o_bs_inner = p->o_bs_inner;
     a.heads = p->heads;
-    const long long ntiles = (long long)a.nqt * p->heads * p->outer;
+    a.mode = mode; a.G = G; a.seq_shift = seq_shift; a.self_mask = self_mask;
+    a.rows_total = (int)((long long)p->outer * p->nq);
+    a.HW = p->inner;
+    long long ntiles;
+    if (mode == 0) {
+        a.nqt = (p->nq + AT_BM - 1) / AT_BM;
+        ntiles = (long long)a.nqt * p->heads * p->outer;
+    } else if (mode == 1) {
+        a.nqt = (int)(((long long)p->outer * p->nq + AT_BM - 1) / AT_BM);       // 128-row blocks of the flattened row space
+        ntiles = (long long)a.nqt * p->heads;
+    } else {
+        a.nqt = (p->inner + G - 1) / G;                                          // groups of G pixels
+        ntiles = (long long)a.nqt * p->heads * p->outer;
+    }
     if (ntiles > 0x7fffffffLL) return VMV_ERR_UNSUPPORTED;
     a.ntiles = (int)ntiles;
     static int num_sms = 0;
