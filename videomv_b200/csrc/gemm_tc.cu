@@ -27,6 +27,10 @@ void count_launch(int n = 1);
 #ifndef VMV_EPI_SPLIT
 #define VMV_EPI_SPLIT 2
 #endif
+#ifndef VMV_EPI_COLS
+#define VMV_EPI_COLS 32
+#endif
+constexpr int EPI_COLS = VMV_EPI_COLS;           // columns an epilogue thread drains per step: 32, or 16 (half the live registers, for more epilogue warps)
 constexpr int EPI_SPLIT = VMV_EPI_SPLIT;         // epilogue warps per TMEM lane quarter: they share a quarter's rows and interleave the tile's 32-column blocks
 constexpr int BM = 128;
 constexpr int BK = 64;
@@ -777,7 +781,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 // (2) request the residual of my first block and my row's LayerNorm statistics
                 if (resrow && hh < nvalid) {
                     ldg256(resrow + hh * 32, *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
-                    ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
+                    if (EPI_COLS == 32) ldg256(resrow + hh * 32 + 16, *reinterpret_cast<uint32_t(*)[8]>(&rcur[8]));
                 }
                 // (slot statistics are merged right here: the loads are independent, so their latency is that of the single
                 // {mean, rstd} load, and only two registers stay live across the accumulator wait)
@@ -788,6 +792,123 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             tc_fence_after();
             if (!a.fast_epi) {
                 if (hh == 0) epilogue_store<BN>(a, nt, split, grow, valid, trow);     // split-K partials / unaligned outputs
+            } else if (EPI_COLS == 16 && !(a.dbg & 2)) {
+                // ---- 16-column steps: the same fused epilogue with half the live registers per thread (one tcgen05.ld.x16, one
+                // 32 B residual / row-bias load and one 32 B store per step), so that more epilogue warps fit the register file
+                const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
+                const bool ln = a.ln_stats != nullptr;
+                float ln_a = 1.f, ln_b = 0.f;
+                if (ln && valid) { ln_a = ln_ms.y; ln_b = -ln_ms.y * ln_ms.x; }
+                const bool has_b = a.bias != nullptr;
+                const int nblk = max((nvalid - hh + EPI_SPLIT - 1) / EPI_SPLIT, 0);     // my 32-column blocks
+                const int nsteps = 2 * nblk;
+                float row_s = 0.f, row_q = 0.f, row_sh = 0.f;
+                int row_cnt = 0;
+                uint32_t v[16], g[16];
+                auto col_of = [&](int st_) { return (hh + EPI_SPLIT * (st_ >> 1)) * EPI_BLK_COLS + (st_ & 1) * 16; };
+                auto request = [&](int st_) {                   // TMEM -> registers for step st_ (value columns, + gate columns for GEGLU)
+                    const int c_ = col_of(st_);
+                    tmem_ld_32x32b_x16(trow + c_, v);
+                    if (geglu) tmem_ld_32x32b_x16(trow + BN / 2 + c_, g);
+                };
+                if (nsteps > 0) request(0);
+#pragma unroll 1
+                for (int st_ = 0; st_ < nsteps; ++st_) {
+                    const int j = st_ >> 1, half = st_ & 1;
+                    const int c = col_of(st_);
+                    uint32_t rbv[8];
+                    if (rb) ldg256(rb + col0 + c, rbv);
+                    tmem_ld_wait();
+                    float x[16];
+                    if (geglu) {
+                        const float4* bv4 = reinterpret_cast<const float4*>(sbias + j * 64 + half * 16);    // value; gate at +32
+                        const float4* cv4 = reinterpret_cast<const float4*>(scol + j * 64 + half * 16);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float4 b4 = bv4[i], g4 = bv4[8 + i], c4 = cv4[i], d4 = cv4[8 + i];
+                            const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, bg[4] = {g4.x, g4.y, g4.z, g4.w};
+                            const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, cg[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float val = fmaf(__uint_as_float(v[4 * i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                                const float gate = fmaf(__uint_as_float(g[4 * i + e]), ln_a, fmaf(ln_b, cg[e], bg[e]));
+                                x[4 * i + e] = geglu_f(val, gate);
+                            }
+                        }
+                    } else {
+                        const float4* bv4 = reinterpret_cast<const float4*>(sbias + j * 32 + half * 16);
+                        const float4* cv4 = reinterpret_cast<const float4*>(scol + j * 32 + half * 16);
+                        if (ln) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = bv4[i], c4 = cv4[i];
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w}, cv[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[4 * i + e] = fmaf(__uint_as_float(v[4 * i + e]), ln_a, fmaf(ln_b, cv[e], bv[e]));
+                            }
+                        } else if (has_b) {
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) {
+                                const float4 b4 = bv4[i];
+                                const float bv[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                                for (int e = 0; e < 4; ++e) x[4 * i + e] = __uint_as_float(v[4 * i + e]) + bv[e];
+                            }
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) x[i] = __uint_as_float(v[i]);
+                        }
+                    }
+                    if (st_ + 1 < nsteps) request(st_ + 1);     // the next step's accumulators travel while this one is finished
+                    if (!geglu) {
+                        if (rb) {
+#pragma unroll
+                            for (int i = 0; i < 8; ++i) {
+                                const float2 f = unpack_half2(rbv[i]);
+                                x[2 * i] += f.x;
+                                x[2 * i + 1] += f.y;
+                            }
+                        }
+                        if (a.act == VMV_ACT_SILU) {
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) x[i] = silu_f(x[i]);
+                        }
+                    }
+                    if (resrow) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const float2 f = unpack_half2(rcur[i]);
+                            x[2 * i] += f.x;
+                            x[2 * i + 1] += f.y;
+                        }
+                        if (st_ + 1 < nsteps) ldg256(resrow + col_of(st_ + 1), *reinterpret_cast<uint32_t(*)[8]>(&rcur[0]));
+                    }
+                    if (a.rowstats) {
+                        if (row_cnt == 0) row_sh = x[0];
+                        row_cnt += 16;
+#pragma unroll
+                        for (int i = 0; i < 16; ++i) {
+                            const float d = x[i] - row_sh;
+                            row_s += d;
+                            row_q = fmaf(d, d, row_q);
+                        }
+                    }
+                    if (valid && !(a.dbg & 1)) {
+                        uint32_t o[8];
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
+                        stg256(drow + col0 + c, o);
+                    }
+                }
+                if (a.rowstats && valid) {
+                    float2 st = make_float2(0.f, 0.f);
+                    if (row_cnt > 0) {
+                        const float inv = 1.f / (float)row_cnt;
+                        st.x = fmaf(row_s, inv, row_sh);
+                        st.y = fmaxf(fmaf(-row_s * inv, row_s, row_q), 0.f);
+                    }
+                    a.rowstats[grow * a.rowstats_nslots + EPI_SPLIT * nt + hh] = st;
+                }
             } else if (!(a.dbg & 2)) {
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
                 // folded LayerNorm as two FMAs per accumulator:  rstd*(acc - mean*colsum) + bias = acc*ln_a + (ln_b*colsum + bias)
