@@ -30,6 +30,13 @@ void count_launch(int n = 1);
 #ifndef VMV_EPI_COLS
 #define VMV_EPI_COLS 32
 #endif
+// VMV_GEMM_DEBUG knock-out experiments (skip stores / epilogue / operand traffic / MMAs) are compiled in only with
+// -DVMV_GEMM_DEBUG_BUILD: their run-time tests sat in the hot loops of the production kernel
+#ifdef VMV_GEMM_DEBUG_BUILD
+#define VMV_DBG(a_) ((a_).dbg)
+#else
+#define VMV_DBG(a_) 0
+#endif
 constexpr int EPI_COLS = VMV_EPI_COLS;           // columns an epilogue thread drains per step: 32, or 16 (half the live registers, for more epilogue warps)
 constexpr int EPI_SPLIT = VMV_EPI_SPLIT;         // epilogue warps per TMEM lane quarter: they share a quarter's rows and interleave the tile's 32-column blocks
 constexpr int BM = 128;
@@ -90,24 +97,24 @@ struct GemmArgs {
     unsigned int* sc_done;
 };
 
-// destination of output row `grow` when the epilogue scatters into the other sharding layout
-__device__ __forceinline__ __half* scatter_row(const GemmArgs& a, long long grow) {
-    const int P = a.sc_world;
-    const long long HWl = a.sc_HWl;
-    int q;
-    long long row;
+// destination of output row `grow` when the epilogue scatters into the other sharding layout (32-bit index arithmetic:
+// M < 2^31)
+__device__ __forceinline__ __half* scatter_row(const GemmArgs& a, long long grow_) {
+    const unsigned P = (unsigned)a.sc_world, HWl = (unsigned)a.sc_HWl, Fl = (unsigned)a.sc_Fl, grow = (unsigned)grow_;
+    unsigned q;
+    unsigned long long row;
     if (a.sc_dir == 0) {                               // rows (b, f, pixel), pixel < P*HWl
-        const long long HW = HWl * P;
-        const long long bf = grow / HW, pix = grow - bf * HW;
-        const long long b = bf / a.sc_Fl, f = bf - b * a.sc_Fl;
-        q = (int)(pix / HWl);
-        row = ((b * P + a.sc_rank) * a.sc_Fl + f) * HWl + (pix - (long long)q * HWl);
+        const unsigned HW = HWl * P;
+        const unsigned bf = grow / HW, pix = grow - bf * HW;
+        const unsigned b = bf / Fl, f = bf - b * Fl;
+        q = pix / HWl;
+        row = ((unsigned long long)(b * P + (unsigned)a.sc_rank) * Fl + f) * HWl + (pix - q * HWl);
     } else {                                           // rows (b, fg, pl), fg < P*Fl
-        const long long F = (long long)a.sc_Fl * P;
-        const long long bf = grow / HWl, pl = grow - bf * HWl;
-        const long long b = bf / F, fg = bf - b * F;
-        q = (int)(fg / a.sc_Fl);
-        row = ((b * a.sc_Fl + (fg - (long long)q * a.sc_Fl)) * P + a.sc_rank) * HWl + pl;
+        const unsigned F = Fl * P;
+        const unsigned bf = grow / HWl, pl = grow - bf * HWl;
+        const unsigned b = bf / F, fg = bf - b * F;
+        q = fg / Fl;
+        row = ((unsigned long long)(b * Fl + (fg - q * Fl)) * P + (unsigned)a.sc_rank) * HWl + pl;
     }
     return a.sc_dst[q] + row * a.ldd;
 }
@@ -518,13 +525,16 @@ struct SmemLayout2 {
     static_assert(DYN_BYTES + V2_EPI_WARPS * 1024 + 1024 <= 232448, "shared memory budget exceeded");
 };
 
-// NBLK is unused by the register epilogue (kept so instantiations stay distinct per use)
-template <int BN, int STAGES, int NBLK>
+// FLAVOR specialises the epilogue at compile time (the one kernel with every path behind run-time branches was 9.9 k SASS
+// instructions = 159 KB of code; ncu showed instruction-fetch stalls in the epilogue warps):
+//   1 = register epilogue with GEGLU, 2 = generic epilogue (split-K partials, unaligned rows),
+//   0 / 4 / 8 / 12 = register epilogue without GEGLU; bit 2: a LayerNorm is folded in, bit 3: a residual is added
+template <int BN, int STAGES, int FLAVOR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmA2,
                 const __grid_constant__ CUtensorMap tmW, const GemmArgs a, const int m_pairs, const int n_tiles,
                 const int splits) {
-    using L = SmemLayout2<BN, STAGES, NBLK>;
+    using L = SmemLayout2<BN, STAGES, FLAVOR>;
     constexpr int TCOLS = TmemCols<2 * BN>::value;
     static_assert(2 * BN <= 512, "two accumulator buffers must fit TMEM");
     // Per-epilogue-warp scratch: 128 bias floats + 128 LayerNorm column sums of the columns the warp owns in the current
@@ -586,7 +596,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             // ------------------------------ TMA producer (both CTAs) ------------------------------
             constexpr uint32_t tx_bytes = 2u * (A_STAGE_BYTES + L::B_STAGE_BYTES);
             int pre = 0;                                    // stages whose barrier arrival + W load were issued pre-wait
-            if (a.w_static && !(a.dbg & 4) && t_begin < t_end) {
+            if (a.w_static && !(VMV_DBG(a) & 4) && t_begin < t_end) {
                 const int split = t_begin / tiles_mn;
                 const int rem0 = t_begin - split * tiles_mn;
                 const int nt = rem0 % n_tiles;
@@ -636,7 +646,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     const uint32_t ph = (it / depth) & 1;
                     const bool prefetched = it < pre;      // first ring pass: arrival + W tile already issued
                     if (!prefetched) mbar_wait(&empty_bar[s], ph ^ 1);
-                    if (a.dbg & 4) {                       // experiment: no operand traffic, barrier protocol only
+                    if (VMV_DBG(a) & 4) {                       // experiment: no operand traffic, barrier protocol only
                         if (rank == 0) mbar_arrive(&full_bar[s]);
                         else mbar_arrive_remote(&full_bar[s], 0);
                         continue;
@@ -691,7 +701,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     tc_fence_after();
                     const uint64_t adesc = umma_desc_sw128_kmajor(smem_u32(smem + L::A_OFF + s * A_STAGE_BYTES));
                     const uint64_t bdesc = umma_desc_sw128_kmajor(smem_u32(smem + L::B_OFF + s * L::B_STAGE_BYTES));
-                    if (!(a.dbg & 8)) {
+                    if (!(VMV_DBG(a) & 8)) {
 #pragma unroll
                         for (int k = 0; k < BK / 16; ++k)
                             umma_f16_ss_2sm(dcol, adesc + 2 * k, bdesc + 2 * k, idesc, (kb > kb_begin || k > 0) ? 1u : 0u);
@@ -715,7 +725,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
         const int r = q * 32 + lane;
         float* sbias = s_epi_scr[warp - 2];
         float* scol = sbias + 128;
-        const bool geglu = a.act == VMV_ACT_GEGLU;
+        constexpr bool geglu = FLAVOR == 1;
         const int out_bn = geglu ? BN / 2 : BN;                 // output columns per tile
         // Bias / LayerNorm column sums of this warp's columns are fetched ONE TILE AHEAD into registers (<= 128 values per
         // array per warp = 4 per lane) and only copied to the smem scratch at the top of their tile: when the epilogue is
@@ -744,7 +754,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 }
             }
         };
-        if (a.fast_epi) fetch_cols(t_begin);
+        if (FLAVOR != 2) fetch_cols(t_begin);
         int acc_it = 0;
         for (int t = t_begin; t < t_end; t += t_step, ++acc_it) {
             const int split = t / tiles_mn;
@@ -760,12 +770,16 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
             const int col0 = nt * out_bn;
             int nvalid = min(out_bn / EPI_BLK_COLS, (a.n_out - col0 + EPI_BLK_COLS - 1) / EPI_BLK_COLS);
             if (nvalid < 0) nvalid = 0;
-            const __half* resrow = (a.residual && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
+            // (compile-time for the non-GEGLU register flavors, run-time otherwise)
+            constexpr bool kFixed = FLAVOR != 1 && FLAVOR != 2;
+            const bool use_res = kFixed ? (FLAVOR & 8) != 0 : a.residual != nullptr;
+            const bool use_ln = kFixed ? (FLAVOR & 4) != 0 : a.ln_stats != nullptr;
+            const __half* resrow = (use_res && valid) ? a.residual + grow * a.ldr + col0 : nullptr;
             __half* drow = nullptr;                              // my output row (possibly in a peer's memory)
             if (valid) drow = a.sc_world ? scatter_row(a, grow) : a.D + grow * a.ldd;
             uint32_t rcur[16];
             float2 ln_ms = make_float2(0.f, 1.f);
-            if (a.fast_epi) {
+            if (FLAVOR != 2) {
                 // (1) this warp's bias / column-sum slices (fetched one tile ago) go to the smem scratch.  Slot j*32+i holds
                 //     column (hh+2j)*32+i of the tile; GEGLU keeps value and gate columns in slots j*64+i and j*64+32+i.
                 __syncwarp();                                   // previous tile's readers are done with the scratch
@@ -785,18 +799,18 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 }
                 // (slot statistics are merged right here: the loads are independent, so their latency is that of the single
                 // {mean, rstd} load, and only two registers stay live across the accumulator wait)
-                if (a.ln_stats != nullptr && valid) ln_ms = ln_row_stats(a, grow);
+                if (use_ln && valid) ln_ms = ln_row_stats(a, grow);
                 __syncwarp();
             }
             mbar_wait(&tmem_full_bar[buf], aph);
             tc_fence_after();
-            if (!a.fast_epi) {
+            if (FLAVOR == 2) {
                 if (hh == 0) epilogue_store<BN>(a, nt, split, grow, valid, trow);     // split-K partials / unaligned outputs
-            } else if (EPI_COLS == 16 && !(a.dbg & 2)) {
+            } else if (EPI_COLS == 16 && !(VMV_DBG(a) & 2)) {
                 // ---- 16-column steps: the same fused epilogue with half the live registers per thread (one tcgen05.ld.x16, one
                 // 32 B residual / row-bias load and one 32 B store per step), so that more epilogue warps fit the register file
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
-                const bool ln = a.ln_stats != nullptr;
+                const bool ln = use_ln;
                 float ln_a = 1.f, ln_b = 0.f;
                 if (ln && valid) { ln_a = ln_ms.y; ln_b = -ln_ms.y * ln_ms.x; }
                 const bool has_b = a.bias != nullptr;
@@ -869,10 +883,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                                 x[2 * i + 1] += f.y;
                             }
                         }
-                        if (a.act == VMV_ACT_SILU) {
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) x[i] = silu_f(x[i]);
-                        }
+
                     }
                     if (resrow) {
 #pragma unroll
@@ -893,7 +904,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             row_q = fmaf(d, d, row_q);
                         }
                     }
-                    if (valid && !(a.dbg & 1)) {
+                    if (valid && !(VMV_DBG(a) & 1)) {
                         uint32_t o[8];
 #pragma unroll
                         for (int i = 0; i < 8; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
@@ -909,10 +920,10 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                     }
                     a.rowstats[grow * a.rowstats_nslots + EPI_SPLIT * nt + hh] = st;
                 }
-            } else if (!(a.dbg & 2)) {
+            } else if (!(VMV_DBG(a) & 2)) {
                 const __half* rb = (a.rowbias && valid) ? a.rowbias + (grow / a.rows_per_group) * a.ld_rowbias : nullptr;
                 // folded LayerNorm as two FMAs per accumulator:  rstd*(acc - mean*colsum) + bias = acc*ln_a + (ln_b*colsum + bias)
-                const bool ln = a.ln_stats != nullptr;
+                const bool ln = use_ln;
                 float ln_a = 1.f, ln_b = 0.f;
                 if (ln && valid) {
                     const float2 ms = ln_ms;
@@ -923,7 +934,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                 int j = 0;
                 // The accumulators of block i+2 are requested from TMEM as soon as block i's have been consumed into x[],
                 // so the tcgen05.ld latency overlaps the residual / activation / pack / store part (VMV_GEMM_DEBUG 16: off).
-                const bool ld_ahead = !(a.dbg & 16);
+                const bool ld_ahead = !(VMV_DBG(a) & 16);
                 bool requested = false;
                 uint32_t v[32];
                 // LayerNorm partial statistics of my row over my blocks (rowstats): sums of (x - row_sh), (x - row_sh)^2 with
@@ -1013,10 +1024,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                                 x[2 * i + 1] += f.y;
                             }
                         }
-                        if (a.act == VMV_ACT_SILU) {
-#pragma unroll
-                            for (int i = 0; i < 32; ++i) x[i] = silu_f(x[i]);
-                        }
+                        // (SiLU outputs -- only the tiny embedding MLPs -- take the generic epilogue: see the flavor dispatch)
                     }
                     if (resrow) {
 #pragma unroll
@@ -1040,7 +1048,7 @@ gemm_tc2_kernel(const __grid_constant__ CUtensorMap tmA1, const __grid_constant_
                             row_q = fmaf(d, d, row_q);
                         }
                     }
-                    if (valid && !(a.dbg & 1)) {
+                    if (valid && !(VMV_DBG(a) & 1)) {
                         uint32_t o[16];
 #pragma unroll
                         for (int i = 0; i < 16; ++i) o[i] = pack_half2(x[2 * i], x[2 * i + 1]);
@@ -1232,13 +1240,13 @@ static int launch_instance(const CUtensorMap& tA1, const CUtensorMap& tA2, const
     return VMV_OK;
 }
 
-template <int BN, int STAGES, int NBLK>
+template <int BN, int STAGES, int FLAVOR>
 static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, const CUtensorMap& tW, const GemmArgs& a,
                             int m_pairs, int n_tiles, int splits, cudaStream_t st) {
-    using L = SmemLayout2<BN, STAGES, NBLK>;
+    using L = SmemLayout2<BN, STAGES, FLAVOR>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, NBLK>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc2_kernel<BN, STAGES, FLAVOR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              L::DYN_BYTES);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(v2 smem=%d) failed: %s", L::DYN_BYTES, cudaGetErrorString(e));
@@ -1256,7 +1264,7 @@ static int launch_instance2(const CUtensorMap& tA1, const CUtensorMap& tA2, cons
     const long long total = (long long)m_pairs * n_tiles * splits;
     int clusters = num_sms / 2;
     if (total < clusters) clusters = (int)total;
-    launch_kernel(gemm_tc2_kernel<BN, STAGES, NBLK>, dim3(2 * clusters), dim3(V2_THREADS), L::DYN_BYTES, st, tA1, tA2, tW, a, m_pairs,
+    launch_kernel(gemm_tc2_kernel<BN, STAGES, FLAVOR>, dim3(2 * clusters), dim3(V2_THREADS), L::DYN_BYTES, st, tA1, tA2, tW, a, m_pairs,
                   n_tiles, splits);
     count_launch();
     VMV_CUDA_LAUNCH_CHECK("vmv_gemm (cta_group::2)");
@@ -1561,9 +1569,25 @@ extern "C" int vmv_gemm(const vmv_gemm_params* p, void* stream) {
             const long long total = (long long)m_pairs * pl.n_tiles;
             if (ares && p->mode == VMV_GEMM_LINEAR && pl.splits <= 1 && a.nkb <= ring && pl.n_tiles >= 2 && total >= 2 * 74) ak.a_res = 1;
         }
-        if (BN == 128) rc = launch_instance2<128, 8, 4>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
-        else if (BN == 160) rc = launch_instance2<160, 8, 5>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
-        else rc = launch_instance2<256, 6, 8>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st);
+        if (p->act == VMV_ACT_SILU && !ak.rowstats && !ak.sc_world) ak.fast_epi = 0;      // rare (embedding MLPs): generic epilogue
+        if (p->act == VMV_ACT_SILU && ak.fast_epi) { set_error("vmv_gemm: SiLU cannot be combined with rowstats_out / scatter"); return VMV_ERR_UNSUPPORTED; }
+        const int flavor = !ak.fast_epi ? 2 : (p->act == VMV_ACT_GEGLU ? 1 : ((ak.ln_stats ? 4 : 0) | (ak.residual ? 8 : 0)));
+#define VMV_L2(BN_, ST_, FL_) rc = launch_instance2<BN_, ST_, FL_>(tA1, tA2, tW, ak, m_pairs, pl.n_tiles, pl.splits, st)
+#define VMV_L2_FLAVORS(BN_, ST_)                                                                      \
+        switch (flavor) {                                                                             \
+            case 0: VMV_L2(BN_, ST_, 0); break;                                                       \
+            case 4: VMV_L2(BN_, ST_, 4); break;                                                       \
+            case 8: VMV_L2(BN_, ST_, 8); break;                                                       \
+            case 12: VMV_L2(BN_, ST_, 12); break;                                                     \
+            case 1: VMV_L2(BN_, ST_, 1); break;                                                       \
+            default: VMV_L2(BN_, ST_, 2); break;                                                      \
+        }
+        if (BN == 160 && flavor == 1) { set_error("vmv_gemm: GEGLU needs block_n 128 or 256"); return VMV_ERR_UNSUPPORTED; }
+        if (BN == 128) { VMV_L2_FLAVORS(128, 8) }
+        else if (BN == 160) { VMV_L2_FLAVORS(160, 8) }
+        else { VMV_L2_FLAVORS(256, 6) }
+#undef VMV_L2_FLAVORS
+#undef VMV_L2
     } else {
         if (a.rowstats || a.sc_world) {
             set_error("vmv_gemm: rowstats_out / scatter are not available in the one-tile-per-CTA kernel (variant 1)");
