@@ -524,6 +524,28 @@ def run_native(args, kind, hw, gs, mean_type, tflop_fwd):
                     model.enable_cuda_graphs(False)
             except Exception as e:  # noqa: BLE001
                 line["e2e_reference_sampler"] = {"error": repr(e)}
+            # ---- the whole 50-step loop as ONE CUDA graph: same kernels, no per-step host work
+            try:
+                model.enable_cuda_graphs(False)
+                loop = lambda: diffusion.ddim_sample_loop(dev_noise, model, model_kwargs=dev_kwargs, guide_scale=gs,
+                                                          ddim_timesteps=DDIM_STEPS, eta=0.0, loop_graph=True)
+                t0 = time.time()
+                loop()
+                torch.cuda.synchronize()
+                t_build = time.time() - t0
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(2):
+                    loop()
+                e1.record()
+                torch.cuda.synchronize()
+                line["loop_graph"] = {"value": FRAMES * 2 / (e0.elapsed_time(e1) / 1e3), "unit": "frames/s", "samples": 2,
+                                      "capture_s": round(t_build, 1), "kernels_in_graph": int(list(model.__dict__["_loop_graphs"].values())[0][4]),
+                                      "how": "ddim_sample_loop(..., loop_graph=True): 50 steps x (CFG-batched UNet + fused CFG/DDIM update) in one graph"}
+                model.__dict__["_loop_graphs"] = {}
+                torch.cuda.empty_cache()
+            except Exception as e:  # noqa: BLE001
+                line["loop_graph"] = {"error": repr(e)}
             # ---- the reference's own CUDA path on this GPU (bounded sample), then the CPU baseline
             try:
                 rc = reference_cuda_leg(kind, hw, dev, model.state_dict())

@@ -253,3 +253,25 @@ def test_reference_sampler_drives_our_module():
     # the two update arithmetics differ in the last fp32 bits; through 10 chained UNet calls with guidance 9 that is
     # amplified to the fp16 noise floor of the network (same bound as test_sampler_with_unet_pair_equals_two_call_loop)
     assert rel < 3e-2
+
+
+def test_whole_sample_loop_as_one_cuda_graph():
+    """the 10-step guided loop captured as ONE CUDA graph equals the step-by-step loop bit for bit
+    (same kernels, same order) and replays with new noise."""
+    from videomv_b200.sampler import DiffusionDDIM
+    meta, d, _ = load_case("t2v_small_t981_cam")
+    model, _ = build(meta, meta["seed_w"])
+    g = torch.Generator().manual_seed(3)
+    noise = torch.randn(1, 4, 24, 8, 8, generator=g).cuda()
+    kw_c = dict(y=d["y"].cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
+    kw_u = dict(y=torch.randn(d["y"].shape, generator=g).cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
+    s = DiffusionDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.0120))
+    a = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10)
+    b = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)
+    c = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)   # replay
+    assert torch.equal(a, b) and torch.equal(b, c)
+    n2 = noise * 0.5
+    a2 = s.ddim_sample_loop(n2, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10)
+    c2 = s.ddim_sample_loop(n2, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)
+    assert torch.equal(a2, c2)
+    assert len(model.__dict__["_loop_graphs"]) == 1

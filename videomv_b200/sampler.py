@@ -10,6 +10,7 @@ which is arithmetically identical per sample and halves weight traffic and launc
 """
 from __future__ import annotations
 
+import os
 from typing import Dict, List, Optional
 
 import torch
@@ -70,8 +71,9 @@ class DiffusionDDIM:
     @torch.no_grad()
     def ddim_sample_loop(self, noise, model, autoencoder=None, model_kwargs=None, clamp=None, percentile=None,
                          condition_fn=None, guide_scale=None, ddim_timesteps: int = 20, eta: float = 0.0,
-                         batch_cfg: bool = True):
-        """Same call as diffusion_ddim.py:247 (first / plain pass: autoencoder=None)."""
+                         batch_cfg: bool = True, loop_graph: bool = False):
+        """Same call as diffusion_ddim.py:247 (first / plain pass: autoencoder=None).  loop_graph=True (or VMV_LOOP_GRAPH=1)
+        with one of this repo's UNets: the whole guided loop is captured once as ONE CUDA graph and replayed."""
         if autoencoder is not None or condition_fn is not None or clamp is not None or percentile is not None:
             raise NotImplementedError("videomv_b200.sampler: LGM refine pass / classifier guidance / clamping are "
                                       "outside the accelerated path (SURVEY.md section 8f)")
@@ -91,6 +93,8 @@ class DiffusionDDIM:
         coef = self.step_coefficients(ddim_timesteps, gs).to(dev)
         t_all = steps.to(device=dev, dtype=torch.long)
         pair = getattr(model, "forward_cfg_pair", None) if (batch_cfg and guide_scale is not None) else None
+        if pair is not None and (loop_graph or os.environ.get("VMV_LOOP_GRAPH", "0") == "1") and hasattr(model, "cfg_sample_loop_graph"):
+            return model.cfg_sample_loop_graph(xt, t_all, coef, kw_c, kw_u)
         tables = dict(sqrt_alphas_cumprod=self.sqrt_alphas_cumprod,
                       sqrt_one_minus_alphas_cumprod=self.sqrt_one_minus_alphas_cumprod,
                       sqrt_recip_alphas_cumprod=self.sqrt_recip_alphas_cumprod,

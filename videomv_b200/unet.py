@@ -237,6 +237,7 @@ class _VideoUNetBase(nn.Module):
         """Drop packed weights / captured graphs (called automatically after load_state_dict and .to())."""
         self.__dict__["_eng"] = None
         self.__dict__["_pair_cache"] = {}
+        self.__dict__["_loop_graphs"] = {}
 
     def _apply(self, fn, *a, **k):
         self.invalidate_engine()
@@ -263,6 +264,7 @@ class _VideoUNetBase(nn.Module):
         eng.shard = parallel.ShardCtx(group, device=eng.device, exchange=exchange, cfg_split=cfg_split) if enable else None
         eng._graphs.clear()
         self.__dict__["_pair_cache"] = {}
+        self.__dict__["_loop_graphs"] = {}
         return self
 
     def graph_launches(self) -> int:
@@ -270,11 +272,8 @@ class _VideoUNetBase(nn.Module):
         eng = self.__dict__.get("_eng")
         return 0 if eng is None else sum(g.launches for g in eng._graphs.values())
 
-    @torch.no_grad()
-    def forward_cfg_pair(self, x, t, kw_cond, kw_uncond):
-        """Classifier-free-guidance pair (diffusion_ddim.py:149-155) as ONE batch-2B evaluation: rows [0,B) use the
-        conditional kwargs, rows [B,2B) the unconditional ones. Per-sample arithmetic is unchanged (all norms and
-        attentions are per sample). Returns (y_out, u_out) fp32."""
+    def _pair_condition(self, x, kw_cond, kw_uncond):
+        """Step-invariant inputs of a CFG pair, cached per (kwargs tensors, latent shape): (kv, cam, fps, concat, split)."""
         eng = self._engine()
         b = x.shape[0]
         key = tuple((k, id(v), v.data_ptr(), v._version, tuple(v.shape)) for kw in (kw_cond, kw_uncond)
@@ -306,8 +305,19 @@ class _VideoUNetBase(nn.Module):
                    (y2, img2, loc2, held))
             if len(cache) >= 4:
                 cache.clear()
+                self.__dict__["_loop_graphs"] = {}
             cache[key] = hit
         kv, cam2, fps2, concat, _ = hit
+        return kv, cam2, fps2, concat, split, key
+
+    @torch.no_grad()
+    def forward_cfg_pair(self, x, t, kw_cond, kw_uncond):
+        """Classifier-free-guidance pair (diffusion_ddim.py:149-155) as ONE batch-2B evaluation: rows [0,B) use the
+        conditional kwargs, rows [B,2B) the unconditional ones. Per-sample arithmetic is unchanged (all norms and
+        attentions are per sample). Returns (y_out, u_out) fp32."""
+        eng = self._engine()
+        b = x.shape[0]
+        kv, cam2, fps2, concat, split, _ = self._pair_condition(x, kw_cond, kw_uncond)
         if split:
             out = eng.forward_core(x.to(device=eng.device, dtype=torch.float32).contiguous(),
                                    t.to(device=eng.device, dtype=torch.int64).contiguous(), kv, cam2, fps2, concat)
@@ -318,6 +328,58 @@ class _VideoUNetBase(nn.Module):
         if eng.shard is not None:
             out = out[0]
         return out[:b].contiguous(), out[b:].contiguous()
+
+    @torch.no_grad()
+    def cfg_sample_loop_graph(self, noise, t_all, coef, kw_cond, kw_uncond):
+        """The WHOLE guided DDIM loop (diffusion_ddim.py:247-260: len(t_all) steps of [CFG pair -> fused guidance + DDIM
+        update]) captured as ONE CUDA graph and replayed: no per-step host work at all.
+        noise [b,C,F,h,w] fp32; t_all int64 [steps] (device); coef fp32 [steps,7] (sampler.step_coefficients).
+        The graph is cached per (conditioning tensors, latent shape, step count); a replay costs one memcpy of the noise."""
+        from . import ops
+        eng = self._engine()
+        b = noise.shape[0]
+        kv, cam2, fps2, concat, split, ckey = self._pair_condition(noise, kw_cond, kw_uncond)
+        graphs = self.__dict__.setdefault("_loop_graphs", {})
+        key = (ckey, int(t_all.numel()))
+        g = graphs.get(key)
+        if g is None:
+            kv_all, L = kv
+            st_x = noise.detach().to(device=eng.device, dtype=torch.float32).contiguous().clone()
+            st_t = t_all.to(device=eng.device, dtype=torch.int64).contiguous().clone()
+            st_c = coef.to(device=eng.device, dtype=torch.float32).contiguous().clone()
+
+            def one_step(xt, i):
+                t = st_t[i].expand(b)
+                if split:
+                    out = eng._forward_impl(xt, t.contiguous(), kv_all, cam2, fps2, concat, L)
+                    y_out, u_out = out[0], out[1]
+                else:
+                    out = eng._forward_impl(torch.cat([xt, xt], 0), torch.cat([t, t], 0), kv_all, cam2, fps2, concat, L)
+                    if eng.shard is not None:
+                        out = out[0]
+                    y_out, u_out = out[:b], out[b:]
+                return ops.cfg_ddim_step(xt, y_out.contiguous(), u_out.contiguous(), st_c[i])
+
+            cur = torch.cuda.current_stream()
+            side = torch.cuda.Stream()
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                for _ in range(2):                     # warm up (function attributes, workspaces, allocator)
+                    one_step(st_x, 0)
+            cur.wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            n0 = ops.launch_count()
+            with torch.cuda.graph(graph):
+                xt = st_x
+                for i in range(int(st_t.numel())):
+                    xt = one_step(xt, i)
+            g = graphs[key] = (graph, st_x, st_c, xt, ops.launch_count() - n0)
+        graph, st_x, st_c, out, _ = g
+        st_x.copy_(noise, non_blocking=True)
+        st_c.copy_(coef, non_blocking=True)
+        graph.replay()
+        return out.clone()
 
     def _check_call(self, x, masked, autoencoder, x0):
         assert self.inpainting or masked is None, "inpainting is not supported"
