@@ -348,13 +348,19 @@ class _VideoUNetBase(nn.Module):
             st_t = t_all.to(device=eng.device, dtype=torch.int64).contiguous().clone()
             st_c = coef.to(device=eng.device, dtype=torch.float32).contiguous().clone()
 
+            nb2 = b if split else 2 * b
+            # the UNet inputs of every step live in two persistent buffers (like the static inputs of the per-step graphs)
+            st_x2 = torch.empty((nb2,) + tuple(st_x.shape[1:]), dtype=torch.float32, device=eng.device)
+            st_t2 = torch.empty((nb2,), dtype=torch.int64, device=eng.device)
+
             def one_step(xt, i):
-                t = st_t[i].expand(b)
+                for h in range(nb2 // b):
+                    st_x2[h * b:(h + 1) * b].copy_(xt)
+                st_t2.copy_(st_t[i].expand(nb2))
+                out = eng._forward_impl(st_x2, st_t2, kv_all, cam2, fps2, concat, L)
                 if split:
-                    out = eng._forward_impl(xt, t.contiguous(), kv_all, cam2, fps2, concat, L)
                     y_out, u_out = out[0], out[1]
                 else:
-                    out = eng._forward_impl(torch.cat([xt, xt], 0), torch.cat([t, t], 0), kv_all, cam2, fps2, concat, L)
                     if eng.shard is not None:
                         out = out[0]
                     y_out, u_out = out[:b], out[b:]
