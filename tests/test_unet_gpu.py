@@ -256,11 +256,8 @@ def test_reference_sampler_drives_our_module():
 
 
 def test_whole_sample_loop_as_one_cuda_graph():
-    """the 10-step guided loop captured as ONE CUDA graph reproduces the step-by-step loop and
-    replays with new noise.  KNOWN ISSUE: unlike eager runs and the per-step graphs (bit-identical, asserted elsewhere), replays
-    of the whole-loop graph agree only to the fp16 noise floor on this reduced-width model (first replay == eager bit for bit,
-    later replays drift by ~2.7e-3 per UNet call; independent of programmatic dependent launch) -- cause not found yet, so the
-    mode stays opt-in and the bound here is the chained-call bound of test_sampler_with_unet_pair_equals_two_call_loop."""
+    """the 10-step guided loop captured as ONE CUDA graph equals the step-by-step loop bit for
+    bit (same kernels, same order) on every replay, also with new noise and after unrelated allocations in between."""
     from videomv_b200.sampler import DiffusionDDIM
     meta, d, _ = load_case("t2v_small_t981_cam")
     model, _ = build(meta, meta["seed_w"])
@@ -270,12 +267,13 @@ def test_whole_sample_loop_as_one_cuda_graph():
     kw_u = dict(y=torch.randn(d["y"].shape, generator=g).cuda(), camera_data=d["cam"], fps=d["fps"].cuda())
     s = DiffusionDDIM(schedule="linear_sd", schedule_param=dict(num_timesteps=1000, init_beta=0.00085, last_beta=0.0120))
     a = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10)
-    b = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)
-    c = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)   # replay
-    assert torch.equal(a, b)
-    assert metrics("whole-loop graph replay vs step loop", c, a)[0] < 3e-2
+    keep = []
+    for _ in range(6):                                # replays, with allocator churn in between (the graph owns all it reads)
+        keep.append(torch.randn(1 << 16, device="cuda"))
+        r = s.ddim_sample_loop(noise, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)
+        assert torch.equal(a, r)
     n2 = noise * 0.5
     a2 = s.ddim_sample_loop(n2, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10)
     c2 = s.ddim_sample_loop(n2, model, model_kwargs=[kw_c, kw_u], guide_scale=9.0, ddim_timesteps=10, loop_graph=True)
-    assert metrics("whole-loop graph replay (new noise) vs step loop", c2, a2)[0] < 3e-2
+    assert torch.equal(a2, c2)
     assert len(model.__dict__["_loop_graphs"]) == 1

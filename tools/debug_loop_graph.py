@@ -26,8 +26,9 @@ def main():
     pg = [run() for _ in range(4)]
     print("per-step graphs equal eager:", [bool(torch.equal(eager[0], e)) for e in pg])
     model.enable_cuda_graphs(False)
-    lg = [run(loop_graph=True) for _ in range(6)]
+    lg = [run(loop_graph=True) for _ in range(8)]
     print("loop graph replays equal eager:", [bool(torch.equal(eager[0], e)) for e in lg])
+    print("loop graph replays equal replay 1:", [bool(torch.equal(lg[0], e)) for e in lg])
     print("loop graph replays equal replay 2:", [bool(torch.equal(lg[1], e)) for e in lg])
     print("rel diff replay1 vs replay2:", float((lg[0] - lg[1]).norm() / lg[0].norm()))
 

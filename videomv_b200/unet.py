@@ -380,8 +380,9 @@ class _VideoUNetBase(nn.Module):
                 xt = st_x
                 for i in range(int(st_t.numel())):
                     xt = one_step(xt, i)
-            g = graphs[key] = (graph, st_x, st_c, xt, ops.launch_count() - n0)
-        graph, st_x, st_c, out, _ = g
+            # every tensor the graph reads must outlive it: the timestep table and the UNet input buffers too
+            g = graphs[key] = (graph, st_x, st_c, xt, ops.launch_count() - n0, (st_t, st_x2, st_t2, kv_all, cam2, fps2, concat))
+        graph, st_x, st_c, out = g[:4]
         st_x.copy_(noise, non_blocking=True)
         st_c.copy_(coef, non_blocking=True)
         graph.replay()
