@@ -87,3 +87,47 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "oracle" not in src.replace("no oracle", ""), fn
+
+
+@pytest.mark.parametrize("ci,co", [(8, 6), (64, 16)])
+def test_upsample_conv_phase_weights_reproduce_interpolate_then_conv(ci, co):
+    """packing.pack_upconv3x3 (host logic of the UPCONV3X3 GEMM mode): four 2x2 phase convs with pre-summed taps on the
+    original image == F.interpolate(scale 2, nearest) followed by Conv2d 3x3 pad 1 (util.py:604-606), here in fp64 on the CPU."""
+    import torch.nn.functional as F
+    from videomv_b200 import packing
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(co, ci, 3, 3, generator=g, dtype=torch.float64)
+    x = torch.randn(2, ci, 5, 7, generator=g, dtype=torch.float64)
+    ref = F.conv2d(F.interpolate(x, scale_factor=2.0, mode="nearest"), w, padding=1)
+    # the packed matrix in fp64 (pack_upconv3x3 rounds to fp16: redo its summation without the final cast)
+    wp = packing.pack_upconv3x3(w.float()).double().reshape(4, co, 2, 2, ci)
+    exact = torch.empty_like(wp)
+    groups = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    for py in (0, 1):
+        for px in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    exact[2 * py + px, :, ty, tx] = sum(w[:, :, ky, kx] for ky in groups[py][ty] for kx in groups[px][tx])
+    assert torch.allclose(wp, exact, rtol=2e-3, atol=2e-3)          # fp16 rounding of the packed weights only
+    out = torch.zeros_like(ref)
+    xp = F.pad(x, (1, 1, 1, 1))
+    for py in (0, 1):
+        for px in (0, 1):
+            acc = torch.zeros(2, co, 5, 7, dtype=torch.float64)
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    dy, dx = ty - 1 + py, tx - 1 + px                 # input offset of this tap
+                    patch = xp[:, :, 1 + dy:1 + dy + 5, 1 + dx:1 + dx + 7]
+                    acc += torch.einsum("bchw,oc->bohw", patch, exact[2 * py + px, :, ty, tx])
+            out[:, :, py::2, px::2] = acc
+    assert torch.allclose(out, ref, rtol=1e-12, atol=1e-12)
+
+
+def test_staged_reference_files_are_verbatim_copies():
+    """oracle/stage_ref.py (baseline arms on the GPU box): the staged files are byte-identical to the reference tree."""
+    from oracle import stage_ref
+    if not os.path.isfile(os.path.join(stage_ref.SRC, stage_ref.FILES[0])):
+        pytest.skip("reference tree not present")
+    assert stage_ref.stage()
+    for rel in stage_ref.FILES:
+        assert open(os.path.join(stage_ref.SRC, rel), "rb").read() == open(os.path.join(stage_ref.DST, rel), "rb").read(), rel
